@@ -1,0 +1,518 @@
+// Block bodies of the element kernels (rows G2-G11, O1-O4, P1 of SURVEY.md §8a).
+//
+// Layout of one CTA: EPB elements x TPE threads per element (TPE = ndof for vector problems, nPe for scalar).
+// Shared memory: the reference-element tables of the group once per CTA, then per element the nodal
+// coordinates, F / F^-1 / det / wJ at every Gauss point and the physical shape-function gradients
+// gN[p][a][d] = dN_a/dx_d.  B (Kelvin-Mandel, _group_elem.py:1241-1312) is never materialised: every B column has
+// `dim` non-zeros, which the contractions below spell out.
+#pragma once
+#include "frame.cuh"
+
+namespace efb {
+
+struct GroupView {
+    int nPg;
+    int coord_stride;
+    long long Ne;
+    const int* connect;
+    const double* coord;
+    const double* dN_pg;
+    const double* N_pg;
+    const double* w_pg;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// shared-memory map (offsets in doubles)
+// ---------------------------------------------------------------------------------------------------------
+template <int DIM, int NPE>
+struct SmemMap {
+    int nPg, EPB, extra;  // extra = op-specific doubles per element
+    EFB_HD SmemMap(int nPg_, int EPB_, int extra_) : nPg(nPg_), EPB(EPB_), extra(extra_) {}
+    // tables
+    EFB_HD int off_dN() const { return 0; }
+    EFB_HD int off_N() const { return nPg * DIM * NPE; }
+    EFB_HD int off_w() const { return off_N() + nPg * NPE; }
+    EFB_HD int tables() const { return off_w() + nPg; }
+    // per element
+    EFB_HD int o_X() const { return 0; }
+    EFB_HD int o_F() const { return NPE * DIM; }
+    EFB_HD int o_Fi() const { return o_F() + nPg * DIM * DIM; }
+    EFB_HD int o_det() const { return o_Fi() + nPg * DIM * DIM; }
+    EFB_HD int o_wJ() const { return o_det() + nPg; }
+    EFB_HD int o_gN() const { return o_wJ() + nPg; }
+    EFB_HD int o_extra() const { return o_gN() + nPg * NPE * DIM; }
+    // odd stride (in doubles) so the same field of neighbouring elements falls in different banks
+    EFB_HD int per_elem() const { return (o_extra() + extra) | 1; }
+    EFB_HD int total() const { return tables() + EPB * per_elem(); }
+    EFB_HD double* elem(double* smem, int el) const { return smem + tables() + el * per_elem(); }
+};
+
+// closed-form det / inverse with the reference's association of products, EasyFEA/FEM/_linalg.py:533-656
+template <int DIM>
+EFB_HD double det_inv(const double* F, double* Fi);
+
+template <>
+EFB_HD double det_inv<2>(const double* F, double* Fi) {
+    const double a = F[0], b = F[1], c = F[2], d = F[3];
+    const double det = (a * d) - (c * b);
+    const double r = 1.0 / det;
+    Fi[0] = r * d;
+    Fi[1] = r * (-b);
+    Fi[2] = r * (-c);
+    Fi[3] = r * a;
+    return det;
+}
+
+template <>
+EFB_HD double det_inv<3>(const double* F, double* Fi) {
+    const double a11 = F[0], a12 = F[1], a13 = F[2];
+    const double a21 = F[3], a22 = F[4], a23 = F[5];
+    const double a31 = F[6], a32 = F[7], a33 = F[8];
+    const double det = a11 * ((a22 * a33) - (a32 * a23)) - a12 * ((a21 * a33) - (a31 * a23)) +
+                       a13 * ((a21 * a32) - (a31 * a22));
+    const double r = 1.0 / det;
+    // adjugate (transposed cofactors)
+    Fi[0] = r * ((a22 * a33) - (a23 * a32));
+    Fi[1] = r * (-((a12 * a33) - (a13 * a32)));
+    Fi[2] = r * ((a12 * a23) - (a13 * a22));
+    Fi[3] = r * (-((a21 * a33) - (a23 * a31)));
+    Fi[4] = r * ((a11 * a33) - (a13 * a31));
+    Fi[5] = r * (-((a11 * a23) - (a13 * a21)));
+    Fi[6] = r * ((a21 * a32) - (a22 * a31));
+    Fi[7] = r * (-((a11 * a32) - (a12 * a31)));
+    Fi[8] = r * ((a11 * a22) - (a12 * a21));
+    return det;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// G2-G6: tables + coordinates -> F, det, wJ, F^-1, gN for the EPB elements of this CTA (4 phases)
+// ---------------------------------------------------------------------------------------------------------
+template <int DIM, int NPE>
+EFB_D void geometry_phases(const GroupView& g, const SmemMap<DIM, NPE>& sm, long long e0, int TPE, int nthreads,
+                           double* smem, bool need_grad) {
+    const int nPg = g.nPg;
+    double* dNt = smem + sm.off_dN();
+    double* Nt = smem + sm.off_N();
+    double* wt = smem + sm.off_w();
+
+    EFB_PHASE(tid, nthreads) {
+        for (int i = tid; i < nPg * DIM * NPE; i += nthreads) dNt[i] = g.dN_pg[i];
+        for (int i = tid; i < nPg * NPE; i += nthreads) Nt[i] = g.N_pg[i];
+        for (int i = tid; i < nPg; i += nthreads) wt[i] = g.w_pg[i];
+        const int el = tid / TPE, t = tid % TPE;
+        const long long e = e0 + el;
+        if (el < sm.EPB && e < g.Ne) {
+            double* X = sm.elem(smem, el) + sm.o_X();
+            for (int i = t; i < NPE * DIM; i += TPE) {
+                const int a = i / DIM, d = i % DIM;
+                X[i] = g.coord[(long long)g.connect[e * NPE + a] * g.coord_stride + d];
+            }
+        }
+    }
+    EFB_PHASE(tid, nthreads) {  // F[p][r][c] = sum_n dN[p][r][n] x[n][c]                 _group_elem.py:864-867
+        const int el = tid / TPE, t = tid % TPE;
+        if (el < sm.EPB && e0 + el < g.Ne) {
+            double* E = sm.elem(smem, el);
+            const double* X = E + sm.o_X();
+            double* F = E + sm.o_F();
+            for (int i = t; i < nPg * DIM * DIM; i += TPE) {
+                const int pr = i / DIM, c = i % DIM;
+                const double* row = dNt + pr * NPE;
+                double s = 0.0;
+                EFB_UNROLL
+                for (int n = 0; n < NPE; ++n) s += row[n] * X[n * DIM + c];
+                F[i] = s;
+            }
+        }
+    }
+    EFB_PHASE(tid, nthreads) {  // det, |det| w, inverse                                    :871-915
+        const int el = tid / TPE, t = tid % TPE;
+        if (el < sm.EPB && e0 + el < g.Ne) {
+            double* E = sm.elem(smem, el);
+            for (int p = t; p < nPg; p += TPE) {
+                const double det = det_inv<DIM>(E + sm.o_F() + p * DIM * DIM, E + sm.o_Fi() + p * DIM * DIM);
+                E[sm.o_det() + p] = det;
+                E[sm.o_wJ() + p] = fabs(det) * wt[p];
+            }
+        }
+    }
+    if (need_grad) {
+        EFB_PHASE(tid, nthreads) {  // gN[p][a][d] = sum_k Fi[p][d][k] dN[p][k][a]        :1083-1105
+            const int el = tid / TPE, t = tid % TPE;
+            if (el < sm.EPB && e0 + el < g.Ne) {
+                double* E = sm.elem(smem, el);
+                const double* Fi = E + sm.o_Fi();
+                double* gN = E + sm.o_gN();
+                for (int i = t; i < nPg * NPE * DIM; i += TPE) {
+                    const int p = i / (NPE * DIM), a = (i / DIM) % NPE, d = i % DIM;
+                    double s = 0.0;
+                    EFB_UNROLL
+                    for (int k = 0; k < DIM; ++k) s += Fi[(p * DIM + d) * DIM + k] * dNt[(p * DIM + k) * NPE + a];
+                    gN[i] = s;
+                }
+            }
+        }
+    }
+}
+
+// entry B[s][(a,d)] of the Kelvin-Mandel strain operator from the gradient (gx,gy,gz) of node a
+template <int DIM>
+EFB_HD double B_entry(int s, int d, const double* g) {
+    if constexpr (DIM == 2) {
+        if (s == 0) return d == 0 ? g[0] : 0.0;
+        if (s == 1) return d == 1 ? g[1] : 0.0;
+        return kInvSqrt2 * g[1 - d];
+    } else {
+        if (s < 3) return d == s ? g[s] : 0.0;
+        if (s == 3) return d == 0 ? 0.0 : kInvSqrt2 * g[d == 1 ? 2 : 1];  // yz
+        if (s == 4) return d == 1 ? 0.0 : kInvSqrt2 * g[d == 0 ? 2 : 0];  // xz
+        return d == 2 ? 0.0 : kInvSqrt2 * g[d == 0 ? 1 : 0];              // xy
+    }
+}
+
+// coefficient with the broadcast modes of FeArray.broadcast
+EFB_HD double coef_at(const double* c, int mode, double scalar, long long e, int p, int nPg) {
+    if (c == nullptr || mode == 0) return c ? c[0] : scalar;
+    if (mode == 1) return c[e];
+    if (mode == 2) return c[p];
+    return c[e * nPg + p];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// G2-G8 export                                                        _group_elem.py:832-1312
+// ---------------------------------------------------------------------------------------------------------
+struct GeomOut {
+    double *F, *detF, *jac, *wJ, *invF, *dN, *B;
+};
+
+template <int DIM, int NPE>
+EFB_D void geometry_block(const GroupView& g, const GeomOut& o, int EPB, long long blockId, int nthreads, double* smem) {
+    constexpr int NS = StrainSize<DIM>::value, NDOF = DIM * NPE;
+    const int TPE = nthreads / EPB;
+    const SmemMap<DIM, NPE> sm(g.nPg, EPB, 0);
+    const long long e0 = blockId * EPB;
+    const int nPg = g.nPg;
+    geometry_phases<DIM, NPE>(g, sm, e0, TPE, nthreads, smem, true);
+    EFB_PHASE(tid, nthreads) {
+        const int el = tid / TPE, t = tid % TPE;
+        const long long e = e0 + el;
+        if (el < EPB && e < g.Ne) {
+            const double* E = sm.elem(smem, el);
+            for (int i = t; i < nPg * DIM * DIM; i += TPE) {
+                if (o.F) o.F[e * nPg * DIM * DIM + i] = E[sm.o_F() + i];
+                if (o.invF) o.invF[e * nPg * DIM * DIM + i] = E[sm.o_Fi() + i];
+            }
+            for (int p = t; p < nPg; p += TPE) {
+                if (o.detF) o.detF[e * nPg + p] = E[sm.o_det() + p];
+                if (o.jac) o.jac[e * nPg + p] = fabs(E[sm.o_det() + p]);
+                if (o.wJ) o.wJ[e * nPg + p] = E[sm.o_wJ() + p];
+            }
+            const double* gN = E + sm.o_gN();
+            if (o.dN) {
+                for (int i = t; i < nPg * DIM * NPE; i += TPE) {  // output layout (p, d, a)
+                    const int p = i / (DIM * NPE), d = (i / NPE) % DIM, a = i % NPE;
+                    o.dN[e * nPg * DIM * NPE + i] = gN[(p * NPE + a) * DIM + d];
+                }
+            }
+            if (o.B) {
+                for (int i = t; i < nPg * NS * NDOF; i += TPE) {  // (p, s, a*DIM+d)
+                    const int p = i / (NS * NDOF), s = (i / NDOF) % NS, col = i % NDOF;
+                    o.B[e * (long long)(nPg * NS * NDOF) + i] = B_entry<DIM>(s, col % DIM, gN + (p * NPE + col / DIM) * DIM);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// O1: K_e = scale * sum_p wJ B^T C B                                   Operators/Bilinear.py:62-79
+// thread (element, column j): cb = wJ C B[:,j] (dim non-zeros per B column), then one FMA triple per row
+// ---------------------------------------------------------------------------------------------------------
+template <int DIM, int NPE>
+EFB_D void elastic_block(const GroupView& g, const double* EFB_RESTRICT C, int C_mode, double scale,
+                         double* EFB_RESTRICT out, int EPB, long long blockId, int nthreads, double* smem) {
+    constexpr int NS = StrainSize<DIM>::value, NDOF = DIM * NPE, NC = NS * NS;
+    const int nPg = g.nPg;
+    const int extra = C_mode == 2 ? nPg * NC : NC;
+    const SmemMap<DIM, NPE> sm(nPg, EPB, extra);
+    const long long e0 = blockId * EPB;
+    geometry_phases<DIM, NPE>(g, sm, e0, NDOF, nthreads, smem, true);
+    EFB_PHASE(tid, nthreads) {  // stage C (contiguous over the elements of the CTA)
+        const int el = tid / NDOF, t = tid % NDOF;
+        const long long e = e0 + el;
+        if (el < EPB && e < g.Ne) {
+            double* Cs = sm.elem(smem, el) + sm.o_extra();
+            const double* src = C_mode == 0 ? C : (C_mode == 1 ? C + e * NC : C + e * (long long)(nPg * NC));
+            for (int i = t; i < extra; i += NDOF) Cs[i] = src[i];
+        }
+    }
+    EFB_PHASE(tid, nthreads) {
+        const int el = tid / NDOF, j = tid % NDOF;
+        const long long e = e0 + el;
+        if (el < EPB && e < g.Ne) {
+            const double* E = sm.elem(smem, el);
+            const double* wJ = E + sm.o_wJ();
+            const double* gN = E + sm.o_gN();
+            const double* Cs = E + sm.o_extra();
+            const int b = j / DIM, jd = j % DIM;
+            double acc[NDOF];
+            EFB_UNROLL
+            for (int i = 0; i < NDOF; ++i) acc[i] = 0.0;
+            for (int p = 0; p < nPg; ++p) {
+                const double* Cp = Cs + (C_mode == 2 ? p * NC : 0);
+                const double* gp = gN + p * NPE * DIM;
+                const double* gb = gp + b * DIM;
+                const double w = wJ[p];
+                double cb[NS];
+                if constexpr (DIM == 2) {
+                    // column (b, jd): B[jd] = g[jd], B[2] = c g[1-jd]
+                    const double b0 = gb[jd], b1 = kInvSqrt2 * gb[1 - jd];
+                    EFB_UNROLL
+                    for (int s = 0; s < NS; ++s) cb[s] = w * (Cp[s * NS + jd] * b0 + Cp[s * NS + 2] * b1);
+                    cb[2] *= kInvSqrt2;
+                    EFB_UNROLL
+                    for (int a = 0; a < NPE; ++a) {
+                        const double gx = gp[a * 2], gy = gp[a * 2 + 1];
+                        acc[a * 2 + 0] += gx * cb[0] + gy * cb[2];
+                        acc[a * 2 + 1] += gy * cb[1] + gx * cb[2];
+                    }
+                } else {
+                    // column (b, jd): jd=0 -> rows (0,4,5) = (gx, c gz, c gy); jd=1 -> (1,3,5) = (gy, c gz, c gx);
+                    //                 jd=2 -> (2,3,4) = (gz, c gy, c gx)
+                    const int r1 = jd == 0 ? 4 : 3, r2 = jd == 2 ? 4 : 5;
+                    const double b0 = gb[jd];
+                    const double b1 = kInvSqrt2 * gb[jd == 2 ? 1 : 2];
+                    const double b2 = kInvSqrt2 * gb[jd == 0 ? 1 : 0];
+                    EFB_UNROLL
+                    for (int s = 0; s < NS; ++s)
+                        cb[s] = w * (Cp[s * NS + jd] * b0 + Cp[s * NS + r1] * b1 + Cp[s * NS + r2] * b2);
+                    cb[3] *= kInvSqrt2;
+                    cb[4] *= kInvSqrt2;
+                    cb[5] *= kInvSqrt2;
+                    EFB_UNROLL
+                    for (int a = 0; a < NPE; ++a) {
+                        const double gx = gp[a * 3], gy = gp[a * 3 + 1], gz = gp[a * 3 + 2];
+                        acc[a * 3 + 0] += gx * cb[0] + gz * cb[4] + gy * cb[5];
+                        acc[a * 3 + 1] += gy * cb[1] + gz * cb[3] + gx * cb[5];
+                        acc[a * 3 + 2] += gz * cb[2] + gy * cb[3] + gx * cb[4];
+                    }
+                }
+            }
+            double* dst = out + e * (long long)(NDOF * NDOF) + j;
+            EFB_UNROLL
+            for (int i = 0; i < NDOF; ++i) dst[i * NDOF] = scale * acc[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// O2: M_e = scale * sum_p coef wJ N^T N (block-diagonal N for dof_n > 1)   Bilinear.py:42-59
+// O3: K_e = scale * sum_p coef wJ dN^T A dN                                 Bilinear.py:25-39, 229-249
+// S4: K_e = scale * sum_p wJ (r N^T N + k dN^T A dN), F_e = scale * sum_p wJ f N   Simulations/_phasefield.py:540-573
+// one body: thread (element, node b) accumulates column b of the scalar (nPe x nPe) matrix
+// ---------------------------------------------------------------------------------------------------------
+struct ScalarOp {
+    // reaction part
+    const double* r;  // coefficient array or nullptr
+    int r_mode;
+    double r_scalar;
+    bool has_r;
+    // diffusion part
+    const double* A;  // (dim,dim) with A_mode leading axes, nullptr = identity
+    int A_mode;
+    const double* k;
+    int k_mode;
+    double k_scalar;
+    bool has_k;
+    // source part (vector output)
+    const double* f;
+    int f_mode;
+    double f_scalar;
+    bool has_f;
+    int dof_n;  // block expansion of the outputs
+    double scale;
+    double* Ke;  // (Ne, nPe*dof_n, nPe*dof_n) or nullptr
+    double* Fe;  // (Ne, nPe*dof_n, dof_n) if f_keep_axis else (Ne, nPe*dof_n)
+    bool f_keep_axis;
+};
+
+template <int DIM, int NPE>
+EFB_D void scalar_block(const GroupView& g, const ScalarOp& op, int EPB, long long blockId, int nthreads, double* smem) {
+    const int nPg = g.nPg;
+    const SmemMap<DIM, NPE> sm(nPg, EPB, NPE * NPE + NPE);
+    const long long e0 = blockId * EPB;
+    const double* Nt = smem + sm.off_N();
+    geometry_phases<DIM, NPE>(g, sm, e0, NPE, nthreads, smem, op.has_k);
+    EFB_PHASE(tid, nthreads) {
+        const int el = tid / NPE, b = tid % NPE;
+        const long long e = e0 + el;
+        if (el < EPB && e < g.Ne) {
+            double* E = sm.elem(smem, el);
+            const double* wJ = E + sm.o_wJ();
+            const double* gN = E + sm.o_gN();
+            double* Ms = E + sm.o_extra();  // [a][b]
+            double* Fs = Ms + NPE * NPE;
+            double acc[NPE];
+            EFB_UNROLL
+            for (int a = 0; a < NPE; ++a) acc[a] = 0.0;
+            double fb = 0.0;
+            for (int p = 0; p < nPg; ++p) {
+                const double w = wJ[p];
+                const double* Np = Nt + p * NPE;
+                if (op.has_r) {
+                    const double c = coef_at(op.r, op.r_mode, op.r_scalar, e, p, nPg) * w * Np[b];
+                    EFB_UNROLL
+                    for (int a = 0; a < NPE; ++a) acc[a] += Np[a] * c;
+                }
+                if (op.has_k) {
+                    const double c = coef_at(op.k, op.k_mode, op.k_scalar, e, p, nPg) * w;
+                    const double* gb = gN + (p * NPE + b) * DIM;
+                    double Ag[DIM];
+                    if (op.A) {
+                        const double* Ap = op.A + (op.A_mode == 0 ? 0 : (op.A_mode == 1 ? e * DIM * DIM : (e * nPg + p) * (long long)(DIM * DIM)));
+                        EFB_UNROLL
+                        for (int i = 0; i < DIM; ++i) {
+                            double s = 0.0;
+                            EFB_UNROLL
+                            for (int kk = 0; kk < DIM; ++kk) s += Ap[i * DIM + kk] * gb[kk];
+                            Ag[i] = c * s;
+                        }
+                    } else {
+                        EFB_UNROLL
+                        for (int i = 0; i < DIM; ++i) Ag[i] = c * gb[i];
+                    }
+                    EFB_UNROLL
+                    for (int a = 0; a < NPE; ++a) {
+                        const double* ga = gN + (p * NPE + a) * DIM;
+                        double s = 0.0;
+                        EFB_UNROLL
+                        for (int i = 0; i < DIM; ++i) s += ga[i] * Ag[i];
+                        acc[a] += s;
+                    }
+                }
+                if (op.has_f) fb += coef_at(op.f, op.f_mode, op.f_scalar, e, p, nPg) * w * Np[b];
+            }
+            EFB_UNROLL
+            for (int a = 0; a < NPE; ++a) Ms[a * NPE + b] = op.scale * acc[a];
+            Fs[b] = op.scale * fb;
+        }
+    }
+    EFB_PHASE(tid, nthreads) {  // block-expanded, coalesced write-out
+        const int el = tid / NPE, t = tid % NPE;
+        const long long e = e0 + el;
+        if (el < EPB && e < g.Ne) {
+            const double* Ms = sm.elem(smem, el) + sm.o_extra();
+            const double* Fs = Ms + NPE * NPE;
+            const int dn = op.dof_n, ndof = NPE * dn;
+            if (op.Ke) {
+                double* dst = op.Ke + e * (long long)(ndof * ndof);
+                for (int i = t; i < ndof * ndof; i += NPE) {
+                    const int row = i / ndof, col = i % ndof;
+                    dst[i] = (row % dn == col % dn) ? Ms[(row / dn) * NPE + col / dn] : 0.0;
+                }
+            }
+            if (op.Fe) {
+                if (op.f_keep_axis) {
+                    double* dst = op.Fe + e * (long long)(ndof * dn);
+                    for (int i = t; i < ndof * dn; i += NPE) {
+                        const int row = i / dn, comp = i % dn;
+                        dst[i] = (row % dn == comp) ? Fs[row / dn] : 0.0;
+                    }
+                } else {
+                    double* dst = op.Fe + e * (long long)ndof;
+                    for (int i = t; i < ndof; i += NPE) dst[i] = Fs[i / dn];
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// P1: eps = B u_e                 Models/Elastic/_laws.py:127-157;  O4b: F_e = sum_p wJ B^T sigma   Linear.py:38-52
+// P7: g = (1 - N d_e)^2 + k_res   Models/_phasefield.py:295-317
+// ---------------------------------------------------------------------------------------------------------
+template <int DIM, int NPE>
+EFB_D void strain_block(const GroupView& g, const int* EFB_RESTRICT connect_dof, const double* EFB_RESTRICT u,
+                        double* EFB_RESTRICT eps, int EPB, long long blockId, int nthreads, double* smem) {
+    constexpr int NS = StrainSize<DIM>::value, NDOF = DIM * NPE;
+    const int nPg = g.nPg;
+    const SmemMap<DIM, NPE> sm(nPg, EPB, NDOF);
+    const long long e0 = blockId * EPB;
+    geometry_phases<DIM, NPE>(g, sm, e0, NDOF, nthreads, smem, true);
+    EFB_PHASE(tid, nthreads) {
+        const int el = tid / NDOF, t = tid % NDOF;
+        const long long e = e0 + el;
+        if (el < EPB && e < g.Ne) {
+            double* ue = sm.elem(smem, el) + sm.o_extra();
+            ue[t] = u[(long long)connect_dof[e * NPE + t / DIM] * DIM + t % DIM];
+        }
+    }
+    EFB_PHASE(tid, nthreads) {
+        const int el = tid / NDOF, t = tid % NDOF;
+        const long long e = e0 + el;
+        if (el < EPB && e < g.Ne) {
+            const double* E = sm.elem(smem, el);
+            const double* gN = E + sm.o_gN();
+            const double* ue = E + sm.o_extra();
+            for (int i = t; i < nPg * NS; i += NDOF) {
+                const int p = i / NS, s = i % NS;
+                double acc = 0.0;
+                for (int a = 0; a < NPE; ++a) {
+                    const double* ga = gN + (p * NPE + a) * DIM;
+                    EFB_UNROLL
+                    for (int d = 0; d < DIM; ++d) acc += B_entry<DIM>(s, d, ga) * ue[a * DIM + d];
+                }
+                eps[e * (long long)(nPg * NS) + i] = acc;
+            }
+        }
+    }
+}
+
+template <int DIM, int NPE>
+EFB_D void internal_force_block(const GroupView& g, const double* EFB_RESTRICT sigma, double* EFB_RESTRICT out, int EPB,
+                                long long blockId, int nthreads, double* smem) {
+    constexpr int NS = StrainSize<DIM>::value, NDOF = DIM * NPE;
+    const int nPg = g.nPg;
+    const SmemMap<DIM, NPE> sm(nPg, EPB, nPg * NS);
+    const long long e0 = blockId * EPB;
+    geometry_phases<DIM, NPE>(g, sm, e0, NDOF, nthreads, smem, true);
+    EFB_PHASE(tid, nthreads) {
+        const int el = tid / NDOF, t = tid % NDOF;
+        const long long e = e0 + el;
+        if (el < EPB && e < g.Ne) {
+            double* sg = sm.elem(smem, el) + sm.o_extra();
+            for (int i = t; i < nPg * NS; i += NDOF) sg[i] = sigma[e * (long long)(nPg * NS) + i];
+        }
+    }
+    EFB_PHASE(tid, nthreads) {
+        const int el = tid / NDOF, t = tid % NDOF;
+        const long long e = e0 + el;
+        if (el < EPB && e < g.Ne) {
+            const double* E = sm.elem(smem, el);
+            const double* gN = E + sm.o_gN();
+            const double* wJ = E + sm.o_wJ();
+            const double* sg = E + sm.o_extra();
+            const int a = t / DIM, d = t % DIM;
+            double acc = 0.0;
+            for (int p = 0; p < nPg; ++p) {
+                const double* ga = gN + (p * NPE + a) * DIM;
+                double s = 0.0;
+                EFB_UNROLL
+                for (int k = 0; k < NS; ++k) s += B_entry<DIM>(k, d, ga) * sg[p * NS + k];
+                acc += wJ[p] * s;
+            }
+            out[e * NDOF + t] = acc;
+        }
+    }
+}
+
+// no geometry needed: thread per (element, Gauss point)
+EFB_HD double degradation_at(const int* connect_dof, const double* d, const double* N_pg, long long e, int p, int nPe,
+                             double k_res) {
+    double s = 0.0;
+    for (int a = 0; a < nPe; ++a) s += N_pg[p * nPe + a] * d[connect_dof[e * nPe + a]];
+    const double om = 1.0 - s;
+    return om * om + k_res;
+}
+
+}  // namespace efb

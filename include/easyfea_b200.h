@@ -1,0 +1,194 @@
+/*
+ * easyfea_b200 — C ABI of the B200-native (sm_100a, FP64) element-integration + CSR-assembly path of EasyFEA.
+ *
+ * The reference (matnoel/EasyFEA v3.5.1) is pure Python: it has no FFI layer for this path.  The entry points
+ * below are what a ctypes binding inside the reference would call in place of its NumPy expressions; each one
+ * cites the reference function it replaces (paths relative to the reference root).  See INTEGRATION.md for the
+ * reference-side stub.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name ends in `_host`; all floating point is FP64;
+ *  - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream); calls are asynchronous;
+ *  - return value: 0 on success, non-zero on error (message via efb_last_error());
+ *  - arrays are C-contiguous with the shapes written beside them; element axis `Ne`, Gauss axis `nPg`,
+ *    Kelvin-Mandel strain size ns = 3 (dim 2) or 6 (dim 3), ndof = nPe*dof_n.
+ *  - no torch / numpy types cross this boundary.
+ */
+#ifndef EASYFEA_B200_H
+#define EASYFEA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ------------------------------------------------------------------------------------------ */
+const char* efb_last_error(void);
+int efb_version(void);
+/* number of CUDA devices visible, or -1 when the runtime cannot initialise (no GPU): never throws */
+int efb_device_count(void);
+
+/* One element group on the device: EasyFEA/FEM/_group_elem.py:41 (`_GroupElem`) reduced to what the path reads.
+ * Tables come from `Get_dN_pg/Get_N_pg/Get_weight_pg(matrixType)` (:1063, :990, :788). */
+typedef struct efb_group {
+    int32_t dim;           /* 2 or 3 */
+    int32_t nPe;           /* nodes per element */
+    int32_t nPg;           /* Gauss points of the matrixType in use */
+    int32_t coord_stride;  /* doubles per row of `coord` (3 in the reference) */
+    int64_t Ne;
+    const int32_t* connect; /* (Ne, nPe) rows of `coord` */
+    const double* coord;    /* (Nn, coord_stride) */
+    const double* dN_pg;    /* (nPg, dim, nPe) */
+    const double* N_pg;     /* (nPg, nPe) */
+    const double* w_pg;     /* (nPg) */
+} efb_group;
+
+/* broadcast modes of a coefficient, FeArray.broadcast EasyFEA/FEM/_linalg.py:426-476 */
+enum { EFB_COEF_SCALAR = 0, EFB_COEF_E = 1, EFB_COEF_PG = 2, EFB_COEF_E_PG = 3 };
+/* leading axes of a tensor coefficient (C, A): (), (Ne,), (Ne,nPg) */
+enum { EFB_TENSOR_CONST = 0, EFB_TENSOR_E = 1, EFB_TENSOR_E_PG = 2 };
+
+/* ---- G2-G8: Gauss-point geometry, _group_elem.py:832-1312 -------------------------------------------- */
+/* Any output pointer may be NULL.  F (Ne,nPg,dim,dim) Get_F_e_pg :832; detF (Ne,nPg) signed, jac = |detF|
+ * Get_jacobian_e_pg :871; wJ Get_weightedJacobian_e_pg :890; invF Get_invF_e_pg :902;
+ * dN (Ne,nPg,dim,nPe) Get_dN_e_pg :1083; B (Ne,nPg,ns,nPe*dim) Get_B_e_pg :1241. */
+int efb_geometry(const efb_group* g, double* F, double* detF, double* jac, double* wJ, double* invF, double* dN,
+                 double* B, void* stream);
+
+/* ---- O1-O4: operators, EasyFEA/FEM/Operators/Bilinear.py, Linear.py ---------------------------------- */
+/* LinearizedElasticity Bilinear.py:62-79: out (Ne,ndof,ndof) = scale * sum_p wJ B^T C B; C (ns,ns) with leading
+ * axes per C_mode. */
+int efb_elastic_Ke(const efb_group* g, const double* C, int C_mode, double scale, double* out, void* stream);
+/* UV Bilinear.py:42-59: out (Ne,ndof,ndof) = scale * sum_p coef wJ N^T N, N block-diagonal for dof_n>1.
+ * coef: device array per coef_mode, or NULL with the value in coef_scalar. */
+int efb_mass_Me(const efb_group* g, const double* coef, int coef_mode, double coef_scalar, int dof_n, double scale,
+                double* out, void* stream);
+/* GradUGradV :25-39 (A == NULL) and GradU_A_GradV :229-249: out (Ne,nPe,nPe) = scale * sum_p coef wJ dN^T A dN. */
+int efb_diffusion_Ke(const efb_group* g, const double* A, int A_mode, const double* coef, int coef_mode,
+                     double coef_scalar, double scale, double* out, void* stream);
+/* Linear.V Linear.py:18-35: out (Ne, nPe*dof_n, dof_n) = scale * sum_p f wJ N^T (the reference keeps the last axis). */
+int efb_source_Fe(const efb_group* g, const double* f, int f_mode, double f_scalar, int dof_n, double scale,
+                  double* out, void* stream);
+/* Linear.InternalForce Linear.py:38-52: out (Ne,ndof) = sum_p wJ B^T sigma, sigma (Ne,nPg,ns). */
+int efb_internal_force(const efb_group* g, const double* sigma, double* out, void* stream);
+/* Calc_Epsilon_e_pg EasyFEA/Models/Elastic/_laws.py:127-157 with Locates_sol_e _group_elem.py:1769:
+ * eps (Ne,nPg,ns) = B u_e, u (Ndof) nodal vector, dof of node n comp i = n*dim+i, connect_dof (Ne,nPe) GLOBAL ids. */
+int efb_strain(const efb_group* g, const int32_t* connect_dof, const double* u, double* eps, void* stream);
+
+/* ---- P2-P7: phase-field law, EasyFEA/Models/_phasefield.py ------------------------------------------- */
+enum { EFB_SPLIT_BOURDIN = 0, EFB_SPLIT_AMOR = 1, EFB_SPLIT_MIEHE = 2, EFB_SPLIT_STRESS = 3, EFB_SPLIT_HE = 4 };
+enum { EFB_REGU_AT1 = 1, EFB_REGU_AT2 = 2 };
+
+/* host-side parameter block (copied by value at launch) */
+typedef struct efb_pf_material {
+    int32_t dim;         /* 2 or 3 */
+    int32_t split;       /* EFB_SPLIT_* */
+    int32_t planeStress; /* 2D only */
+    int32_t _pad;
+    double E, v, lambda, mu, bulk;    /* Isotropic.get_lambda/get_mu/get_bulk, Models/Elastic/_laws.py:376-405 */
+    double C[36];                      /* (ns,ns) row-major, material.C */
+    double sqrtC[36], inv_sqrtC[36];   /* Get_sqrt_C_S :223-247 (He split only) */
+} efb_pf_material;
+
+/* Calc_C :396-431 and Calc_psi_e_pg :335-358 on a strain field eps (Ne,nPg,ns).  Outputs may be NULL:
+ * cP,cM (Ne,nPg,ns,ns); psiP,psiM (Ne,nPg).  If g_e_pg != NULL also writes Cdeg = g*cP + cM (S3,
+ * EasyFEA/Simulations/_phasefield.py:462-469).  The 3D repeated-eigenvalue case is chosen per ELEMENT as the
+ * reference does (:863,884,904-906); non-finite points are repaired per point (DESIGN.md "degenerate states"). */
+int efb_pf_split(const efb_pf_material* m, const double* eps, int64_t Ne, int32_t nPg,
+                 int32_t* elem_bits /* (Ne) int32 workspace; may be NULL in 2D or for Bourdin/Amor */, double* cP,
+                 double* cM, double* psiP, double* psiM, const double* g_e_pg, double* Cdeg, void* stream);
+/* Get_g_e_pg :295-317: g (Ne,nPg) = (1 - N d_e)^2 + k_res, d (Nn) nodal damage. */
+int efb_pf_degradation(const efb_group* g, const int32_t* connect_dof, const double* d, double k_res, double* out,
+                       void* stream);
+/* history + reaction/source terms: psiP <- max(psiP, psiP_old) (Simulations/_phasefield.py:513-530, in place);
+ * r = Get_r_e_pg :253-271, f = Get_f_e_pg :273-293.  psiP_old, r, f may be NULL. */
+int efb_pf_history_rf(double* psiP, const double* psiP_old, int64_t n, int regu, double Gc, double l0, double* r,
+                      double* f, void* stream);
+/* damage sub-problem element system (S4, Simulations/_phasefield.py:540-573), one launch:
+ * Ke (Ne,nPe,nPe) = scale * sum_p wJ (r N^T N + k dN^T A dN), Fe (Ne,nPe) = scale * sum_p wJ f N;
+ * r,f (Ne,nPg); A (dim,dim) constant. */
+int efb_pf_damage_Ke_Fe(const efb_group* g, const double* r, const double* f, const double* A, double k,
+                        double scale, double* Ke, double* Fe, void* stream);
+
+/* ---- A1: CSR pattern, EasyFEA/Simulations/_simu.py:1062-1102 ------------------------------------------ */
+/* The pattern of a dof_n-block problem is the block expansion of the node adjacency graph, so it is built from
+ * node pairs and is bit-exact against scipy's sorted/unique indptr/indices (DESIGN.md "CSR pattern").  The groups
+ * that contribute (dict order of Construct_local_matrix_system, _simu.py:1033) are described by HOST arrays of
+ * length n_groups (<= 8): device connect pointers (GLOBAL node ids), Ne, nPe.
+ * Stages — the caller owns every buffer and reads sizes back between stages:
+ *   1. efb_csr_count_node_rows : cnt (Nn) int32 = number of (group, element, local node) touching each node
+ *   2. efb_exclusive_scan_i32  : rowptr (Nn+1) int64 from cnt
+ *   3. efb_csr_fill_node_rows  : qlist (sum_g Ne*nPe) int64 = ASCENDING element-row ids q = qoff_g + e*nPe_g + a
+ *   4. efb_csr_count_adj       : deg (Nn) int32 = number of distinct neighbour nodes (err_flag != 0: > 512)
+ *   5. efb_exclusive_scan_i32  : adjptr (Nn+1) int64
+ *   6. efb_csr_fill_adj        : adj (nnz_node) int32 ascending neighbour ids per node
+ *   7. efb_csr_expand          : indptr (Ndof+1), indices (nnz = dof_n^2 nnz_node) as int32 or int64
+ *   8. efb_csr_slot_map        : pos (sum_g Ne*nPe*nPe) int32 = index of node b in adj(node a) for every (e,a,b)
+ *   9. efb_csr_inv_map         : the reference's `inv` (int32, k = (g,e,i,j) order, :1098-1101) for API parity
+ */
+int efb_csr_count_node_rows(int n_groups, const int32_t* const* connect_host, const int64_t* Ne_host,
+                            const int32_t* nPe_host, int64_t Nn, int32_t* cnt, void* stream);
+/* out (n+1) int64 exclusive prefix sums of in (n) int32; workspace >= 8*(n/1024 + 2) bytes */
+int efb_exclusive_scan_i32(const int32_t* in, int64_t n, int64_t* out, void* workspace, void* stream);
+int efb_csr_fill_node_rows(int n_groups, const int32_t* const* connect_host, const int64_t* Ne_host,
+                           const int32_t* nPe_host, int64_t Nn, const int64_t* rowptr, int32_t* cursor /* (Nn) scratch */,
+                           int64_t* qlist, void* stream);
+int efb_csr_count_adj(int n_groups, const int32_t* const* connect_host, const int64_t* Ne_host,
+                      const int32_t* nPe_host, int64_t Nn, const int64_t* rowptr, const int64_t* qlist, int32_t* deg,
+                      int32_t* err_flag, void* stream);
+int efb_csr_fill_adj(int n_groups, const int32_t* const* connect_host, const int64_t* Ne_host,
+                     const int32_t* nPe_host, int64_t Nn, const int64_t* rowptr, const int64_t* qlist,
+                     const int64_t* adjptr, int32_t* adj, void* stream);
+int efb_csr_expand(int64_t Nn, int dof_n, int64_t Ndof, int64_t nnz_node, const int64_t* adjptr, const int32_t* adj,
+                   int index_bytes, void* indptr, void* indices, void* stream);
+int efb_csr_slot_map(int n_groups, const int32_t* const* connect_host, const int64_t* Ne_host,
+                     const int32_t* nPe_host, const int64_t* adjptr, const int32_t* adj, int32_t* pos, void* stream);
+int efb_csr_inv_map(int n_groups, const int32_t* const* connect_host, const int64_t* Ne_host, const int32_t* nPe_host,
+                    int dof_n, const int64_t* adjptr, const int32_t* pos, int32_t* inv, void* stream);
+/* vector pattern (isMatrix=False, _simu.py:1075-1078): has (Ndof) int32 = 1 where the row receives an element entry;
+ * its exclusive scan is the (Ndof,1) CSR indptr; efb_csr_compact_rows packs a dense vector into that CSR's data */
+int efb_csr_row_has_entry(int64_t Nn, int dof_n, int64_t Ndof, const int64_t* rowptr, int32_t* has, void* stream);
+int efb_csr_compact_rows(int64_t Ndof, const int64_t* indptr64, const double* dense, double* out, void* stream);
+
+/* ---- A2: deterministic replay, _simu.py:989-1060 ------------------------------------------------------- */
+/* data_out (nnz) = np.bincount(inv, weights=concat_g(X_e.ravel())): every slot is summed in ascending entry order k,
+ * bit-identical to np.bincount, without atomics.  data_host[g] -> device (Ne_g, ndof_g, ndof_g).  Precondition: the
+ * nodes of an element are distinct.  max_deg = max_n deg(n). */
+int efb_csr_replay_matrix(int n_groups, const double* const* data_host, const int64_t* Ne_host,
+                          const int32_t* nPe_host, int dof_n, int64_t Nn, const int64_t* rowptr, const int64_t* qlist,
+                          const int64_t* adjptr, const int32_t* pos, int32_t max_deg, double* data_out, void* stream);
+/* out (Nn*dof_n) dense = ordered sum of the element vectors (Ne_g, ndof_g); rows without elements are 0 */
+int efb_csr_replay_vector(int n_groups, const double* const* data_host, const int64_t* Ne_host,
+                          const int32_t* nPe_host, int dof_n, int64_t Nn, const int64_t* rowptr, const int64_t* qlist,
+                          double* out, void* stream);
+
+/* ---- consumer: Jacobi-PCG building blocks (north star; the reference dispatches in Solvers.py:225-394) ---- */
+/* All scalars stay on the device; dot products are fixed-order two-stage reductions: producers write
+ * efb_pcg_partials_size() doubles of partials, efb_pcg_reduce folds them (deterministic). */
+int efb_pcg_partials_size(void);
+/* y[r] = sum_k data[k] x[indices[k]] for local rows r < nrows (masked rows give 0); x is indexed by GLOBAL column;
+ * if dot_partials != NULL also the partials of sum_r x[x_row_offset + r] * y[r].  lanes_per_row in {4,8,16,32}. */
+int efb_spmv_csr(int64_t nrows, int index_bytes, const void* indptr, const void* indices, const double* data,
+                 const double* x, int64_t x_row_offset, const uint8_t* row_mask, double* y, double* dot_partials,
+                 int lanes_per_row, void* stream);
+int efb_csr_diagonal(int64_t nrows, int64_t row_offset, int index_bytes, const void* indptr, const void* indices,
+                     const double* data, double* diag, void* stream);
+int efb_pcg_inv_diag(int64_t n, const double* diag, const uint8_t* free_mask, double* out, void* stream);
+int efb_pcg_dot(int64_t n, const double* a, const double* b, double* partials, void* stream);
+int efb_pcg_reduce(const double* partials, int m /* 1 or 2 */, double* out, void* stream);
+/* r = mask(b - Ax); z = r/diag; p = z; partials of (r.z, r.r) */
+int efb_pcg_init(int64_t n, const double* b, const double* Ax, const double* inv_diag, const uint8_t* free_mask, double* r,
+                 double* z, double* p, double* partials, void* stream);
+/* alpha = rz/pAp; x += alpha p; r -= alpha Ap; z = r/diag; partials of (r.z, r.r) */
+int efb_pcg_update_xr(int64_t n, const double* rz, const double* pAp, const double* p, const double* Ap, double* x,
+                      double* r, const double* inv_diag, const uint8_t* free_mask, double* z, double* partials,
+                      void* stream);
+/* p = z + (rz_new/rz_old) p */
+int efb_pcg_update_p(int64_t n, const double* rz_new, const double* rz_old, const double* z, const uint8_t* free_mask,
+                     double* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EASYFEA_B200_H */

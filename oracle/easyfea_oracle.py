@@ -341,11 +341,12 @@ def eigen_projectors(v, clamp=False):
         vals, M1, M3 = _eig3(M, I, e2, e3, e1, arg)
         if clamp:
             bad = ~(np.isfinite(vals).all(-1) & np.isfinite(M1).all((-1, -2)) & np.isfinite(M3).all((-1, -2)))
-            argc = np.where(gnz, np.clip(np.nan_to_num(arg, nan=0.0), -1.0, 1.0), 0.0)
+            gpos = g > 0  # g <= 0 or NaN counts as the triple-eigenvalue case
+            argc = np.where(gpos, np.clip(np.nan_to_num(arg, nan=0.0), -1.0, 1.0), 0.0)
             thc = 1 / 3 * np.arccos(argc)
-            p2 = gnz & (thc == np.pi / 3)
-            p3 = gnz & (thc == 0)
-            p1 = gnz & ~p2 & ~p3
+            p2 = gpos & (thc == np.pi / 3)
+            p3 = gpos & (thc == 0)
+            p1 = gpos & ~p2 & ~p3
             rv, rM1, rM3 = _eig3(M, I, p2, p3, p1, argc)
             vals = np.where(bad[..., None], rv, vals)
             M1 = np.where(bad[..., None, None], rM1, M1)
