@@ -1,0 +1,223 @@
+"""Global CSR assembly on the device — the drop-in for `_Simu.__Get_csr_map` / `__Assemble_csr`
+(EasyFEA/Simulations/_simu.py:989-1102; level 2 of the boundary).
+
+`NodeGraph` holds what depends on connectivity only (node -> element rows, node adjacency, slot positions); it is
+built once per tuple of contributing groups and shared by every `dof_n`.  `CsrPattern` is its block expansion for one
+`(dof_n, Ndof)`: `indptr/indices` bit-identical to scipy's canonical pattern, index dtype chosen like scipy
+(`int32` unless `max(Ndof, n_entries) > 2**31-1`).  `replay_*` sums element entries in ascending entry order, i.e.
+bit-identical to the reference's `np.bincount`, with no atomics.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import device as dv
+from .mesh import device_group
+
+_I32MAX = np.iinfo(np.int32).max
+
+
+def _group_args(dgs, pointers):
+    n = len(dgs)
+    ptrs = (ctypes.c_void_p * n)(*[p.data_ptr() if p is not None else 0 for p in pointers])
+    Ne = (ctypes.c_int64 * n)(*[dg.Ne for dg in dgs])
+    nPe = (ctypes.c_int32 * n)(*[dg.nPe for dg in dgs])
+    return n, ptrs, Ne, nPe
+
+
+def _scan(cnt: torch.Tensor) -> torch.Tensor:
+    n = cnt.numel()
+    out = dv.empty((n + 1,), torch.int64)
+    work = dv.empty((n // 1024 + 2,), torch.int64)
+    _lib.call("efb_exclusive_scan_i32", dv.ptr(cnt), n, dv.ptr(out), dv.ptr(work), dv.stream_ptr())
+    return out
+
+
+class NodeGraph:
+    """Connectivity-only part of the assembly map for an ordered tuple of element groups (A1, stages 1-6 and 8)."""
+
+    def __init__(self, groups, Nn: int):
+        self.dgs = [device_group(g) for g in groups]
+        if not 1 <= len(self.dgs) <= 8:
+            raise ValueError("between 1 and 8 element groups can contribute to one matrix")
+        self.Nn = int(Nn)
+        for dg in self.dgs:
+            if dg.Ncoords > self.Nn:
+                raise ValueError("a group references more coordinates than Nn")
+        connects = [dg.connect_glob for dg in self.dgs]
+        n, ptrs, Ne, nPe = _group_args(self.dgs, connects)
+        st = dv.stream_ptr()
+        Nn = self.Nn
+        cnt = dv.empty((Nn,), torch.int32)
+        _lib.call("efb_csr_count_node_rows", n, ptrs, Ne, nPe, Nn, dv.ptr(cnt), st)
+        self.rowptr = _scan(cnt)
+        n_rows = int(self.rowptr[-1].item())
+        self.qlist = dv.empty((n_rows,), torch.int64)
+        _lib.call("efb_csr_fill_node_rows", n, ptrs, Ne, nPe, Nn, dv.ptr(self.rowptr), dv.ptr(cnt), dv.ptr(self.qlist), st)
+        deg = cnt  # reuse
+        err = torch.zeros(1, dtype=torch.int32, device=cnt.device)
+        _lib.call("efb_csr_count_adj", n, ptrs, Ne, nPe, Nn, dv.ptr(self.rowptr), dv.ptr(self.qlist), dv.ptr(deg), dv.ptr(err), st)
+        if int(err.item()) != 0:
+            raise _lib.EfbError("a node has more than 512 distinct neighbour nodes (kAdjCap)")
+        self.max_deg = int(deg.max().item()) if Nn else 0
+        self.adjptr = _scan(deg)
+        self.nnz_node = int(self.adjptr[-1].item())
+        self.adj = dv.empty((self.nnz_node,), torch.int32)
+        _lib.call("efb_csr_fill_adj", n, ptrs, Ne, nPe, Nn, dv.ptr(self.rowptr), dv.ptr(self.qlist), dv.ptr(self.adjptr),
+                  dv.ptr(self.adj), st)
+        n_pos = sum(dg.Ne * dg.nPe * dg.nPe for dg in self.dgs)
+        self.pos = dv.empty((n_pos,), torch.int32)
+        _lib.call("efb_csr_slot_map", n, ptrs, Ne, nPe, dv.ptr(self.adjptr), dv.ptr(self.adj), dv.ptr(self.pos), st)
+        self._connect_args = (n, ptrs, Ne, nPe, connects)
+
+    def n_entries(self, dof_n: int) -> int:
+        return sum(dg.Ne * (dg.nPe * dof_n) ** 2 for dg in self.dgs)
+
+
+class DeviceCsr:
+    """CSR matrix resident on the device (`indptr`, `indices`, `data` torch tensors)."""
+
+    def __init__(self, indptr, indices, data, shape):
+        self.indptr, self.indices, self.data, self.shape = indptr, indices, data, tuple(shape)
+
+    @property
+    def nnz(self) -> int:
+        return int(self.data.numel())
+
+    @property
+    def index_bytes(self) -> int:
+        return 4 if self.indices.dtype == torch.int32 else 8
+
+    def to_scipy(self):
+        from scipy import sparse
+
+        m = sparse.csr_matrix((dv.to_host(self.data), dv.to_host(self.indices), dv.to_host(self.indptr)), shape=self.shape)
+        m.has_canonical_format = True  # canonical by construction, like _simu.py:1058-1059
+        return m
+
+
+class CsrPattern:
+    """Canonical CSR pattern of one assembly key `(dof_n, isMatrix, Ndof, groups)` — `__Get_csr_map`, _simu.py:1062-1102."""
+
+    def __init__(self, graph: NodeGraph, dof_n: int, Ndof: int, isMatrix: bool = True):
+        self.graph, self.dof_n, self.Ndof, self.isMatrix = graph, int(dof_n), int(Ndof), bool(isMatrix)
+        d, Nn = self.dof_n, graph.Nn
+        if Ndof < Nn * d:
+            raise ValueError("Ndof < Nn*dof_n")
+        st = dv.stream_ptr()
+        if isMatrix:
+            n_entries = graph.n_entries(d)
+            self.nnz = graph.nnz_node * d * d
+            big = max(Ndof, n_entries) > _I32MAX  # scipy's rule (coo -> csr picks int64 when nnz or shape needs it)
+            self.index_dtype = torch.int64 if big else torch.int32
+            self.indptr = dv.empty((Ndof + 1,), self.index_dtype)
+            self.indices = dv.empty((self.nnz,), self.index_dtype)
+            _lib.call("efb_csr_expand", Nn, d, Ndof, graph.nnz_node, dv.ptr(graph.adjptr), dv.ptr(graph.adj),
+                      8 if big else 4, dv.ptr(self.indptr), dv.ptr(self.indices), st)
+        else:
+            has = dv.empty((Ndof,), torch.int32)
+            _lib.call("efb_csr_row_has_entry", Nn, d, Ndof, dv.ptr(graph.rowptr), dv.ptr(has), st)
+            self.indptr64 = _scan(has)
+            self.nnz = int(self.indptr64[-1].item())
+            n_entries = sum(dg.Ne * dg.nPe * d for dg in graph.dgs)
+            big = max(Ndof, n_entries) > _I32MAX
+            self.index_dtype = torch.int64 if big else torch.int32
+            self.indptr = self.indptr64.to(self.index_dtype)
+            self.indices = torch.zeros(self.nnz, dtype=self.index_dtype, device=has.device)
+        self.shape = (Ndof, Ndof) if isMatrix else (Ndof, 1)
+
+    # -- values ------------------------------------------------------------------------------------------------
+    def _data_args(self, datas):
+        g = self.graph
+        if len(datas) != len(g.dgs):
+            raise ValueError("one data array per contributing group")
+        tens = []
+        for dg, X in zip(g.dgs, datas):
+            ndof = dg.nPe * self.dof_n
+            want = dg.Ne * ndof * (ndof if self.isMatrix else 1)
+            t = dv.to_device(X)
+            assert t.numel() == want, f"Not enough data to fill a {self.shape} CSR."
+            tens.append(t)
+        return _group_args(g.dgs, tens) + (tens,)
+
+    def replay(self, datas, out=None) -> torch.Tensor:
+        """CSR `data` (nnz) from per-group element arrays: np.bincount(inv, weights=concat(data)) bit for bit."""
+        g = self.graph
+        n, ptrs, Ne, nPe, keep = self._data_args(datas)
+        st = dv.stream_ptr()
+        if self.isMatrix:
+            if out is None:
+                out = dv.empty((self.nnz,))
+            _lib.call("efb_csr_replay_matrix", n, ptrs, Ne, nPe, self.dof_n, g.Nn, dv.ptr(g.rowptr), dv.ptr(g.qlist),
+                      dv.ptr(g.adjptr), dv.ptr(g.pos), g.max_deg, dv.ptr(out), st)
+            return out
+        dense = torch.zeros(self.Ndof, dtype=torch.float64, device=g.rowptr.device)
+        _lib.call("efb_csr_replay_vector", n, ptrs, Ne, nPe, self.dof_n, g.Nn, dv.ptr(g.rowptr), dv.ptr(g.qlist), dv.ptr(dense), st)
+        if out is None:
+            out = dv.empty((self.nnz,))
+        _lib.call("efb_csr_compact_rows", self.Ndof, dv.ptr(self.indptr64), dv.ptr(dense), dv.ptr(out), st)
+        self.last_dense = dense
+        return out
+
+    def assemble(self, datas) -> DeviceCsr:
+        return DeviceCsr(self.indptr, self.indices, self.replay(datas), self.shape)
+
+    def inv_map(self) -> torch.Tensor:
+        """The reference's `inv` array (int32, entry order k), for API parity / tests."""
+        g = self.graph
+        n, ptrs, Ne, nPe, _ = g._connect_args
+        if self.isMatrix:
+            inv = dv.empty((g.n_entries(self.dof_n),), torch.int32)
+            _lib.call("efb_csr_inv_map", n, ptrs, Ne, nPe, self.dof_n, dv.ptr(g.adjptr), dv.ptr(g.pos), dv.ptr(inv), dv.stream_ptr())
+            return inv
+        parts = []
+        d = self.dof_n
+        for dg in g.dgs:  # inv of a vector entry = slot of its row
+            rows = (dg.connect_glob.to(torch.int64)[:, :, None] * d + torch.arange(d, device=dg.connect_glob.device)).reshape(-1)
+            parts.append(self.indptr64[rows].to(torch.int32))
+        return torch.cat(parts)
+
+
+class Assembler:
+    """Caches node graphs and patterns per assembly key, like `@cache_computed_values` on `__Get_csr_map`."""
+
+    def __init__(self):
+        self._graphs = {}
+        self._patterns = {}
+
+    def clear(self):
+        self._graphs.clear()
+        self._patterns.clear()
+
+    def pattern(self, dof_n, isMatrix, Ndof, groups) -> CsrPattern:
+        gkey = tuple(id(g) for g in groups)
+        d = int(dof_n)
+        Nn = max(int(g.Ncoords) for g in groups)
+        if (gkey, Nn) not in self._graphs:
+            self._graphs[(gkey, Nn)] = (NodeGraph(groups, Nn), tuple(groups))  # keep the groups alive with their ids
+        key = (gkey, Nn, d, bool(isMatrix), int(Ndof))
+        if key not in self._patterns:
+            self._patterns[key] = CsrPattern(self._graphs[(gkey, Nn)][0], d, Ndof, isMatrix)
+        return self._patterns[key]
+
+    def Get_csr_map(self, dof_n, isMatrix, Ndof, groups):
+        """(inv, indices, indptr, nnz) as NumPy arrays — same tuple as `_Simu.__Get_csr_map`."""
+        p = self.pattern(dof_n, isMatrix, Ndof, groups)
+        return dv.to_host(p.inv_map()), dv.to_host(p.indices), dv.to_host(p.indptr), p.nnz
+
+    def Assemble_csr(self, dict_group_data: dict, dof_n: int, Ndof: int, isMatrix: bool = True, as_device: bool = False):
+        """`_Simu.__Assemble_csr` (_simu.py:989-1060): {group: X_e or None} -> scipy csr (or DeviceCsr)."""
+        from scipy import sparse
+
+        shape = (Ndof, Ndof) if isMatrix else (Ndof, 1)
+        groups = tuple(g for g, X in dict_group_data.items() if X is not None) if dict_group_data else ()
+        if not groups or sum(np.size(dict_group_data[g]) if not isinstance(dict_group_data[g], torch.Tensor)
+                             else dict_group_data[g].numel() for g in groups) == 0:
+            return sparse.csr_matrix(shape)
+        pat = self.pattern(dof_n, isMatrix, Ndof, groups)
+        A = pat.assemble([dict_group_data[g] for g in groups])
+        return A if as_device else A.to_scipy()

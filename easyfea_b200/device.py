@@ -1,0 +1,50 @@
+"""Device plumbing: torch owns device memory and streams, the C-ABI library does the work (raw pointers only)."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def device() -> torch.device:
+    _lib.require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream_ptr() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t) -> ctypes.c_void_p | None:
+    """raw device pointer of a contiguous torch tensor (None passes NULL)"""
+    if t is None:
+        return None
+    assert t.is_contiguous()
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def to_device(a, dtype=None) -> torch.Tensor:
+    """host array -> contiguous device tensor; floats become float64, integer dtypes are kept unless `dtype` is given"""
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device(), dtype=dtype if dtype is not None else a.dtype).contiguous()
+    arr = np.asarray(a)
+    if dtype is None:
+        dtype = arr.dtype if arr.dtype.kind in "iu" else np.float64
+    return torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype)).to(device())
+
+
+def empty(shape, dtype=torch.float64) -> torch.Tensor:
+    return torch.empty(tuple(int(s) for s in shape), dtype=dtype, device=device())
+
+
+def to_host(t: torch.Tensor) -> np.ndarray:
+    """fresh, writable, C-contiguous numpy array (callers of the operator API mutate results in place)"""
+    return t.detach().cpu().numpy()
+
+
+def ptr_array(tensors) -> ctypes.Array:
+    """host array of device pointers (`const T* const*` arguments)"""
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])

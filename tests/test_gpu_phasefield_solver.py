@@ -1,0 +1,149 @@
+"""GPU parity of the phase-field law + simulation-level builders, and of the Jacobi-PCG consumer.  -m gpu"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import easyfea_oracle as orc
+from tests.helpers import make_mesh, rel_err
+from tests.test_hostcheck_pf_csr import generic_states
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def efb():
+    from easyfea_b200 import _lib, assembly, mesh, operators, phasefield, solver
+
+    _lib.require_cuda()
+
+    class NS:
+        pass
+
+    ns = NS()
+    ns.asm, ns.mesh, ns.op, ns.pf, ns.solver = assembly, mesh, operators, phasefield, solver
+    return ns
+
+
+@pytest.mark.parametrize("dim,planeStress", [(2, False), (2, True), (3, False)])
+@pytest.mark.parametrize("split", ["Bourdin", "Amor", "Miehe", "Stress", "He"])
+def test_split_generic_states(efb, dim, planeStress, split):
+    om = orc.IsoMaterial(dim, 210000.0, 0.3, planeStress)
+    pfm = efb.pf.PhaseFieldModel(efb.pf.IsotropicMaterial(dim, 210000.0, 0.3, planeStress), split, "AT2", 2.7, 0.01)
+    eps = generic_states(dim, 2000, 4, seed=21)
+    cP, cM = pfm.Calc_C(eps, verif=True)
+    psiP, psiM = pfm.Calc_psi_e_pg(eps)
+    ocP, ocM = orc.calc_C(om, split, eps)
+    opP, opM = orc.calc_psi(om, split, eps)
+    assert rel_err(cP, ocP) < TOL and rel_err(cM, ocM) < TOL
+    assert rel_err(psiP, opP) < TOL and rel_err(psiM, opM) < TOL
+    psi = 0.5 * np.einsum("epi,ij,epj->ep", eps, om.C, eps)
+    assert rel_err(psiP + psiM, psi) < TOL  # tests/Models/phasefield_test.py:133-137
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("split", ["Amor", "Miehe", "Stress", "He"])
+def test_split_degenerate_states(efb, dim, split):
+    om = orc.IsoMaterial(dim, 210000.0, 0.3)
+    pfm = efb.pf.PhaseFieldModel(efb.pf.IsotropicMaterial(dim, 210000.0, 0.3, False), split, "AT2", 2.7, 0.01)
+    ns = 3 if dim == 2 else 6
+    rng = np.random.default_rng(2)
+    eps = rng.normal(size=(12, 3, ns)) * 1e-3
+    eps[0] = 0.0
+    eps[1] = 0.0; eps[1, :, 0] = 1e-3
+    eps[2] = 0.0; eps[2, :, :dim] = 1e-3
+    eps[3, 1] = 0.0
+    eps[4, 0] = 0.0; eps[4, 0, :2] = 2e-3
+    eps[5] = 0.0; eps[5, :, 0] = 1e-3; eps[5, :, 1:dim] = -0.3e-3
+    cP, cM = pfm.Calc_C(eps)
+    assert np.isfinite(cP).all() and np.isfinite(cM).all()
+    assert rel_err(cP + cM, np.broadcast_to(om.C, cP.shape)) < 1e-11
+    ocP, _ = orc.calc_C(om, split, eps, clamp=True)
+    assert rel_err(cP[6:], ocP[6:]) < TOL
+
+
+@pytest.mark.parametrize("name", ["QUAD9", "HEXA8", "TRI3", "TETRA4", "HEXA27"])
+@pytest.mark.parametrize("split", ["Amor", "Miehe", "Stress", "He"])
+def test_golden_splits_on_solved_like_fields(efb, name, split):
+    d = dict(np.load(os.path.join(GOLD, f"{name}.npz")))
+    g = efb.mesh.ElemGroup(name, d["connect"], d["coords"])
+    pfm = efb.pf.PhaseFieldModel(efb.pf.IsotropicMaterial(g.dim, 210000.0, 0.3, False), split, "AT2", 2.7, 0.01)
+    for mt in ("rigi", "mass"):
+        cP, cM = pfm.Calc_C(d[f"eps_{mt}"])
+        psiP, psiM = pfm.Calc_psi_e_pg(d[f"eps_{mt}"])
+        assert rel_err(cP, d[f"cP_{split}_{mt}"]) < TOL and rel_err(cM, d[f"cM_{split}_{mt}"]) < TOL
+        assert rel_err(psiP, d[f"psiP_{split}_{mt}"]) < TOL and rel_err(psiM, d[f"psiM_{split}_{mt}"]) < TOL
+    assert rel_err(pfm.Get_g_e_pg(d["dmg"], g, "rigi"), d["g_rigi"]) < TOL
+
+
+@pytest.mark.parametrize("elemType,split,regu", [("TRI3", "Miehe", "AT2"), ("TETRA4", "He", "AT2"), ("QUAD9", "Amor", "AT1"),
+                                                 ("HEXA8", "Stress", "AT1")])
+def test_simulation_level_builders(efb, elemType, split, regu):
+    """S3 / S4 of SURVEY §8a against the oracle compositions (configs 3 and 4 element types + two more)."""
+    from easyfea_b200 import elements as el
+
+    rng = np.random.default_rng(8)
+    coords, connect = make_mesh(elemType)
+    g = efb.mesh.ElemGroup(elemType, connect, coords)
+    dim = g.dim
+    Nn = coords.shape[0]
+    thickness = 0.5 if dim == 2 else 1.0
+    om = orc.IsoMaterial(dim, 210e9, 0.3, False)
+    pfm = efb.pf.PhaseFieldModel(efb.pf.IsotropicMaterial(dim, 210e9, 0.3, False, thickness), split, regu, 2.7e3, 1e-2)
+    u = rng.normal(size=Nn * dim) * 1e-5
+    dmg = rng.uniform(0, 0.9, Nn)
+    u_e = orc.locate_sol_e(u, connect, dim)
+    tr, tm = el.gauss_table(elemType, "rigi"), el.gauss_table(elemType, "mass")
+    geo_r = orc.geometry(coords[connect][:, :, :dim], tr.dN_pg, tr.weights)
+    geo_m = orc.geometry(coords[connect][:, :, :dim], tm.dN_pg, tm.weights)
+    Ke = pfm.elastic_Ke_dev(g, u, dmg).cpu().numpy()
+    ref = thickness * orc.pf_elastic_Ke(geo_r, tr.N_pg, om, split, u_e, dmg[connect], clamp=True)
+    assert rel_err(Ke, ref) < 1e-11
+    old = rng.uniform(0, 1, (g.Ne, tm.nPg)) * float(np.median(orc.calc_psi(om, split, orc.strain(geo_m, u_e), True)[0]))
+    Kd, Fd, psiP = pfm.damage_system_dev(g, u, old)
+    rK, rF, rpsi = orc.pf_damage_system(geo_m, tm.N_pg, om, split, regu, 2.7e3, 1e-2, u_e, old, clamp=True)
+    assert rel_err(psiP.cpu().numpy(), rpsi) < 1e-11
+    assert rel_err(Kd.cpu().numpy(), thickness * rK) < 1e-11
+    assert rel_err(Fd.cpu().numpy(), thickness * rF[..., 0]) < 1e-11
+
+
+def test_pcg_elastic_cube(efb):
+    """HEXA8 cube clamped at x=0, u_x=0.1 at x=1 (config 2 BCs): ||Ax-b||/||b|| <= 1e-8 and x matches a direct solve."""
+    import scipy.sparse.linalg as spla
+    import torch
+
+    from easyfea_b200 import meshgen
+
+    n = 12
+    coords, connect = meshgen.structured_mesh("HEXA8", n, jitter=0.15, seed=0)
+    g = efb.mesh.ElemGroup("HEXA8", connect, coords, all_nodes_used=True)
+    Nn = coords.shape[0]
+    Ndof = 3 * Nn
+    om = orc.IsoMaterial(3, 210000.0, 0.3)
+    A = efb.asm.Assembler()
+    K = A.Assemble_csr({g: efb.op.elastic_Ke_dev(g, om.C)}, 3, Ndof, True, as_device=True)
+    x0 = np.zeros(Ndof)
+    known = np.zeros(Ndof, bool)
+    left = np.flatnonzero(coords[:, 0] < 1e-9 + coords[:, 0].min())
+    right = np.flatnonzero(coords[:, 0] > coords[:, 0].max() - 1e-9)
+    # structured ids: clamp the x=0 lattice plane, pull the x=1 plane
+    lat = np.arange(Nn) % (n + 1)
+    left, right = np.flatnonzero(lat == 0), np.flatnonzero(lat == n)
+    for c in range(3):
+        known[left * 3 + c] = True
+    known[right * 3] = True
+    x0[right * 3] = 0.1
+    b = np.zeros(Ndof)
+    x, info = efb.solver.pcg(K, b, x0=x0, free_mask=~known, tol=1e-8, maxiter=5000)
+    assert info["converged"], info
+    x = x.cpu().numpy()
+    Ks = K.to_scipy()
+    free = ~known
+    rhs = (b - Ks @ (x0 * known))[free]
+    res = np.linalg.norm(Ks[free][:, free] @ x[free] - rhs) / np.linalg.norm(rhs)
+    assert res <= 1e-8
+    xd = spla.spsolve(Ks[free][:, free].tocsc(), rhs)
+    assert np.linalg.norm(x[free] - xd) / np.linalg.norm(xd) < 1e-6
+    assert np.array_equal(x[known], x0[known])
