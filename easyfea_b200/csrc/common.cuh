@@ -24,6 +24,8 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 // opt in to large dynamic shared memory once per kernel
 template <class K>
 inline int ensure_smem(K kernel, size_t bytes) {
+    // these kernels live in shared memory, not L1: ask for the largest carve-out so several CTAs fit an SM
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (bytes > 48 * 1024) {
         if (bytes > 227 * 1024) {
             set_error("kernel needs %zu bytes of shared memory (> 227 KB)", bytes);

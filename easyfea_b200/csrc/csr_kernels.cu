@@ -191,6 +191,27 @@ __global__ void __launch_bounds__(256) k_replay_matrix(GroupTable T, int d, long
     replay_node(T, d, n, rowptr, qlist, adjptr, pos, smem + (size_t)warp * acc_per_warp, out);
 }
 
+template <int D, int NPE>
+__global__ void __launch_bounds__(256) k_replay_fast(const double* data, long long Nn, const long long* rowptr, const long long* qlist,
+                                                     const long long* adjptr, const int* pos, int acc_per_warp, double* out) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5;
+    const long long n = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (n >= Nn) return;
+    replay_node_fast<D, NPE, 4>(data, n, rowptr, qlist, adjptr, pos, smem + (size_t)warp * acc_per_warp, out);
+}
+
+template <int D, int NPE>
+static int launch_replay_fast(const double* data, long long Nn, const long long* rowptr, const long long* qlist,
+                              const long long* adjptr, const int* pos, int max_deg, double* out, cudaStream_t st) {
+    const int warps = 8;
+    const int acc_per_warp = D * D * max_deg;
+    const size_t bytes = sizeof(double) * (size_t)acc_per_warp * warps;
+    if (ensure_smem(k_replay_fast<D, NPE>, bytes)) return 1;
+    k_replay_fast<D, NPE><<<blocks_for(Nn, warps), warps * 32, bytes, st>>>(data, Nn, rowptr, qlist, adjptr, pos, acc_per_warp, out);
+    return check_launch("efb_csr_replay_matrix");
+}
+
 __global__ void k_replay_vector(GroupTable T, int d, long long nrows, const long long* rowptr, const long long* qlist, double* out) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r < nrows) replay_vector_item(T, d, r, rowptr, qlist, out);
@@ -333,6 +354,16 @@ extern "C" int efb_csr_replay_matrix(int n_groups, const double* const* data_hos
     GroupTable T;
     if (make_table(T, n_groups, nullptr, data_host, Ne_host, nPe_host, dof_n)) return 1;
     if (Nn == 0) return 0;
+    if (n_groups == 1) {  // single group with a compiled (dof_n, nPe): hoisted index math, batched loads
+#define EFB_FAST(D, N)                                                                                                 \
+    if (dof_n == D && nPe_host[0] == N)                                                                                \
+        return launch_replay_fast<D, N>(data_host[0], Nn, (const long long*)rowptr, (const long long*)qlist,           \
+                                        (const long long*)adjptr, pos, max_deg, data_out, as_stream(stream));
+        EFB_FAST(3, 8) EFB_FAST(3, 4) EFB_FAST(3, 10) EFB_FAST(3, 27) EFB_FAST(3, 20) EFB_FAST(3, 6)
+        EFB_FAST(2, 3) EFB_FAST(2, 4) EFB_FAST(2, 6) EFB_FAST(2, 8) EFB_FAST(2, 9)
+        EFB_FAST(1, 3) EFB_FAST(1, 4) EFB_FAST(1, 6) EFB_FAST(1, 8) EFB_FAST(1, 9) EFB_FAST(1, 10) EFB_FAST(1, 27) EFB_FAST(1, 20)
+#undef EFB_FAST
+    }
     const int warps = 8;
     const int acc_per_warp = dof_n * dof_n * max_deg;
     const size_t bytes = sizeof(double) * (size_t)acc_per_warp * warps;

@@ -19,7 +19,11 @@
 #ifdef __CUDACC__
 #define EFB_ATOMIC_ADD_I32(ptr, v) atomicAdd((ptr), (v))
 #define EFB_LANES(lane) for (int lane = threadIdx.x & 31, _efb_l1 = 1; _efb_l1; _efb_l1 = 0, __syncwarp())
+#define EFB_LANE_COPIES 1
+#define EFB_LANE_SLOT(lane) 0
 #else
+#define EFB_LANE_COPIES 32
+#define EFB_LANE_SLOT(lane) (lane)
 static inline int efb_host_fetch_add(int* p, int v) {
     int old = *p;
     *p += v;
@@ -195,6 +199,61 @@ EFB_D void replay_node(const GroupTable& T, int d, long long n, const long long*
     }
     EFB_LANES(lane) {
         double* dst = out + (long long)d * d * a0;
+        for (int i = lane; i < blk; i += 32) dst[i] = acc[i];
+    }
+}
+
+// single-group fast path: D and NPE are compile-time, so the (row, node, component) decomposition of a lane's values is
+// hoisted out of every loop, and the values of SB sources are in flight before the ordered accumulation starts
+template <int D, int NPE, int SB>
+EFB_D void replay_node_fast(const double* EFB_RESTRICT data, long long n, const long long* EFB_RESTRICT rowptr,
+                            const long long* EFB_RESTRICT qlist, const long long* EFB_RESTRICT adjptr,
+                            const int* EFB_RESTRICT pos, double* acc, double* EFB_RESTRICT out) {
+    constexpr int NDOF = D * NPE, NV = D * NDOF, VPL = (NV + 31) / 32;
+    const long long a0 = adjptr[n];
+    const int deg = (int)(adjptr[n + 1] - a0);
+    const int rowlen = D * deg, blk = D * rowlen;
+    const long long s_begin = rowptr[n], s_end = rowptr[n + 1];
+    EFB_LANES(lane) {
+        for (int i = lane; i < blk; i += 32) acc[i] = 0.0;
+    }
+    // per-lane registers on the device; the host emulation keeps one copy per emulated lane
+    double v[EFB_LANE_COPIES][SB][VPL];
+    int pb[EFB_LANE_COPIES][SB][VPL];
+    for (long long s0 = s_begin; s0 < s_end; s0 += SB) {
+        EFB_LANES(lane) {  // issue the loads of up to SB sources
+            EFB_UNROLL
+            for (int u = 0; u < SB; ++u) {
+                if (s0 + u < s_end) {
+                    const long long q = qlist[s0 + u];  // = e*NPE + a
+                    const double* src = data + q * (long long)NV;
+                    const int* prow = pos + q * NPE;
+                    EFB_UNROLL
+                    for (int k = 0; k < VPL; ++k) {
+                        const int i = lane + 32 * k;
+                        if (i < NV) {
+                            v[EFB_LANE_SLOT(lane)][u][k] = src[i];
+                            pb[EFB_LANE_SLOT(lane)][u][k] = prow[(i % NDOF) / D];
+                        }
+                    }
+                }
+            }
+        }
+        EFB_UNROLL
+        for (int u = 0; u < SB; ++u) {  // ordered accumulation: source by source (ascending k of every slot)
+            EFB_LANES(lane) {
+                if (s0 + u < s_end) {
+                    EFB_UNROLL
+                    for (int k = 0; k < VPL; ++k) {
+                        const int i = lane + 32 * k;
+                        if (i < NV) acc[(i / NDOF) * rowlen + pb[EFB_LANE_SLOT(lane)][u][k] * D + (i % NDOF) % D] += v[EFB_LANE_SLOT(lane)][u][k];
+                    }
+                }
+            }
+        }
+    }
+    EFB_LANES(lane) {
+        double* dst = out + (long long)D * D * a0;
         for (int i = lane; i < blk; i += 32) dst[i] = acc[i];
     }
 }

@@ -2,6 +2,8 @@
 #include "common.cuh"
 #include "elem_kernels.cuh"
 
+#include <string.h>
+
 namespace efb {
 
 static GroupView view_of(const efb_group* g) {
@@ -17,10 +19,13 @@ static GroupView view_of(const efb_group* g) {
     return v;
 }
 
-static int elems_per_block(int TPE) {
-    int epb = 192 / TPE;
+// elements per CTA: ~256 threads, and at most ~72 KB of shared memory so that 3 CTAs fit an SM
+template <int DIM, int NPE>
+static int elems_per_block(int TPE, int nPg, int extra) {
+    int epb = 256 / TPE;
     if (epb < 1) epb = 1;
     if (epb > 16) epb = 16;
+    while (epb > 1 && SmemMap<DIM, NPE>(nPg, epb, extra).total() * sizeof(double) > 72 * 1024) --epb;
     return epb;
 }
 
@@ -45,7 +50,7 @@ __global__ void __launch_bounds__(256) k_geometry(GroupView g, GeomOut o, int EP
 
 template <int DIM, int NPE>
 static int launch_geometry(const efb_group* g, const GeomOut& o, cudaStream_t st) {
-    const int TPE = DIM * NPE, EPB = elems_per_block(TPE);
+    const int TPE = DIM * NPE, EPB = elems_per_block<DIM, NPE>(TPE, g->nPg, 0);
     const SmemMap<DIM, NPE> sm(g->nPg, EPB, 0);
     const size_t bytes = sizeof(double) * sm.total();
     if (ensure_smem(k_geometry<DIM, NPE>, bytes)) return 1;
@@ -56,23 +61,48 @@ static int launch_geometry(const efb_group* g, const GeomOut& o, cudaStream_t st
 }
 
 // ---------------------------------------------------------------------------------------------------------
-template <int DIM, int NPE>
-__global__ void __launch_bounds__(256) k_elastic(GroupView g, const double* C, int C_mode, double scale, double* out, int EPB) {
+template <int DIM, int NPE, int CMODE>
+__global__ void __launch_bounds__(256) k_elastic(GroupView g, CMat Cconst, const double* C, double scale, double* out, int EPB) {
     extern __shared__ double smem[];
-    elastic_block<DIM, NPE>(g, C, C_mode, scale, out, EPB, blockIdx.x, blockDim.x, smem);
+    elastic_block<DIM, NPE, CMODE>(g, Cconst, C, scale, out, EPB, blockIdx.x, blockDim.x, smem);
+}
+
+template <int DIM, int NPE, int CMODE>
+static int launch_elastic_mode(const efb_group* g, const CMat& Cconst, const double* C, double scale, double* out, cudaStream_t st) {
+    constexpr int NS = StrainSize<DIM>::value;
+    const int extra = CMODE == 2 ? g->nPg * NS * NS : (CMODE == 1 ? NS * NS : 0);
+    const int TPE = ElasticTile<DIM, NPE>::TPE, EPB = elems_per_block<DIM, NPE>(TPE, g->nPg, extra);
+    const SmemMap<DIM, NPE> sm(g->nPg, EPB, extra);
+    const size_t bytes = sizeof(double) * sm.total();
+    if (ensure_smem(k_elastic<DIM, NPE, CMODE>, bytes)) return 1;
+    const long long nblk = (g->Ne + EPB - 1) / EPB;
+    if (nblk == 0) return 0;
+    k_elastic<DIM, NPE, CMODE><<<(unsigned)nblk, EPB * TPE, bytes, st>>>(view_of(g), Cconst, C, scale, out, EPB);
+    return check_launch("efb_elastic_Ke");
 }
 
 template <int DIM, int NPE>
-static int launch_elastic(const efb_group* g, const double* C, int C_mode, double scale, double* out, cudaStream_t st) {
+static int launch_elastic(const efb_group* g, const double* C, const double* C_host, int C_mode, double scale, double* out,
+                          cudaStream_t st) {
     constexpr int NS = StrainSize<DIM>::value;
-    const int TPE = DIM * NPE, EPB = elems_per_block(TPE);
-    const SmemMap<DIM, NPE> sm(g->nPg, EPB, C_mode == 2 ? g->nPg * NS * NS : NS * NS);
-    const size_t bytes = sizeof(double) * sm.total();
-    if (ensure_smem(k_elastic<DIM, NPE>, bytes)) return 1;
-    const long long nblk = (g->Ne + EPB - 1) / EPB;
-    if (nblk == 0) return 0;
-    k_elastic<DIM, NPE><<<(unsigned)nblk, EPB * TPE, bytes, st>>>(view_of(g), C, C_mode, scale, out, EPB);
-    return check_launch("efb_elastic_Ke");
+    CMat Cconst;
+    memset(&Cconst, 0, sizeof(Cconst));
+    if (C_mode == 0) {
+        // a homogeneous C travels as a kernel argument (constant bank)
+        if (C_host) {
+            memcpy(Cconst.v, C_host, sizeof(double) * NS * NS);
+        } else {  // only a device copy was given: fetch it (synchronises the stream)
+            cudaError_t err = cudaMemcpyAsync(Cconst.v, C, sizeof(double) * NS * NS, cudaMemcpyDeviceToHost, st);
+            if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+            if (err != cudaSuccess) {
+                set_error("efb_elastic_Ke: reading C: %s", cudaGetErrorString(err));
+                return 1;
+            }
+        }
+        return launch_elastic_mode<DIM, NPE, 0>(g, Cconst, C, scale, out, st);
+    }
+    if (C_mode == 1) return launch_elastic_mode<DIM, NPE, 1>(g, Cconst, C, scale, out, st);
+    return launch_elastic_mode<DIM, NPE, 2>(g, Cconst, C, scale, out, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -84,7 +114,7 @@ __global__ void __launch_bounds__(256) k_scalar(GroupView g, ScalarOp op, int EP
 
 template <int DIM, int NPE>
 static int launch_scalar(const efb_group* g, const ScalarOp& op, cudaStream_t st, const char* what) {
-    const int TPE = NPE, EPB = elems_per_block(TPE);
+    const int TPE = NPE, EPB = elems_per_block<DIM, NPE>(TPE, g->nPg, NPE * NPE + NPE);
     const SmemMap<DIM, NPE> sm(g->nPg, EPB, NPE * NPE + NPE);
     const size_t bytes = sizeof(double) * sm.total();
     if (ensure_smem(k_scalar<DIM, NPE>, bytes)) return 1;
@@ -103,7 +133,7 @@ __global__ void __launch_bounds__(256) k_strain(GroupView g, const int* connect_
 
 template <int DIM, int NPE>
 static int launch_strain(const efb_group* g, const int* connect_dof, const double* u, double* eps, cudaStream_t st) {
-    const int TPE = DIM * NPE, EPB = elems_per_block(TPE);
+    const int TPE = DIM * NPE, EPB = elems_per_block<DIM, NPE>(TPE, g->nPg, TPE);
     const SmemMap<DIM, NPE> sm(g->nPg, EPB, TPE);
     const size_t bytes = sizeof(double) * sm.total();
     if (ensure_smem(k_strain<DIM, NPE>, bytes)) return 1;
@@ -122,7 +152,7 @@ __global__ void __launch_bounds__(256) k_internal_force(GroupView g, const doubl
 template <int DIM, int NPE>
 static int launch_internal_force(const efb_group* g, const double* sigma, double* out, cudaStream_t st) {
     constexpr int NS = StrainSize<DIM>::value;
-    const int TPE = DIM * NPE, EPB = elems_per_block(TPE);
+    const int TPE = DIM * NPE, EPB = elems_per_block<DIM, NPE>(TPE, g->nPg, g->nPg * NS);
     const SmemMap<DIM, NPE> sm(g->nPg, EPB, g->nPg * NS);
     const size_t bytes = sizeof(double) * sm.total();
     if (ensure_smem(k_internal_force<DIM, NPE>, bytes)) return 1;
@@ -159,13 +189,14 @@ extern "C" int efb_geometry(const efb_group* g, double* F, double* detF, double*
     EFB_NO_INSTANCE(g)
 }
 
-extern "C" int efb_elastic_Ke(const efb_group* g, const double* C, int C_mode, double scale, double* out, void* stream) {
+extern "C" int efb_elastic_Ke(const efb_group* g, const double* C, const double* C_host, int C_mode, double scale, double* out,
+                              void* stream) {
     if (validate(g)) return 1;
-    if (!C || !out || C_mode < 0 || C_mode > 2) {
+    if ((!C && !(C_mode == 0 && C_host)) || !out || C_mode < 0 || C_mode > 2) {
         set_error("efb_elastic_Ke: bad arguments");
         return 1;
     }
-#define X(D, N) EFB_DISPATCH(D, N, (launch_elastic<D, N>(g, C, C_mode, scale, out, as_stream(stream))))
+#define X(D, N) EFB_DISPATCH(D, N, (launch_elastic<D, N>(g, C, C_host, C_mode, scale, out, as_stream(stream))))
     EFB_FOR_EACH_ELEM(X)
 #undef X
     EFB_NO_INSTANCE(g)

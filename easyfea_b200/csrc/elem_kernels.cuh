@@ -26,6 +26,9 @@ struct GroupView {
 // ---------------------------------------------------------------------------------------------------------
 template <int DIM, int NPE>
 struct SmemMap {
+    // doubles per node in the gradient table gN[p][a][GS]: 3D rows are padded to 4 so (gx,gy) / (gz,-) are two
+    // 16-byte loads
+    static constexpr int GS = (DIM == 3) ? 4 : 2;
     int nPg, EPB, extra;  // extra = op-specific doubles per element
     EFB_HD SmemMap(int nPg_, int EPB_, int extra_) : nPg(nPg_), EPB(EPB_), extra(extra_) {}
     // tables
@@ -39,12 +42,17 @@ struct SmemMap {
     EFB_HD int o_Fi() const { return o_F() + nPg * DIM * DIM; }
     EFB_HD int o_det() const { return o_Fi() + nPg * DIM * DIM; }
     EFB_HD int o_wJ() const { return o_det() + nPg; }
-    EFB_HD int o_gN() const { return o_wJ() + nPg; }
-    EFB_HD int o_extra() const { return o_gN() + nPg * NPE * DIM; }
-    // odd stride (in doubles) so the same field of neighbouring elements falls in different banks
-    EFB_HD int per_elem() const { return (o_extra() + extra) | 1; }
-    EFB_HD int total() const { return tables() + EPB * per_elem(); }
-    EFB_HD double* elem(double* smem, int el) const { return smem + tables() + el * per_elem(); }
+    EFB_HD int o_gN() const { return (o_wJ() + nPg + 1) & ~1; }  // 16-byte aligned
+    EFB_HD int o_extra() const { return o_gN() + nPg * NPE * GS; }
+    // even stride (keeps 16-byte alignment) that is not a multiple of 16 doubles, so the same field of the elements
+    // sharing a warp falls in different banks
+    EFB_HD int per_elem() const {
+        int n = (o_extra() + extra + 1) & ~1;
+        return (n % 16 == 0) ? n + 2 : n;
+    }
+    EFB_HD int tables_padded() const { return (tables() + 1) & ~1; }
+    EFB_HD int total() const { return tables_padded() + EPB * per_elem(); }
+    EFB_HD double* elem(double* smem, int el) const { return smem + tables_padded() + el * per_elem(); }
 };
 
 // closed-form det / inverse with the reference's association of products, EasyFEA/FEM/_linalg.py:533-656
@@ -89,7 +97,7 @@ EFB_HD double det_inv<3>(const double* F, double* Fi) {
 // ---------------------------------------------------------------------------------------------------------
 template <int DIM, int NPE>
 EFB_D void geometry_phases(const GroupView& g, const SmemMap<DIM, NPE>& sm, long long e0, int TPE, int nthreads,
-                           double* smem, bool need_grad) {
+                           double* smem, bool need_grad, bool warp_local = false) {
     const int nPg = g.nPg;
     double* dNt = smem + sm.off_dN();
     double* Nt = smem + sm.off_N();
@@ -109,7 +117,7 @@ EFB_D void geometry_phases(const GroupView& g, const SmemMap<DIM, NPE>& sm, long
             }
         }
     }
-    EFB_PHASE(tid, nthreads) {  // F[p][r][c] = sum_n dN[p][r][n] x[n][c]                 _group_elem.py:864-867
+    EFB_PHASE_E(tid, nthreads, warp_local) {  // F[p][r][c] = sum_n dN[p][r][n] x[n][c]   _group_elem.py:864-867
         const int el = tid / TPE, t = tid % TPE;
         if (el < sm.EPB && e0 + el < g.Ne) {
             double* E = sm.elem(smem, el);
@@ -125,7 +133,7 @@ EFB_D void geometry_phases(const GroupView& g, const SmemMap<DIM, NPE>& sm, long
             }
         }
     }
-    EFB_PHASE(tid, nthreads) {  // det, |det| w, inverse                                    :871-915
+    EFB_PHASE_E(tid, nthreads, warp_local) {  // det, |det| w, inverse                      :871-915
         const int el = tid / TPE, t = tid % TPE;
         if (el < sm.EPB && e0 + el < g.Ne) {
             double* E = sm.elem(smem, el);
@@ -137,18 +145,19 @@ EFB_D void geometry_phases(const GroupView& g, const SmemMap<DIM, NPE>& sm, long
         }
     }
     if (need_grad) {
-        EFB_PHASE(tid, nthreads) {  // gN[p][a][d] = sum_k Fi[p][d][k] dN[p][k][a]        :1083-1105
+        EFB_PHASE_E(tid, nthreads, warp_local) {  // gN[p][a][d] = sum_k Fi[p][d][k] dN[p][k][a]   :1083-1105
             const int el = tid / TPE, t = tid % TPE;
             if (el < sm.EPB && e0 + el < g.Ne) {
                 double* E = sm.elem(smem, el);
                 const double* Fi = E + sm.o_Fi();
                 double* gN = E + sm.o_gN();
+                constexpr int GS = SmemMap<DIM, NPE>::GS;
                 for (int i = t; i < nPg * NPE * DIM; i += TPE) {
                     const int p = i / (NPE * DIM), a = (i / DIM) % NPE, d = i % DIM;
                     double s = 0.0;
                     EFB_UNROLL
                     for (int k = 0; k < DIM; ++k) s += Fi[(p * DIM + d) * DIM + k] * dNt[(p * DIM + k) * NPE + a];
-                    gN[i] = s;
+                    gN[(p * NPE + a) * GS + d] = s;
                 }
             }
         }
@@ -211,13 +220,13 @@ EFB_D void geometry_block(const GroupView& g, const GeomOut& o, int EPB, long lo
             if (o.dN) {
                 for (int i = t; i < nPg * DIM * NPE; i += TPE) {  // output layout (p, d, a)
                     const int p = i / (DIM * NPE), d = (i / NPE) % DIM, a = i % NPE;
-                    o.dN[e * nPg * DIM * NPE + i] = gN[(p * NPE + a) * DIM + d];
+                    o.dN[e * nPg * DIM * NPE + i] = gN[(p * NPE + a) * SmemMap<DIM, NPE>::GS + d];
                 }
             }
             if (o.B) {
                 for (int i = t; i < nPg * NS * NDOF; i += TPE) {  // (p, s, a*DIM+d)
                     const int p = i / (NS * NDOF), s = (i / NDOF) % NS, col = i % NDOF;
-                    o.B[e * (long long)(nPg * NS * NDOF) + i] = B_entry<DIM>(s, col % DIM, gN + (p * NPE + col / DIM) * DIM);
+                    o.B[e * (long long)(nPg * NS * NDOF) + i] = B_entry<DIM>(s, col % DIM, gN + (p * NPE + col / DIM) * SmemMap<DIM, NPE>::GS);
                 }
             }
         }
@@ -226,81 +235,128 @@ EFB_D void geometry_block(const GroupView& g, const GeomOut& o, int EPB, long lo
 
 // ---------------------------------------------------------------------------------------------------------
 // O1: K_e = scale * sum_p wJ B^T C B                                   Operators/Bilinear.py:62-79
-// thread (element, column j): cb = wJ C B[:,j] (dim non-zeros per B column), then one FMA triple per row
+//
+// Register tiling: thread (b, h) of an element owns the DIM columns of node b and the rows of NA = NPE/RSPLIT nodes
+// (chunk h), i.e. NA*DIM*DIM accumulators.  Per Gauss point it forms cb[jd] = wJ C B[:, (b,jd)] (dim non-zeros per B
+// column) once and then spends DIM FMAs per accumulator; the only shared-memory traffic of the inner loop is one
+// broadcast read of the NA row-node gradients.  A homogeneous C (mode 0) is a kernel argument and is read from the
+// constant bank; per-element / per-Gauss-point C is staged in shared memory.
 // ---------------------------------------------------------------------------------------------------------
+struct CMat {
+    double v[36];
+};
+
+struct alignas(16) Pair {
+    double x, y;
+};
+
 template <int DIM, int NPE>
-EFB_D void elastic_block(const GroupView& g, const double* EFB_RESTRICT C, int C_mode, double scale,
+struct ElasticTile {
+    // rows are split so that a thread keeps at most ~90 accumulators
+    static constexpr int RSPLIT = (DIM == 2) ? 1 : (NPE == 8 ? 2 : NPE == 27 ? 3 : NPE == 20 ? 2 : NPE == 18 ? 2 : NPE == 15 ? 3 : 1);
+    static constexpr int NA = NPE / RSPLIT;
+    static constexpr int TPE = NPE * RSPLIT;
+    static_assert(NA * RSPLIT == NPE, "RSPLIT must divide NPE");
+};
+
+template <int DIM, int NPE, int CMODE>
+EFB_D void elastic_block(const GroupView& g, const CMat& Cconst, const double* EFB_RESTRICT C, double scale,
                          double* EFB_RESTRICT out, int EPB, long long blockId, int nthreads, double* smem) {
     constexpr int NS = StrainSize<DIM>::value, NDOF = DIM * NPE, NC = NS * NS;
+    constexpr int GS = SmemMap<DIM, NPE>::GS;
+    using Tile = ElasticTile<DIM, NPE>;
+    constexpr int NA = Tile::NA, TPE = Tile::TPE;
     const int nPg = g.nPg;
-    const int extra = C_mode == 2 ? nPg * NC : NC;
+    const int extra = CMODE == 2 ? nPg * NC : (CMODE == 1 ? NC : 0);
     const SmemMap<DIM, NPE> sm(nPg, EPB, extra);
     const long long e0 = blockId * EPB;
-    geometry_phases<DIM, NPE>(g, sm, e0, NDOF, nthreads, smem, true);
-    EFB_PHASE(tid, nthreads) {  // stage C (contiguous over the elements of the CTA)
-        const int el = tid / NDOF, t = tid % NDOF;
-        const long long e = e0 + el;
-        if (el < EPB && e < g.Ne) {
-            double* Cs = sm.elem(smem, el) + sm.o_extra();
-            const double* src = C_mode == 0 ? C : (C_mode == 1 ? C + e * NC : C + e * (long long)(nPg * NC));
-            for (int i = t; i < extra; i += NDOF) Cs[i] = src[i];
+    constexpr bool kWarpLocal = (32 % TPE == 0);  // an element never straddles two warps
+    geometry_phases<DIM, NPE>(g, sm, e0, TPE, nthreads, smem, true, kWarpLocal);
+    if (CMODE != 0) {
+        EFB_PHASE_E(tid, nthreads, kWarpLocal) {  // stage C (contiguous over the elements of the CTA)
+            const int el = tid / TPE, t = tid % TPE;
+            const long long e = e0 + el;
+            if (el < EPB && e < g.Ne) {
+                double* Cs = sm.elem(smem, el) + sm.o_extra();
+                const double* src = CMODE == 1 ? C + e * NC : C + e * (long long)(nPg * NC);
+                for (int i = t; i < extra; i += TPE) Cs[i] = src[i];
+            }
         }
     }
     EFB_PHASE(tid, nthreads) {
-        const int el = tid / NDOF, j = tid % NDOF;
+        const int el = tid / TPE, t = tid % TPE;
         const long long e = e0 + el;
         if (el < EPB && e < g.Ne) {
             const double* E = sm.elem(smem, el);
             const double* wJ = E + sm.o_wJ();
             const double* gN = E + sm.o_gN();
             const double* Cs = E + sm.o_extra();
-            const int b = j / DIM, jd = j % DIM;
-            double acc[NDOF];
+            const int b = t % NPE, a0 = (t / NPE) * NA;
+            double acc[NA * DIM][DIM];
             EFB_UNROLL
-            for (int i = 0; i < NDOF; ++i) acc[i] = 0.0;
+            for (int i = 0; i < NA * DIM; ++i)
+                EFB_UNROLL
+                for (int j = 0; j < DIM; ++j) acc[i][j] = 0.0;
             for (int p = 0; p < nPg; ++p) {
-                const double* Cp = Cs + (C_mode == 2 ? p * NC : 0);
-                const double* gp = gN + p * NPE * DIM;
-                const double* gb = gp + b * DIM;
+                const double* gp = gN + p * NPE * GS;
                 const double w = wJ[p];
-                double cb[NS];
+                // C(s, r) of this Gauss point: constant bank (mode 0) or shared memory
+#define EFB_C(s_, r_) (CMODE == 0 ? Cconst.v[(s_) * NS + (r_)] : Cs[(CMODE == 2 ? p * NC : 0) + (s_) * NS + (r_)])
+                double cb[DIM][NS];
                 if constexpr (DIM == 2) {
-                    // column (b, jd): B[jd] = g[jd], B[2] = c g[1-jd]
-                    const double b0 = gb[jd], b1 = kInvSqrt2 * gb[1 - jd];
+                    const double bx = gp[b * GS], by = gp[b * GS + 1];
+                    const double hx = kInvSqrt2 * bx, hy = kInvSqrt2 * by;
                     EFB_UNROLL
-                    for (int s = 0; s < NS; ++s) cb[s] = w * (Cp[s * NS + jd] * b0 + Cp[s * NS + 2] * b1);
-                    cb[2] *= kInvSqrt2;
+                    for (int s = 0; s < NS; ++s) {
+                        cb[0][s] = w * (EFB_C(s, 0) * bx + EFB_C(s, 2) * hy);
+                        cb[1][s] = w * (EFB_C(s, 1) * by + EFB_C(s, 2) * hx);
+                    }
+                    cb[0][2] *= kInvSqrt2;
+                    cb[1][2] *= kInvSqrt2;
                     EFB_UNROLL
-                    for (int a = 0; a < NPE; ++a) {
-                        const double gx = gp[a * 2], gy = gp[a * 2 + 1];
-                        acc[a * 2 + 0] += gx * cb[0] + gy * cb[2];
-                        acc[a * 2 + 1] += gy * cb[1] + gx * cb[2];
+                    for (int a = 0; a < NA; ++a) {
+                        const Pair ga = *reinterpret_cast<const Pair*>(gp + (a0 + a) * GS);
+                        EFB_UNROLL
+                        for (int jd = 0; jd < 2; ++jd) {
+                            acc[a * 2 + 0][jd] += ga.x * cb[jd][0] + ga.y * cb[jd][2];
+                            acc[a * 2 + 1][jd] += ga.y * cb[jd][1] + ga.x * cb[jd][2];
+                        }
                     }
                 } else {
-                    // column (b, jd): jd=0 -> rows (0,4,5) = (gx, c gz, c gy); jd=1 -> (1,3,5) = (gy, c gz, c gx);
-                    //                 jd=2 -> (2,3,4) = (gz, c gy, c gx)
-                    const int r1 = jd == 0 ? 4 : 3, r2 = jd == 2 ? 4 : 5;
-                    const double b0 = gb[jd];
-                    const double b1 = kInvSqrt2 * gb[jd == 2 ? 1 : 2];
-                    const double b2 = kInvSqrt2 * gb[jd == 0 ? 1 : 0];
+                    const double bx = gp[b * GS], by = gp[b * GS + 1], bz = gp[b * GS + 2];
+                    const double hx = kInvSqrt2 * bx, hy = kInvSqrt2 * by, hz = kInvSqrt2 * bz;
                     EFB_UNROLL
-                    for (int s = 0; s < NS; ++s)
-                        cb[s] = w * (Cp[s * NS + jd] * b0 + Cp[s * NS + r1] * b1 + Cp[s * NS + r2] * b2);
-                    cb[3] *= kInvSqrt2;
-                    cb[4] *= kInvSqrt2;
-                    cb[5] *= kInvSqrt2;
+                    for (int s = 0; s < NS; ++s) {
+                        // B[:, (b,0)] = (bx,0,0,0,hz,hy); B[:, (b,1)] = (0,by,0,hz,0,hx); B[:, (b,2)] = (0,0,bz,hy,hx,0)
+                        cb[0][s] = w * (EFB_C(s, 0) * bx + EFB_C(s, 4) * hz + EFB_C(s, 5) * hy);
+                        cb[1][s] = w * (EFB_C(s, 1) * by + EFB_C(s, 3) * hz + EFB_C(s, 5) * hx);
+                        cb[2][s] = w * (EFB_C(s, 2) * bz + EFB_C(s, 3) * hy + EFB_C(s, 4) * hx);
+                    }
                     EFB_UNROLL
-                    for (int a = 0; a < NPE; ++a) {
-                        const double gx = gp[a * 3], gy = gp[a * 3 + 1], gz = gp[a * 3 + 2];
-                        acc[a * 3 + 0] += gx * cb[0] + gz * cb[4] + gy * cb[5];
-                        acc[a * 3 + 1] += gy * cb[1] + gz * cb[3] + gx * cb[5];
-                        acc[a * 3 + 2] += gz * cb[2] + gy * cb[3] + gx * cb[4];
+                    for (int jd = 0; jd < 3; ++jd) {
+                        cb[jd][3] *= kInvSqrt2;
+                        cb[jd][4] *= kInvSqrt2;
+                        cb[jd][5] *= kInvSqrt2;
+                    }
+                    EFB_UNROLL
+                    for (int a = 0; a < NA; ++a) {
+                        const Pair gxy = *reinterpret_cast<const Pair*>(gp + (a0 + a) * GS);
+                        const double gx = gxy.x, gy = gxy.y, gz = gp[(a0 + a) * GS + 2];
+                        EFB_UNROLL
+                        for (int jd = 0; jd < 3; ++jd) {
+                            acc[a * 3 + 0][jd] += gx * cb[jd][0] + gz * cb[jd][4] + gy * cb[jd][5];
+                            acc[a * 3 + 1][jd] += gy * cb[jd][1] + gz * cb[jd][3] + gx * cb[jd][5];
+                            acc[a * 3 + 2][jd] += gz * cb[jd][2] + gy * cb[jd][3] + gx * cb[jd][4];
+                        }
                     }
                 }
+#undef EFB_C
             }
-            double* dst = out + e * (long long)(NDOF * NDOF) + j;
+            double* dst = out + e * (long long)(NDOF * NDOF) + (long long)(a0 * DIM) * NDOF + b * DIM;
             EFB_UNROLL
-            for (int i = 0; i < NDOF; ++i) dst[i * NDOF] = scale * acc[i];
+            for (int i = 0; i < NA * DIM; ++i)
+                EFB_UNROLL
+                for (int j = 0; j < DIM; ++j) dst[i * NDOF + j] = scale * acc[i][j];
         }
     }
 }
@@ -366,7 +422,7 @@ EFB_D void scalar_block(const GroupView& g, const ScalarOp& op, int EPB, long lo
                 }
                 if (op.has_k) {
                     const double c = coef_at(op.k, op.k_mode, op.k_scalar, e, p, nPg) * w;
-                    const double* gb = gN + (p * NPE + b) * DIM;
+                    const double* gb = gN + (p * NPE + b) * SmemMap<DIM, NPE>::GS;
                     double Ag[DIM];
                     if (op.A) {
                         const double* Ap = op.A + (op.A_mode == 0 ? 0 : (op.A_mode == 1 ? e * DIM * DIM : (e * nPg + p) * (long long)(DIM * DIM)));
@@ -383,7 +439,7 @@ EFB_D void scalar_block(const GroupView& g, const ScalarOp& op, int EPB, long lo
                     }
                     EFB_UNROLL
                     for (int a = 0; a < NPE; ++a) {
-                        const double* ga = gN + (p * NPE + a) * DIM;
+                        const double* ga = gN + (p * NPE + a) * SmemMap<DIM, NPE>::GS;
                         double s = 0.0;
                         EFB_UNROLL
                         for (int i = 0; i < DIM; ++i) s += ga[i] * Ag[i];
@@ -458,7 +514,7 @@ EFB_D void strain_block(const GroupView& g, const int* EFB_RESTRICT connect_dof,
                 const int p = i / NS, s = i % NS;
                 double acc = 0.0;
                 for (int a = 0; a < NPE; ++a) {
-                    const double* ga = gN + (p * NPE + a) * DIM;
+                    const double* ga = gN + (p * NPE + a) * SmemMap<DIM, NPE>::GS;
                     EFB_UNROLL
                     for (int d = 0; d < DIM; ++d) acc += B_entry<DIM>(s, d, ga) * ue[a * DIM + d];
                 }
@@ -495,7 +551,7 @@ EFB_D void internal_force_block(const GroupView& g, const double* EFB_RESTRICT s
             const int a = t / DIM, d = t % DIM;
             double acc = 0.0;
             for (int p = 0; p < nPg; ++p) {
-                const double* ga = gN + (p * NPE + a) * DIM;
+                const double* ga = gN + (p * NPE + a) * SmemMap<DIM, NPE>::GS;
                 double s = 0.0;
                 EFB_UNROLL
                 for (int k = 0; k < NS; ++k) s += B_entry<DIM>(k, d, ga) * sg[p * NS + k];

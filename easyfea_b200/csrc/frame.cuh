@@ -13,12 +13,17 @@
 #define EFB_D __device__ __forceinline__
 // run the following statement once for this thread, then barrier
 #define EFB_PHASE(tid, nthreads) for (int tid = threadIdx.x, _efb_once = 1; _efb_once; _efb_once = 0, __syncthreads())
+// same, but when `warp_local` (every element's threads sit inside one warp) a warp barrier is enough, so the warps of
+// a CTA drift apart and one warp's geometry phases overlap another warp's FP64 main loop
+#define EFB_PHASE_E(tid, nthreads, warp_local) \
+    for (int tid = threadIdx.x, _efb_once = 1; _efb_once; _efb_once = 0, ((warp_local) ? __syncwarp() : __syncthreads()))
 #define EFB_RESTRICT __restrict__
 #define EFB_UNROLL _Pragma("unroll")
 #else
 #define EFB_HD inline
 #define EFB_D inline
 #define EFB_PHASE(tid, nthreads) for (int tid = 0; tid < (nthreads); ++tid)
+#define EFB_PHASE_E(tid, nthreads, warp_local) for (int tid = 0; tid < (nthreads); ++tid)
 #define EFB_RESTRICT
 #define EFB_UNROLL
 #endif

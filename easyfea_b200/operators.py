@@ -8,6 +8,7 @@ ndarray out.  `*_dev` variants take and return torch CUDA tensors for device-res
 """
 from __future__ import annotations
 
+import ctypes
 import numbers
 
 import numpy as np
@@ -82,11 +83,15 @@ def elastic_Ke_dev(groupElem, C, matrixType=RIGI, scale=1.0, out=None):
     mt = _mt(matrixType)
     ns = 3 if dg.dim == 2 else 6
     Carr, mode = tensor_mode(C, dg.Ne, dg.nPg(mt), ns)
-    Cd = dv.to_device(Carr)
     ndof = dg.nPe * dg.dim
     if out is None:
         out = dv.empty((dg.Ne, ndof, ndof))
-    _lib.call("efb_elastic_Ke", dg.cstruct(mt), dv.ptr(Cd), mode, float(scale), dv.ptr(out), dv.stream_ptr())
+    if mode == 0:  # homogeneous C: by value through the kernel arguments, no device copy needed
+        Ch = np.ascontiguousarray(Carr.cpu().numpy() if isinstance(Carr, torch.Tensor) else Carr, dtype=np.float64)
+        _lib.call("efb_elastic_Ke", dg.cstruct(mt), None, ctypes.c_void_p(Ch.ctypes.data), 0, float(scale), dv.ptr(out), dv.stream_ptr())
+    else:
+        Cd = dv.to_device(Carr)
+        _lib.call("efb_elastic_Ke", dg.cstruct(mt), dv.ptr(Cd), None, mode, float(scale), dv.ptr(out), dv.stream_ptr())
     return out
 
 

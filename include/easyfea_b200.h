@@ -58,8 +58,10 @@ int efb_geometry(const efb_group* g, double* F, double* detF, double* jac, doubl
 
 /* ---- O1-O4: operators, EasyFEA/FEM/Operators/Bilinear.py, Linear.py ---------------------------------- */
 /* LinearizedElasticity Bilinear.py:62-79: out (Ne,ndof,ndof) = scale * sum_p wJ B^T C B; C (ns,ns) with leading
- * axes per C_mode. */
-int efb_elastic_Ke(const efb_group* g, const double* C, int C_mode, double scale, double* out, void* stream);
+ * axes per C_mode (device).  A homogeneous C (EFB_TENSOR_CONST) is passed to the kernel by value: give its ns*ns
+ * values in C_host (HOST pointer; then C may be NULL), otherwise they are fetched from C with a stream sync. */
+int efb_elastic_Ke(const efb_group* g, const double* C, const double* C_host, int C_mode, double scale, double* out,
+                   void* stream);
 /* UV Bilinear.py:42-59: out (Ne,ndof,ndof) = scale * sum_p coef wJ N^T N, N block-diagonal for dof_n>1.
  * coef: device array per coef_mode, or NULL with the value in coef_scalar. */
 int efb_mass_Me(const efb_group* g, const double* coef, int coef_mode, double coef_scalar, int dof_n, double scale,

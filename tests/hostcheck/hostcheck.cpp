@@ -50,16 +50,26 @@ extern "C" int hc_geometry(const efb_group* g, double* F, double* detF, double* 
     return 2;
 }
 
+template <int D, int N, int CMODE>
+static void run_elastic(const efb_group* g, const double* C, double scale, double* out) {
+    constexpr int NS = StrainSize<D>::value;
+    const int TPE = ElasticTile<D, N>::TPE, EPB = epb_for(TPE);
+    SmemMap<D, N> sm(g->nPg, EPB, CMODE == 2 ? g->nPg * NS * NS : (CMODE == 1 ? NS * NS : 0));
+    std::vector<double> smem(sm.total());
+    CMat Cc;
+    memset(&Cc, 0, sizeof(Cc));
+    if (CMODE == 0) memcpy(Cc.v, C, sizeof(double) * NS * NS);
+    for (long long b = 0; b * EPB < g->Ne; ++b)
+        elastic_block<D, N, CMODE>(view_of(g), Cc, C, scale, out, EPB, b, EPB * TPE, smem.data());
+}
+
 extern "C" int hc_elastic_Ke(const efb_group* g, const double* C, int C_mode, double scale, double* out) {
-#define X(D, N)                                                                                       \
-    if (g->dim == D && g->nPe == N) {                                                                 \
-        constexpr int NS = StrainSize<D>::value;                                                      \
-        const int TPE = D * N, EPB = epb_for(TPE);                                                    \
-        SmemMap<D, N> sm(g->nPg, EPB, C_mode == 2 ? g->nPg * NS * NS : NS * NS);                      \
-        std::vector<double> smem(sm.total());                                                         \
-        for (long long b = 0; b * EPB < g->Ne; ++b)                                                   \
-            elastic_block<D, N>(view_of(g), C, C_mode, scale, out, EPB, b, EPB * TPE, smem.data());   \
-        return 0;                                                                                     \
+#define X(D, N)                                                       \
+    if (g->dim == D && g->nPe == N) {                                 \
+        if (C_mode == 0) run_elastic<D, N, 0>(g, C, scale, out);      \
+        else if (C_mode == 1) run_elastic<D, N, 1>(g, C, scale, out); \
+        else run_elastic<D, N, 2>(g, C, scale, out);                  \
+        return 0;                                                     \
     }
     FOR_EACH(X)
 #undef X
@@ -245,8 +255,16 @@ extern "C" void hc_replay_matrix(void* p, int n_groups, const double* const* dat
     GroupTable T;
     make_table(T, n_groups, nullptr, data, Ne, nPe, d);
     std::vector<double> acc((size_t)d * d * P->max_deg);
-    for (long long n = 0; n < Nn; ++n)
+    for (long long n = 0; n < Nn; ++n) {
+#define FAST(D, N)                                                                                                          \
+    if (n_groups == 1 && d == D && nPe[0] == N) {                                                                           \
+        replay_node_fast<D, N, 4>(data[0], n, P->rowptr.data(), P->qlist.data(), P->adjptr.data(), P->pos.data(), acc.data(), out); \
+        continue;                                                                                                           \
+    }
+        FAST(3, 8) FAST(3, 4) FAST(3, 27) FAST(2, 3) FAST(2, 9) FAST(1, 3) FAST(1, 8) FAST(1, 27)
+#undef FAST
         replay_node(T, d, n, P->rowptr.data(), P->qlist.data(), P->adjptr.data(), P->pos.data(), acc.data(), out);
+    }
 }
 
 extern "C" void hc_replay_vector(void* p, int n_groups, const double* const* data, const int64_t* Ne, const int32_t* nPe, int d,
