@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libeasyfea_b200.so")
+# EASYFEA_B200_LIB: development override used by scripts/ to time alternative builds of the same C ABI
+LIB_PATH = os.environ.get("EASYFEA_B200_LIB") or os.path.join(_HERE, "libeasyfea_b200.so")
 
 c_i32, c_i64, c_f64, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
 

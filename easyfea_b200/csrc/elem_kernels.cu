@@ -61,23 +61,48 @@ static int launch_geometry(const efb_group* g, const GeomOut& o, cudaStream_t st
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// persistent: each CTA walks element batches blockIdx.x, blockIdx.x + gridDim.x, ...; the reference-element tables are
+// staged once per CTA, and for warp-local element types the warps of a CTA run their batches independently
+constexpr int kElasticThreads = 128;
+
 template <int DIM, int NPE, int CMODE>
-__global__ void __launch_bounds__(256) k_elastic(GroupView g, CMat Cconst, const double* C, double scale, double* out, int EPB) {
+__global__ void __launch_bounds__(kElasticThreads) k_elastic(GroupView g, CMat C2, const double* C, double scale, double* out, int EPB,
+                                                              long long nblk) {
     extern __shared__ double smem[];
-    elastic_block<DIM, NPE, CMODE>(g, Cconst, C, scale, out, EPB, blockIdx.x, blockDim.x, smem);
+    bool first = true;
+    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        elastic_block<DIM, NPE, CMODE>(g, C2, C, scale, out, EPB, blk, blockDim.x, smem, first);
+        first = false;
+    }
+}
+
+// CTAs that keep every SM full: resident CTAs per SM (occupancy query) x number of SMs
+template <class K>
+static long long persistent_grid(K kernel, int threads, size_t smem_bytes, long long nblk) {
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem_bytes) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const long long full = (long long)sms * per_sm;
+    return nblk < full ? nblk : full;
 }
 
 template <int DIM, int NPE, int CMODE>
-static int launch_elastic_mode(const efb_group* g, const CMat& Cconst, const double* C, double scale, double* out, cudaStream_t st) {
+static int launch_elastic_mode(const efb_group* g, const CMat& C2, const double* C, double scale, double* out, cudaStream_t st) {
     constexpr int NS = StrainSize<DIM>::value;
+    using SM = ElasticSmem<DIM, NPE>;
     const int extra = CMODE == 2 ? g->nPg * NS * NS : (CMODE == 1 ? NS * NS : 0);
-    const int TPE = ElasticTile<DIM, NPE>::TPE, EPB = elems_per_block<DIM, NPE>(TPE, g->nPg, extra);
-    const SmemMap<DIM, NPE> sm(g->nPg, EPB, extra);
+    const int TPE = ElasticTile<DIM, NPE>::TPE;
+    int EPB = kElasticThreads / TPE;
+    if (EPB < 1) EPB = 1;
+    while (EPB > 1 && SM(g->nPg, EPB, extra).total() * sizeof(double) > 100 * 1024) --EPB;
+    const SM sm(g->nPg, EPB, extra);
     const size_t bytes = sizeof(double) * sm.total();
     if (ensure_smem(k_elastic<DIM, NPE, CMODE>, bytes)) return 1;
     const long long nblk = (g->Ne + EPB - 1) / EPB;
     if (nblk == 0) return 0;
-    k_elastic<DIM, NPE, CMODE><<<(unsigned)nblk, EPB * TPE, bytes, st>>>(view_of(g), Cconst, C, scale, out, EPB);
+    const long long grid = persistent_grid(k_elastic<DIM, NPE, CMODE>, EPB * TPE, bytes, nblk);
+    k_elastic<DIM, NPE, CMODE><<<(unsigned)grid, EPB * TPE, bytes, st>>>(view_of(g), C2, C, scale, out, EPB, nblk);
     return check_launch("efb_elastic_Ke");
 }
 
@@ -99,6 +124,7 @@ static int launch_elastic(const efb_group* g, const double* C, const double* C_h
                 return 1;
             }
         }
+        prescale_C<DIM>(Cconst);  // Kelvin-Mandel C -> S C S (elem_kernels.cuh, O1)
         return launch_elastic_mode<DIM, NPE, 0>(g, Cconst, C, scale, out, st);
     }
     if (C_mode == 1) return launch_elastic_mode<DIM, NPE, 1>(g, Cconst, C, scale, out, st);

@@ -236,11 +236,14 @@ EFB_D void geometry_block(const GroupView& g, const GeomOut& o, int EPB, long lo
 // ---------------------------------------------------------------------------------------------------------
 // O1: K_e = scale * sum_p wJ B^T C B                                   Operators/Bilinear.py:62-79
 //
-// Register tiling: thread (b, h) of an element owns the DIM columns of node b and the rows of NA = NPE/RSPLIT nodes
-// (chunk h), i.e. NA*DIM*DIM accumulators.  Per Gauss point it forms cb[jd] = wJ C B[:, (b,jd)] (dim non-zeros per B
-// column) once and then spends DIM FMAs per accumulator; the only shared-memory traffic of the inner loop is one
-// broadcast read of the NA row-node gradients.  A homogeneous C (mode 0) is a kernel argument and is read from the
-// constant bank; per-element / per-Gauss-point C is staged in shared memory.
+// Thread (a, h) of an element owns the DIM rows of node a and the columns of NB = NPE/CSPLIT nodes (chunk h), i.e.
+// DIM*NB*DIM accumulators.  With S = diag(1,..,1, 1/sqrt2,..) the Kelvin-Mandel operator is B = S G, G holding the plain
+// gradients (DIM non-zeros per column), so K_e = sum_p w G^T (S C S) G: the kernel receives C2 = S C S.  Per Gauss
+// point a thread forms bc[i][:] = w G[:, (a,i)]^T C2 once (3 DIM NS flops) and then spends exactly DIM FMAs per
+// accumulator; the only shared-memory traffic of the inner loop is one broadcast read of the NB column-node gradients.
+// Geometry is one phase: thread p of an element takes Gauss point p — F, det, F^-1 stay in registers and only
+// w|det F| and the physical gradients go to shared memory.  A homogeneous C2 (mode 0) is a kernel argument (constant
+// bank); per-element / per-Gauss-point C is staged in shared memory, scaled to C2 on the way.
 // ---------------------------------------------------------------------------------------------------------
 struct CMat {
     double v[36];
@@ -250,40 +253,132 @@ struct alignas(16) Pair {
     double x, y;
 };
 
+// C -> S C S in place (row-major ns x ns)
+template <int DIM>
+EFB_HD double kelvin_factor(int s, int r) {
+    const bool a = s >= DIM, b = r >= DIM;
+    return (a && b) ? 0.5 : ((a || b) ? kInvSqrt2 : 1.0);
+}
+
+template <int DIM>
+inline void prescale_C(CMat& C) {
+    constexpr int NS = StrainSize<DIM>::value;
+    for (int s = 0; s < NS; ++s)
+        for (int r = 0; r < NS; ++r) C.v[s * NS + r] *= kelvin_factor<DIM>(s, r);
+}
+
 template <int DIM, int NPE>
 struct ElasticTile {
-    // rows are split so that a thread keeps at most ~90 accumulators
-    static constexpr int RSPLIT = (DIM == 2) ? 1 : (NPE == 8 ? 2 : NPE == 27 ? 3 : NPE == 20 ? 2 : NPE == 18 ? 2 : NPE == 15 ? 3 : 1);
-    static constexpr int NA = NPE / RSPLIT;
-    static constexpr int TPE = NPE * RSPLIT;
-    static_assert(NA * RSPLIT == NPE, "RSPLIT must divide NPE");
+    // columns are split so that a thread keeps at most ~81 accumulators
+#ifndef EFB_HEXA8_CSPLIT
+#define EFB_HEXA8_CSPLIT 1
+#endif
+    static constexpr int CSPLIT =
+        (DIM == 2) ? 1 : (NPE == 8 ? EFB_HEXA8_CSPLIT : NPE == 27 ? 3 : NPE == 20 ? 4 : NPE == 18 ? 2 : NPE == 15 ? 3 : NPE == 10 ? 2 : 1);
+    static constexpr int NB = NPE / CSPLIT;
+    static constexpr int TPE = NPE * CSPLIT;
+    static_assert(NB * CSPLIT == NPE, "CSPLIT must divide NPE");
+};
+
+// shared-memory map of the stiffness kernel (offsets in doubles)
+template <int DIM, int NPE>
+struct ElasticSmem {
+    static constexpr int GS = (DIM == 3) ? 4 : 2;     // doubles per node in gN (3D padded to 4: two 16-byte loads)
+    static constexpr int TS = (DIM * NPE) | 1;        // odd stride of one Gauss point in the dN table: the threads of an
+                                                      // element read different Gauss points without bank conflicts
+    static constexpr int GPS = NPE * GS + 2;          // stride of one Gauss point in gN (same reason, keeps 16-byte alignment)
+    int nPg, EPB, extra;
+    EFB_HD ElasticSmem(int nPg_, int EPB_, int extra_) : nPg(nPg_), EPB(EPB_), extra(extra_) {}
+    EFB_HD int off_dN() const { return 0; }
+    EFB_HD int off_w() const { return nPg * TS; }
+    EFB_HD int tables_padded() const { return (off_w() + nPg + 1) & ~1; }
+    EFB_HD int o_X() const { return 0; }
+    EFB_HD int o_wJ() const { return NPE * DIM; }
+    EFB_HD int o_gN() const { return (o_wJ() + nPg + 1) & ~1; }
+    EFB_HD int o_extra() const { return o_gN() + nPg * GPS; }
+    // stride = 2 (mod 4) doubles: the same field of the elements sharing a warp starts in distinct 16-byte bank groups
+    EFB_HD int per_elem() const {
+        int n = (o_extra() + extra + 1) & ~1;
+        return (n % 4 == 2) ? n : n + 2;
+    }
+    EFB_HD int total() const { return tables_padded() + EPB * per_elem(); }
+    EFB_HD double* elem(double* smem, int el) const { return smem + tables_padded() + el * per_elem(); }
 };
 
 template <int DIM, int NPE, int CMODE>
-EFB_D void elastic_block(const GroupView& g, const CMat& Cconst, const double* EFB_RESTRICT C, double scale,
-                         double* EFB_RESTRICT out, int EPB, long long blockId, int nthreads, double* smem) {
+EFB_D void elastic_block(const GroupView& g, const CMat& C2const, const double* EFB_RESTRICT C, double scale,
+                         double* EFB_RESTRICT out, int EPB, long long blockId, int nthreads, double* smem,
+                         bool load_tables = true) {
     constexpr int NS = StrainSize<DIM>::value, NDOF = DIM * NPE, NC = NS * NS;
-    constexpr int GS = SmemMap<DIM, NPE>::GS;
+    using SM = ElasticSmem<DIM, NPE>;
     using Tile = ElasticTile<DIM, NPE>;
-    constexpr int NA = Tile::NA, TPE = Tile::TPE;
+    constexpr int GS = SM::GS, TS = SM::TS, GPS = SM::GPS;
+    constexpr int NB = Tile::NB, TPE = Tile::TPE;
     const int nPg = g.nPg;
     const int extra = CMODE == 2 ? nPg * NC : (CMODE == 1 ? NC : 0);
-    const SmemMap<DIM, NPE> sm(nPg, EPB, extra);
+    const SM sm(nPg, EPB, extra);
     const long long e0 = blockId * EPB;
-    constexpr bool kWarpLocal = (32 % TPE == 0);  // an element never straddles two warps
-    geometry_phases<DIM, NPE>(g, sm, e0, TPE, nthreads, smem, true, kWarpLocal);
-    if (CMODE != 0) {
-        EFB_PHASE_E(tid, nthreads, kWarpLocal) {  // stage C (contiguous over the elements of the CTA)
-            const int el = tid / TPE, t = tid % TPE;
-            const long long e = e0 + el;
-            if (el < EPB && e < g.Ne) {
-                double* Cs = sm.elem(smem, el) + sm.o_extra();
+    constexpr bool kWarpLocal = (32 % TPE == 0);  // an element never straddles two warps: warp barriers are enough
+    double* dNt = smem + sm.off_dN();
+    double* wt = smem + sm.off_w();
+
+    if (load_tables) {
+        EFB_PHASE(tid, nthreads) {
+            for (int i = tid; i < nPg * DIM * NPE; i += nthreads) dNt[(i / (DIM * NPE)) * TS + i % (DIM * NPE)] = g.dN_pg[i];
+            for (int i = tid; i < nPg; i += nthreads) wt[i] = g.w_pg[i];
+        }
+    }
+    EFB_PHASE_E(tid, nthreads, kWarpLocal) {  // gather the nodal coordinates (and C)
+        const int el = tid / TPE, t = tid % TPE;
+        const long long e = e0 + el;
+        if (el < EPB && e < g.Ne) {
+            double* E = sm.elem(smem, el);
+            for (int a = t; a < NPE; a += TPE) {
+                const double* src = g.coord + (long long)g.connect[e * NPE + a] * g.coord_stride;
+                EFB_UNROLL
+                for (int d = 0; d < DIM; ++d) E[sm.o_X() + a * DIM + d] = src[d];
+            }
+            if (CMODE != 0) {
+                double* Cs = E + sm.o_extra();
                 const double* src = CMODE == 1 ? C + e * NC : C + e * (long long)(nPg * NC);
-                for (int i = t; i < extra; i += TPE) Cs[i] = src[i];
+                for (int i = t; i < extra; i += TPE) Cs[i] = src[i] * kelvin_factor<DIM>((i % NC) / NS, i % NS);
             }
         }
     }
-    EFB_PHASE(tid, nthreads) {
+    EFB_PHASE_E(tid, nthreads, kWarpLocal) {  // G2-G6 per Gauss point, in registers    _group_elem.py:832-1105
+        const int el = tid / TPE, t = tid % TPE;
+        if (el < EPB && e0 + el < g.Ne) {
+            double* E = sm.elem(smem, el);
+            const double* X = E + sm.o_X();
+            for (int p = t; p < nPg; p += TPE) {
+                const double* dNp = dNt + p * TS;
+                double F[DIM * DIM], Fi[DIM * DIM];
+                EFB_UNROLL
+                for (int i = 0; i < DIM * DIM; ++i) F[i] = 0.0;
+                EFB_UNROLL
+                for (int n = 0; n < NPE; ++n) {  // F[r][c] = sum_n dN[p][r][n] x[n][c]
+                    EFB_UNROLL
+                    for (int r = 0; r < DIM; ++r)
+                        EFB_UNROLL
+                        for (int c = 0; c < DIM; ++c) F[r * DIM + c] += dNp[r * NPE + n] * X[n * DIM + c];
+                }
+                const double det = det_inv<DIM>(F, Fi);
+                E[sm.o_wJ() + p] = scale * (fabs(det) * wt[p]);
+                double* gp = E + sm.o_gN() + p * GPS;
+                EFB_UNROLL
+                for (int a = 0; a < NPE; ++a) {  // gN[a][d] = sum_k Fi[d][k] dN[p][k][a]
+                    EFB_UNROLL
+                    for (int d = 0; d < DIM; ++d) {
+                        double s = 0.0;
+                        EFB_UNROLL
+                        for (int k = 0; k < DIM; ++k) s += Fi[d * DIM + k] * dNp[k * NPE + a];
+                        gp[a * GS + d] = s;
+                    }
+                }
+            }
+        }
+    }
+    EFB_PHASE_E(tid, nthreads, kWarpLocal) {
         const int el = tid / TPE, t = tid % TPE;
         const long long e = e0 + el;
         if (el < EPB && e < g.Ne) {
@@ -291,72 +386,91 @@ EFB_D void elastic_block(const GroupView& g, const CMat& Cconst, const double* E
             const double* wJ = E + sm.o_wJ();
             const double* gN = E + sm.o_gN();
             const double* Cs = E + sm.o_extra();
-            const int b = t % NPE, a0 = (t / NPE) * NA;
-            double acc[NA * DIM][DIM];
+            const int a = t % NPE, b0 = (t / NPE) * NB;
+            double acc[DIM][NB * DIM];
             EFB_UNROLL
-            for (int i = 0; i < NA * DIM; ++i)
+            for (int i = 0; i < DIM; ++i)
                 EFB_UNROLL
-                for (int j = 0; j < DIM; ++j) acc[i][j] = 0.0;
+                for (int j = 0; j < NB * DIM; ++j) acc[i][j] = 0.0;
             for (int p = 0; p < nPg; ++p) {
-                const double* gp = gN + p * NPE * GS;
+                const double* gp = gN + p * GPS;
                 const double w = wJ[p];
-                // C(s, r) of this Gauss point: constant bank (mode 0) or shared memory
-#define EFB_C(s_, r_) (CMODE == 0 ? Cconst.v[(s_) * NS + (r_)] : Cs[(CMODE == 2 ? p * NC : 0) + (s_) * NS + (r_)])
-                double cb[DIM][NS];
+                // C2(s, r) of this Gauss point: constant bank (mode 0) or shared memory
+#define EFB_C(s_, r_) (CMODE == 0 ? C2const.v[(s_) * NS + (r_)] : Cs[(CMODE == 2 ? p * NC : 0) + (s_) * NS + (r_)])
+                double bc[DIM][NS];
                 if constexpr (DIM == 2) {
-                    const double bx = gp[b * GS], by = gp[b * GS + 1];
-                    const double hx = kInvSqrt2 * bx, hy = kInvSqrt2 * by;
+                    // G[:, (a,0)] = (gx, 0, gy); G[:, (a,1)] = (0, gy, gx)
+                    const double wx = w * gp[a * GS], wy = w * gp[a * GS + 1];
                     EFB_UNROLL
-                    for (int s = 0; s < NS; ++s) {
-                        cb[0][s] = w * (EFB_C(s, 0) * bx + EFB_C(s, 2) * hy);
-                        cb[1][s] = w * (EFB_C(s, 1) * by + EFB_C(s, 2) * hx);
+                    for (int r = 0; r < NS; ++r) {
+                        bc[0][r] = wx * EFB_C(0, r) + wy * EFB_C(2, r);
+                        bc[1][r] = wy * EFB_C(1, r) + wx * EFB_C(2, r);
                     }
-                    cb[0][2] *= kInvSqrt2;
-                    cb[1][2] *= kInvSqrt2;
                     EFB_UNROLL
-                    for (int a = 0; a < NA; ++a) {
-                        const Pair ga = *reinterpret_cast<const Pair*>(gp + (a0 + a) * GS);
+                    for (int b = 0; b < NB; ++b) {
+                        const Pair gb = *reinterpret_cast<const Pair*>(gp + (b0 + b) * GS);
                         EFB_UNROLL
-                        for (int jd = 0; jd < 2; ++jd) {
-                            acc[a * 2 + 0][jd] += ga.x * cb[jd][0] + ga.y * cb[jd][2];
-                            acc[a * 2 + 1][jd] += ga.y * cb[jd][1] + ga.x * cb[jd][2];
+                        for (int i = 0; i < 2; ++i) {
+                            double s0 = acc[i][b * 2 + 0], s1 = acc[i][b * 2 + 1];
+                            s0 += bc[i][0] * gb.x;
+                            s0 += bc[i][2] * gb.y;
+                            s1 += bc[i][1] * gb.y;
+                            s1 += bc[i][2] * gb.x;
+                            acc[i][b * 2 + 0] = s0;
+                            acc[i][b * 2 + 1] = s1;
                         }
                     }
                 } else {
-                    const double bx = gp[b * GS], by = gp[b * GS + 1], bz = gp[b * GS + 2];
-                    const double hx = kInvSqrt2 * bx, hy = kInvSqrt2 * by, hz = kInvSqrt2 * bz;
+                    // G[:, (a,0)] = (gx,0,0,0,gz,gy); G[:, (a,1)] = (0,gy,0,gz,0,gx); G[:, (a,2)] = (0,0,gz,gy,gx,0)
+                    const double wx = w * gp[a * GS], wy = w * gp[a * GS + 1], wz = w * gp[a * GS + 2];
                     EFB_UNROLL
-                    for (int s = 0; s < NS; ++s) {
-                        // B[:, (b,0)] = (bx,0,0,0,hz,hy); B[:, (b,1)] = (0,by,0,hz,0,hx); B[:, (b,2)] = (0,0,bz,hy,hx,0)
-                        cb[0][s] = w * (EFB_C(s, 0) * bx + EFB_C(s, 4) * hz + EFB_C(s, 5) * hy);
-                        cb[1][s] = w * (EFB_C(s, 1) * by + EFB_C(s, 3) * hz + EFB_C(s, 5) * hx);
-                        cb[2][s] = w * (EFB_C(s, 2) * bz + EFB_C(s, 3) * hy + EFB_C(s, 4) * hx);
+                    for (int r = 0; r < NS; ++r) {
+                        bc[0][r] = wx * EFB_C(0, r) + wz * EFB_C(4, r) + wy * EFB_C(5, r);
+                        bc[1][r] = wy * EFB_C(1, r) + wz * EFB_C(3, r) + wx * EFB_C(5, r);
+                        bc[2][r] = wz * EFB_C(2, r) + wy * EFB_C(3, r) + wx * EFB_C(4, r);
                     }
                     EFB_UNROLL
-                    for (int jd = 0; jd < 3; ++jd) {
-                        cb[jd][3] *= kInvSqrt2;
-                        cb[jd][4] *= kInvSqrt2;
-                        cb[jd][5] *= kInvSqrt2;
-                    }
-                    EFB_UNROLL
-                    for (int a = 0; a < NA; ++a) {
-                        const Pair gxy = *reinterpret_cast<const Pair*>(gp + (a0 + a) * GS);
-                        const double gx = gxy.x, gy = gxy.y, gz = gp[(a0 + a) * GS + 2];
+                    for (int b = 0; b < NB; ++b) {
+                        const Pair gxy = *reinterpret_cast<const Pair*>(gp + (b0 + b) * GS);
+                        const double gx = gxy.x, gy = gxy.y, gz = gp[(b0 + b) * GS + 2];
                         EFB_UNROLL
-                        for (int jd = 0; jd < 3; ++jd) {
-                            acc[a * 3 + 0][jd] += gx * cb[jd][0] + gz * cb[jd][4] + gy * cb[jd][5];
-                            acc[a * 3 + 1][jd] += gy * cb[jd][1] + gz * cb[jd][3] + gx * cb[jd][5];
-                            acc[a * 3 + 2][jd] += gz * cb[jd][2] + gy * cb[jd][3] + gx * cb[jd][4];
+                        for (int i = 0; i < 3; ++i) {
+                            double s0 = acc[i][b * 3 + 0], s1 = acc[i][b * 3 + 1], s2 = acc[i][b * 3 + 2];
+                            s0 += bc[i][0] * gx;
+                            s0 += bc[i][4] * gz;
+                            s0 += bc[i][5] * gy;
+                            s1 += bc[i][1] * gy;
+                            s1 += bc[i][3] * gz;
+                            s1 += bc[i][5] * gx;
+                            s2 += bc[i][2] * gz;
+                            s2 += bc[i][3] * gy;
+                            s2 += bc[i][4] * gx;
+                            acc[i][b * 3 + 0] = s0;
+                            acc[i][b * 3 + 1] = s1;
+                            acc[i][b * 3 + 2] = s2;
                         }
                     }
                 }
 #undef EFB_C
             }
-            double* dst = out + e * (long long)(NDOF * NDOF) + (long long)(a0 * DIM) * NDOF + b * DIM;
+            // rows (a,i) of K_e, columns of the NB nodes of this chunk: NB*DIM contiguous doubles per row
+            double* dst = out + e * (long long)(NDOF * NDOF) + (long long)(a * DIM) * NDOF + b0 * DIM;
+            constexpr bool kVec = (NDOF % 2 == 0) && ((NB * DIM) % 2 == 0);
             EFB_UNROLL
-            for (int i = 0; i < NA * DIM; ++i)
-                EFB_UNROLL
-                for (int j = 0; j < DIM; ++j) dst[i * NDOF + j] = scale * acc[i][j];
+            for (int i = 0; i < DIM; ++i) {
+                if constexpr (kVec) {
+                    EFB_UNROLL
+                    for (int j = 0; j < NB * DIM; j += 2) {
+                        Pair v;
+                        v.x = acc[i][j];
+                        v.y = acc[i][j + 1];
+                        *reinterpret_cast<Pair*>(dst + i * NDOF + j) = v;
+                    }
+                } else {
+                    EFB_UNROLL
+                    for (int j = 0; j < NB * DIM; ++j) dst[i * NDOF + j] = acc[i][j];
+                }
+            }
         }
     }
 }
