@@ -1,0 +1,165 @@
+"""Pin the NumPy oracle against the LIVE reference (EasyFEA v3.5.1 at /root/reference, gmsh stubbed) on fresh seeded
+meshes — larger and differently seeded than the committed golden fixtures.  Skipped where the reference is absent
+(the GPU box); there the fixtures of tests/golden/ stand in (tests/test_oracle_golden.py).
+
+The reference's own property tests for this path are re-run on the oracle outputs too
+(tests/Models/phasefield_test.py:90-137: cP + cM == C, psi split consistency)."""
+import numpy as np
+import pytest
+
+from oracle import easyfea_oracle as orc
+from oracle.ref_import import import_reference, reference_available
+from tests.helpers import make_mesh, rel_err
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="live reference (/root/reference) not present")
+
+TOL = 1e-12
+CASES = ["TRI3", "QUAD9", "TETRA4", "HEXA8", "HEXA27"]
+
+
+@pytest.fixture(scope="module")
+def ref():
+    import_reference()
+    import EasyFEA
+    from EasyFEA import Models, Simulations
+    from EasyFEA.FEM import ElemType, FeArray, GroupElemFactory, MatrixType, Mesh, Operators
+
+    class R:
+        pass
+
+    R.Models, R.Simulations, R.ElemType, R.FeArray = Models, Simulations, ElemType, FeArray
+    R.GroupElemFactory, R.MatrixType, R.Mesh, R.Operators = GroupElemFactory, MatrixType, Mesh, Operators
+    R.version = getattr(EasyFEA, "__version__", "?")
+    return R
+
+
+def build(ref, name, seed):
+    coords, connect = make_mesh(name, seed=seed)
+    g = ref.GroupElemFactory.Create(ref.ElemType(name), connect, coords)
+    mesh = ref.Mesh({ref.ElemType(name): g})
+    return coords, connect, g, mesh
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_geometry_operators_live(ref, name):
+    coords, connect, g, mesh = build(ref, name, seed=11)
+    dim = g.dim
+    rng = np.random.default_rng(5)
+    mat = ref.Models.Elastic.Isotropic(dim, E=210000.0, v=0.3, planeStress=False)
+    MT = ref.MatrixType
+    geo = {}
+    for mt in ("rigi", "mass"):
+        geo[mt] = orc.geometry(coords[connect][:, :, :dim], g.Get_dN_pg(MT(mt)), g.Get_weight_pg(MT(mt)))
+        assert rel_err(geo[mt]["F"], np.asarray(g.Get_F_e_pg(MT(mt)))) < TOL
+        assert rel_err(geo[mt]["jac"], np.asarray(g.Get_jacobian_e_pg(MT(mt)))) < TOL
+        assert rel_err(geo[mt]["detF"], np.asarray(g.Get_jacobian_e_pg(MT(mt), absoluteValues=False))) < TOL
+        assert rel_err(geo[mt]["invF"], np.asarray(g.Get_invF_e_pg(MT(mt)))) < TOL
+        assert rel_err(geo[mt]["dN"], np.asarray(g.Get_dN_e_pg(MT(mt)))) < TOL
+        assert rel_err(geo[mt]["wJ"], np.asarray(g.Get_weightedJacobian_e_pg(MT(mt)))) < TOL
+    assert rel_err(orc.B_matrix(geo["rigi"]["dN"]), np.asarray(g.Get_B_e_pg(MT.rigi))) < TOL
+    Ne, nPg, nPgm = g.Ne, geo["rigi"]["wJ"].shape[1], geo["mass"]["wJ"].shape[1]
+    ns = 3 if dim == 2 else 6
+    B = ref.Operators.Bilinear
+    # every broadcast mode of C / coef
+    for C in (mat.C, mat.C[None] * rng.uniform(0.5, 2, (Ne, 1, 1)), mat.C[None, None] * rng.uniform(0.5, 2, (Ne, nPg, 1, 1))):
+        assert rel_err(orc.linearized_elasticity(geo["rigi"], C), B.LinearizedElasticity(g, C)) < TOL
+    N_mass = g.Get_N_pg(MT.mass)
+    for coef in (1.7, rng.uniform(1, 2, Ne), rng.uniform(1, 2, (Ne, nPgm))):
+        for dof_n in (1, dim):
+            assert rel_err(orc.uv(geo["mass"], N_mass, coef, dof_n), B.UV(g, coef, dof_n)) < TOL
+        assert rel_err(orc.source_v(geo["mass"], N_mass, coef, 1), ref.Operators.Linear.V(g, coef, 1)) < TOL
+    assert rel_err(orc.source_v(geo["mass"], N_mass, 2.5, dim), ref.Operators.Linear.V(g, 2.5, dim)) < TOL
+    A = np.eye(dim) + 0.2 * rng.uniform(size=(dim, dim))
+    assert rel_err(orc.grad_u_a_grad_v(geo["rigi"], A, 3.0), B.GradU_A_GradV(g, A, 3.0)) < TOL
+    coef = rng.uniform(1, 2, (Ne, nPg))
+    assert rel_err(orc.grad_u_a_grad_v(geo["rigi"], None, coef), B.GradUGradV(g, coef)) < TOL
+    u = rng.normal(size=mesh.Nn * dim) * 1e-3
+    eps_ref = np.asarray(mat.Calc_Epsilon_e_pg(u, g, MT.rigi))
+    assert rel_err(orc.strain(geo["rigi"], orc.locate_sol_e(u, connect, dim)), eps_ref) < TOL
+    sig = rng.normal(size=(Ne, nPg, ns))
+    assert rel_err(orc.internal_force(geo["rigi"], sig), ref.Operators.Linear.InternalForce(g, ref.FeArray.asfearray(sig))) < TOL
+
+
+@pytest.mark.parametrize("name", ["TRI3", "QUAD9", "TETRA4", "HEXA8"])
+@pytest.mark.parametrize("split", ["Bourdin", "Amor", "Miehe", "Stress", "He"])
+def test_phasefield_law_live(ref, name, split):
+    coords, connect, g, mesh = build(ref, name, seed=13)
+    dim = g.dim
+    rng = np.random.default_rng(17)
+    MT = ref.MatrixType
+    for planeStress in ((False, True) if dim == 2 else (False,)):
+        mat = ref.Models.Elastic.Isotropic(dim, E=210000.0, v=0.3, planeStress=planeStress)
+        omat = orc.IsoMaterial(dim, 210000.0, 0.3, planeStress=planeStress)
+        assert np.array_equal(omat.C, np.asarray(mat.C))
+        pfm = ref.Models.PhaseField(mat, split, "AT2", 2.7, 0.01)
+        u = rng.normal(size=mesh.Nn * dim) * 1e-3
+        for mt in ("rigi", "mass"):
+            eps = np.asarray(mat.Calc_Epsilon_e_pg(u, g, MT(mt)))
+            cP, cM = pfm.Calc_C(ref.FeArray.asfearray(eps.copy()), verif=False)
+            pP, pM = pfm.Calc_psi_e_pg(ref.FeArray.asfearray(eps.copy()))
+            ocP, ocM = orc.calc_C(omat, split, eps)
+            opP, opM = orc.calc_psi(omat, split, eps)
+            # Bourdin returns the constant C with singleton leading axes (Models/_phasefield.py:433-449)
+            cP, cM = np.broadcast_to(np.asarray(cP), ocP.shape), np.broadcast_to(np.asarray(cM), ocM.shape)
+            assert rel_err(ocP, np.asarray(cP)) < TOL and rel_err(ocM, np.asarray(cM)) < TOL
+            assert rel_err(opP, np.asarray(pP)) < TOL and rel_err(opM, np.asarray(pM)) < TOL
+            # the reference's own properties (tests/Models/phasefield_test.py:105-137)
+            assert rel_err(ocP + ocM, np.broadcast_to(omat.C, ocP.shape)) < TOL
+            psi = 0.5 * np.einsum("epi,ij,epj->ep", eps, omat.C, eps)
+            assert rel_err(opP + opM, psi) < 1e-11
+        d = rng.uniform(0, 0.95, mesh.Nn)
+        assert rel_err(orc.degradation(d[connect], g.Get_N_pg(MT.rigi)), np.asarray(pfm.Get_g_e_pg(d, g, MT.rigi))) < TOL
+    for regu in ("AT1", "AT2"):
+        pfm = ref.Models.PhaseField(mat, split, regu, 2.7, 0.01)
+        psiP = rng.uniform(0, 500, (g.Ne, 3))
+        assert orc.pf_k(regu, 2.7, 0.01) == pfm.k
+        assert rel_err(orc.pf_r(regu, 2.7, 0.01, psiP), np.asarray(pfm.Get_r_e_pg(ref.FeArray.asfearray(psiP)))) < TOL
+        assert rel_err(orc.pf_f(regu, 2.7, 0.01, psiP), np.asarray(pfm.Get_f_e_pg(ref.FeArray.asfearray(psiP)))) < TOL
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_csr_map_and_assembly_live(ref, name):
+    coords, connect, g, mesh = build(ref, name, seed=19)
+    dim = g.dim
+    mat = ref.Models.Elastic.Isotropic(dim, E=210000.0, v=0.3, planeStress=False)
+    simu = ref.Simulations.Elastic(mesh, mat)
+    Nn = mesh.Nn
+    for dof_n in (1, dim):
+        for isMatrix in (True, False):
+            inv, indices, indptr, nnz = simu._Simu__Get_csr_map(dof_n, isMatrix, Nn * dof_n, (g,))
+            oinv, oind, optr, onnz = orc.csr_map([connect], dof_n, Nn * dof_n, isMatrix)
+            assert onnz == nnz
+            for a, b in ((oinv, inv), (oind, indices), (optr, indptr)):
+                assert a.dtype == b.dtype and np.array_equal(a, b)
+    # full simulation-level assembly: K of Simulations.Elastic == oracle K_e + replay, bit for bit
+    K = simu.Get_K_C_M_F()[0]
+    tabw = g.Get_weight_pg(ref.MatrixType.rigi)
+    geo = orc.geometry(coords[connect][:, :, :dim], g.Get_dN_pg(ref.MatrixType.rigi), tabw)
+    Ke_ref = ref.Operators.Bilinear.LinearizedElasticity(g, mat.C)
+    if dim == 2:
+        Ke_ref = Ke_ref * mat.thickness
+    inv, indices, indptr, nnz = orc.csr_map([connect], dim, Nn * dim, True)
+    assert np.array_equal(K.indptr, indptr) and np.array_equal(K.indices, indices)
+    assert np.array_equal(orc.assemble_replay([Ke_ref], inv, nnz), K.data)
+    Ke = orc.linearized_elasticity(geo, np.asarray(mat.C)) * (mat.thickness if dim == 2 else 1.0)
+    assert rel_err(orc.assemble_replay([Ke], inv, nnz), K.data) < TOL
+
+
+def test_known_answers_survey_appendix_c():
+    """KAT1/KAT3 of SURVEY.md Appendix C (values minted from the live reference during the survey)."""
+    from easyfea_b200 import elements as el
+
+    X = np.array([(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)], dtype=float)
+    tab = el.gauss_table("HEXA8", "rigi")
+    geo = orc.geometry(X[None], tab.dN_pg, tab.weights)
+    C = orc.IsoMaterial(3, 210000.0, 0.3).C
+    K = orc.linearized_elasticity(geo, C)[0]
+    assert np.allclose(K[0, :4], [49358.974358974374, 16826.923076923074, 16826.92307692307, -22435.897435897437], rtol=1e-12)
+    assert np.isclose(np.trace(K), 1184615.384615385, rtol=1e-12)
+    assert np.isclose(np.linalg.norm(K), 362046.1519938722, rtol=1e-12)
+    T = np.array([(0, 0), (2, 0), (0.5, 1.5)], dtype=float)
+    tab = el.gauss_table("TRI3", "rigi")
+    geo = orc.geometry(T[None], tab.dN_pg, tab.weights)
+    G = orc.grad_u_a_grad_v(geo, None, 1.0)[0]
+    assert np.allclose(G, [[0.75, -0.25, -0.5], [-0.25, 0.4166666666666667, -0.16666666666666666],
+                           [-0.5, -0.16666666666666666, 0.6666666666666666]], rtol=1e-12)
