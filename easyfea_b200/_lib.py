@@ -68,6 +68,7 @@ SIGNATURES = {
     "efb_pcg_init": [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "efb_pcg_update_xr": [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "efb_pcg_update_p": [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "efb_pack_f64": [c_i64, c_vp, c_vp, c_vp, c_vp],
     "efb_pcg_partials_size": [],
     "efb_version": [],
     "efb_device_count": [],

@@ -144,15 +144,17 @@ class CsrPattern:
             tens.append(t)
         return _group_args(g.dgs, tens) + (tens,)
 
-    def replay(self, datas, out=None) -> torch.Tensor:
-        """CSR `data` (nnz) from per-group element arrays: np.bincount(inv, weights=concat(data)) bit for bit."""
+    def replay(self, datas, out=None, n_nodes=None) -> torch.Tensor:
+        """CSR `data` (nnz) from per-group element arrays: np.bincount(inv, weights=concat(data)) bit for bit.
+        `n_nodes` restricts the matrix replay to the rows of nodes [0, n_nodes) (owned rows of a sharded run)."""
         g = self.graph
+        Nn = g.Nn if n_nodes is None else min(int(n_nodes), g.Nn)
         n, ptrs, Ne, nPe, keep = self._data_args(datas)
         st = dv.stream_ptr()
         if self.isMatrix:
             if out is None:
                 out = dv.empty((self.nnz,))
-            _lib.call("efb_csr_replay_matrix", n, ptrs, Ne, nPe, self.dof_n, g.Nn, dv.ptr(g.rowptr), dv.ptr(g.qlist),
+            _lib.call("efb_csr_replay_matrix", n, ptrs, Ne, nPe, self.dof_n, Nn, dv.ptr(g.rowptr), dv.ptr(g.qlist),
                       dv.ptr(g.adjptr), dv.ptr(g.pos), g.max_deg, dv.ptr(out), st)
             return out
         dense = torch.zeros(self.Ndof, dtype=torch.float64, device=g.rowptr.device)

@@ -163,6 +163,11 @@ __global__ void k_inv_diag(long long n, const double* __restrict__ diag, const u
     if (i < n) out[i] = (mask && !mask[i]) ? 0.0 : 1.0 / diag[i];
 }
 
+// send-buffer packing of the halo exchange: dst[i] = src[idx[i]]
+__global__ void k_pack(long long n, const int* __restrict__ idx, const double* __restrict__ src, double* __restrict__ dst) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = src[idx[i]];
+}
+
 template <class IDX>
 static int launch_spmv(long long nrows, const void* indptr, const void* indices, const double* data, const double* x,
                        long long x_row_offset, const unsigned char* row_mask, double* y, double* partials, int lpr, cudaStream_t st) {
@@ -242,4 +247,12 @@ extern "C" int efb_pcg_update_p(int64_t n, const double* rz_new, const double* r
                                 double* p, void* stream) {
     k_update_p<<<kRedBlocks, 256, 0, as_stream(stream)>>>(n, rz_new, rz_old, z, free_mask, p);
     return check_launch("efb_pcg_update_p");
+}
+
+extern "C" int efb_pack_f64(int64_t n, const int32_t* idx, const double* src, double* dst, void* stream) {
+    if (n == 0) return 0;
+    long long nblk = (n + 255) / 256;
+    if (nblk > 148 * 16) nblk = 148 * 16;
+    k_pack<<<(unsigned)nblk, 256, 0, as_stream(stream)>>>(n, idx, src, dst);
+    return check_launch("efb_pack_f64");
 }

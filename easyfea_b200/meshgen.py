@@ -74,3 +74,38 @@ def structured_mesh(elemType: str, n, lengths=None, jitter: float = 0.0, seed: i
     for d in range(dim):
         coords[:, d] = lattice[:, d] * (lengths[d] / (npts[d] - 1))
     return coords, np.ascontiguousarray(connect, dtype=np.int64)
+
+
+def hexa8_slab(n, rank: int, world: int, jitter: float = 0.0, seed: int = 0):
+    """Rank `rank`'s view of the `nx x ny x (world*nz)` HEXA8 mesh (unit cells, x fastest) cut into z-slabs of `nz` layers —
+    the weak-scaling input of SURVEY.md §8e, built WITHOUT the global mesh.
+
+    Returns (connect (Nc, 8) GLOBAL node ids, elem_ids (Nc,) global and ascending, owner_of(ids) -> rank,
+    coords_of(ids) -> (k, 3)) for a superset of the rank's local elements: its own layers plus the first layer of the
+    next slab (whose elements touch the interface plane this rank owns — they are the ghost elements).  The jitter of a
+    node depends only on (seed, its lattice plane), so ranks sharing a plane see the same coordinates."""
+    nx, ny, nz = (n,) * 3 if np.isscalar(n) else tuple(n)
+    P, L = (nx + 1) * (ny + 1), nx * ny
+    lay0 = rank * nz
+    lay1 = min((rank + 1) * nz + 1, world * nz)  # one ghost layer above
+    _, c = structured_mesh("HEXA8", (nx, ny, lay1 - lay0))
+    connect = c + lay0 * P
+    elem_ids = np.arange(lay0 * L, lay1 * L, dtype=np.int64)
+    h = 1.0 / max(nx, ny, nz)
+
+    def owner_of(ids):
+        plane = np.asarray(ids, dtype=np.int64) // P
+        return np.minimum(np.maximum(plane - 1, 0) // nz, world - 1)
+
+    def coords_of(ids):
+        ids = np.asarray(ids, dtype=np.int64)
+        plane, rem = ids // P, ids % P
+        lat = np.stack([rem % (nx + 1), rem // (nx + 1), plane], axis=1).astype(np.float64)
+        if jitter:
+            for k in np.unique(plane):
+                sel = plane == k
+                jit = np.random.default_rng([seed, int(k)]).uniform(-jitter, jitter, size=(P, 3))
+                lat[sel] += jit[rem[sel]]
+        return lat * h
+
+    return connect, elem_ids, owner_of, coords_of

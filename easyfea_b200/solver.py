@@ -62,7 +62,7 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
     x_full = torch.zeros(n_glob, dtype=torch.float64, device=dev)
     x = x_full[row_offset:row_offset + nrows]
     if x0 is not None:
-        x.copy_(dv.to_device(x0))
+        x.copy_(dv.to_device(x0).reshape(-1)[:nrows])  # a local [owned | halo] vector may be passed: the owned part counts
     p_full = torch.zeros(n_glob, dtype=torch.float64, device=dev)
     p = p_full[row_offset:row_offset + nrows]
     r, z, Ap = dv.empty((nrows,)), dv.empty((nrows,)), dv.empty((nrows,))

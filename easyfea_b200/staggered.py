@@ -1,0 +1,214 @@
+"""Device-resident drivers of the two consumers named by the north star: the linear-elastic solve of config 2
+(`Simulations.Elastic`, EasyFEA/Simulations/_elastic.py:123-152 + `_Simu.Solve`) and the staggered phase-field loop of
+configs 3/4 (`Simulations.PhaseField.Solve`, EasyFEA/Simulations/_phasefield.py:300-432).
+
+Everything between the mesh upload and the converged nodal fields stays in HBM: element systems (S1/S3/S4), the
+deterministic CSR replay (A2) and the Jacobi-PCG.  Dirichlet conditions are applied by masking (projected CG) with the
+prescribed values carried in the start vector, which is what `Solvers.__Solver_1` (Solvers.py:502-553) obtains by
+slicing `A[unknown][:, unknown]` and `b_u - A_uk x_k` on the host.
+
+The same driver runs single-GPU (`world == 1`: every node is owned) and row-sharded (`easyfea_b200.dist`): vectors are
+laid out `[owned | halo]`, matrices hold the owned rows, and after each solve the halo part of the new field is
+refreshed so the ghost elements integrate with up-to-date nodal values.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import device as dv
+from . import operators as op
+from .assembly import Assembler, DeviceCsr
+from .solver import pcg
+
+
+class LocalSystem:
+    """Assembly of the owned rows of one element group in local numbering (single GPU: all rows)."""
+
+    def __init__(self, group, part=None, comm_factory=None):
+        self.group = group
+        self.asm = Assembler()
+        self.part = part
+        self.n_local = int(group.Ncoords)
+        self.n_owned = self.n_local if part is None else int(part.n_owned)
+        self._comm_factory = comm_factory
+        self._comms = {}
+
+    def comm(self, dof_n: int):
+        if self.part is None or self.part.world == 1:
+            return None
+        if dof_n not in self._comms:
+            self._comms[dof_n] = self._comm_factory(self.part, dof_n)
+        return self._comms[dof_n]
+
+    def matrix(self, Xe, dof_n: int) -> DeviceCsr:
+        d = int(dof_n)
+        pat = self.asm.pattern(d, True, self.n_local * d, (self.group,))
+        data = pat.replay([Xe], n_nodes=self.n_owned)
+        nrows = self.n_owned * d
+        if self.n_owned == self.n_local:
+            return DeviceCsr(pat.indptr, pat.indices, data, (nrows, nrows))
+        if not hasattr(pat, "_nnz_owned"):
+            pat._nnz_owned = int(pat.indptr[nrows].item())
+        nz = pat._nnz_owned
+        return DeviceCsr(pat.indptr[:nrows + 1], pat.indices[:nz], data[:nz], (nrows, self.n_local * d))
+
+    def vector(self, Fe, dof_n: int) -> torch.Tensor:
+        d = int(dof_n)
+        pat = self.asm.pattern(d, False, self.n_local * d, (self.group,))
+        pat.replay([Fe])
+        return pat.last_dense[: self.n_owned * d]
+
+    def refresh_halo(self, x_local: torch.Tensor, dof_n: int) -> None:
+        c = self.comm(dof_n)
+        if c is not None:
+            c.halo_exchange(x_local)
+
+
+class Dirichlet:
+    """Prescribed dofs of one problem in LOCAL numbering (only owned dofs matter for the solve)."""
+
+    def __init__(self, n_dofs_local: int):
+        self.n = int(n_dofs_local)
+        self.dofs = np.empty(0, dtype=np.int64)
+        self.values = np.empty(0)
+
+    def add(self, nodes, values, components, dof_n: int):
+        """`add_dirichlet(nodes, values, directions)` of the reference (_simu.py `add_dirichlet`): one value per component."""
+        nodes = np.asarray(nodes, dtype=np.int64)
+        for val, c in zip(values, components):
+            self.dofs = np.concatenate([self.dofs, nodes * dof_n + int(c)])
+            self.values = np.concatenate([self.values, np.full(nodes.size, float(val))])
+
+    def device_arrays(self, n_owned_dofs: int):
+        """(free_mask uint8 (n_owned_dofs), dofs int64 tensor, values tensor) — later entries win, like the reference"""
+        mask = np.ones(n_owned_dofs, dtype=np.uint8)
+        sel = self.dofs < n_owned_dofs
+        mask[self.dofs[sel]] = 0
+        return dv.to_device(mask, np.uint8), dv.to_device(self.dofs, np.int64), dv.to_device(self.values)
+
+
+def _apply(x_local: torch.Tensor, dofs: torch.Tensor, values: torch.Tensor) -> None:
+    if dofs.numel():
+        x_local[dofs] = values
+
+
+class ElasticSolve:
+    """Config 2: K = assemble(LinearizedElasticity(C)) then Jacobi-PCG on the free dofs."""
+
+    def __init__(self, system: LocalSystem, C, thickness: float = 1.0):
+        self.sys, self.C, self.thickness = system, np.asarray(C, dtype=np.float64), float(thickness)
+        self.dim = int(system.group.dim)
+        self.bc = Dirichlet(system.n_local * self.dim)
+        self.u = torch.zeros(system.n_local * self.dim, dtype=torch.float64, device=dv.device())
+
+    def assemble(self) -> DeviceCsr:
+        scale = self.thickness if self.dim == 2 else 1.0
+        Ke = op.elastic_Ke_dev(self.sys.group, self.C, op.RIGI, scale)
+        return self.sys.matrix(Ke, self.dim)
+
+    def solve(self, tol=1e-8, maxiter=None, b=None):
+        d = self.dim
+        K = self.assemble()
+        nown = self.sys.n_owned * d
+        mask, dofs, vals = self.bc.device_arrays(nown)
+        _apply(self.u, dofs, vals)
+        self.sys.refresh_halo(self.u, d)
+        rhs = torch.zeros(nown, dtype=torch.float64, device=self.u.device) if b is None else dv.to_device(b)
+        x, info = pcg(K, rhs, x0=self.u, free_mask=mask, tol=tol, maxiter=maxiter, comm=self.sys.comm(d))
+        self.u[:nown] = x
+        self.sys.refresh_halo(self.u, d)
+        return self.u, info
+
+
+class PhaseFieldStaggered:
+    """`Simulations.PhaseField` reduced to the staggered loop: damage then displacement, each assembled and solved on
+    the device.  `model` is an `easyfea_b200.phasefield.PhaseFieldModel`."""
+
+    def __init__(self, system: LocalSystem, model, pcg_tol: float = 1e-10, pcg_maxiter: int = None):
+        self.sys, self.pfm = system, model
+        self.dim = int(system.group.dim)
+        dev = dv.device()
+        self.u = torch.zeros(system.n_local * self.dim, dtype=torch.float64, device=dev)
+        self.d = torch.zeros(system.n_local, dtype=torch.float64, device=dev)
+        self.psiP = None       # (Ne, nPg_mass) of the last damage assembly, Simulations/_phasefield.py:536
+        self.psiP_old = None   # history field, replaced in Save_Iter only (:623-625)
+        self.bc_u = Dirichlet(system.n_local * self.dim)
+        self.bc_d = Dirichlet(system.n_local)
+        self.pcg_tol, self.pcg_maxiter = pcg_tol, pcg_maxiter
+        self.info = {}
+
+    def Bc_Init(self):
+        self.bc_u = Dirichlet(self.sys.n_local * self.dim)
+        self.bc_d = Dirichlet(self.sys.n_local)
+
+    def add_dirichlet(self, nodes, values, components, problemType="elastic"):
+        if problemType == "damage":
+            self.bc_d.add(nodes, values, components, 1)
+        else:
+            self.bc_u.add(nodes, values, components, self.dim)
+
+    # -- the two sub-problems ----------------------------------------------------------------------------------
+    def solve_damage(self):
+        """`__Solve_damage` (:573-578) with `__Construct_Damage_Matrix` (:540-571)."""
+        s = self.sys
+        Ke, Fe, self.psiP = self.pfm.damage_system_dev(s.group, self.u, self.psiP_old)
+        K = s.matrix(Ke, 1)
+        F = s.vector(Fe, 1)
+        mask, dofs, vals = self.bc_d.device_arrays(s.n_owned)
+        _apply(self.d, dofs, vals)
+        s.refresh_halo(self.d, 1)
+        x, info = pcg(K, F, x0=self.d, free_mask=mask, tol=self.pcg_tol, maxiter=self.pcg_maxiter, comm=s.comm(1))
+        self.d[: s.n_owned] = x
+        s.refresh_halo(self.d, 1)
+        self.info["damage"] = info
+        return self.d
+
+    def solve_elastic(self):
+        """`__Solve_elastic` with `__Construct_Elastic_Matrix` (:444-482): the split uses the CURRENT displacement."""
+        s, dim = self.sys, self.dim
+        Ke = self.pfm.elastic_Ke_dev(s.group, self.u, self.d)
+        K = s.matrix(Ke, dim)
+        nown = s.n_owned * dim
+        mask, dofs, vals = self.bc_u.device_arrays(nown)
+        _apply(self.u, dofs, vals)
+        s.refresh_halo(self.u, dim)
+        rhs = torch.zeros(nown, dtype=torch.float64, device=self.u.device)
+        x, info = pcg(K, rhs, x0=self.u, free_mask=mask, tol=self.pcg_tol, maxiter=self.pcg_maxiter, comm=s.comm(dim))
+        self.u[:nown] = x
+        s.refresh_halo(self.u, dim)
+        self.info["elastic"] = info
+        return self.u
+
+    def iterate(self):
+        """one staggered iteration; returns max |d_new - d_old| over the owned nodes (device scalar, all-reduced)"""
+        d_n = self.d[: self.sys.n_owned].clone()
+        self.solve_damage()
+        self.solve_elastic()
+        conv = (self.d[: self.sys.n_owned] - d_n).abs().max().reshape(1)
+        dmax = self.d[: self.sys.n_owned].max().reshape(1)
+        c = self.sys.comm(1)
+        if c is not None:
+            c.all_reduce_max(conv)
+            c.all_reduce_max(dmax)
+        return conv, dmax
+
+    def Solve(self, tolConv=1.0, maxIter=500, convOption=0):
+        """(u, d, converged) — convergence on max |d_np1 - d_n| (convOption 0 of the reference, :372-373, 392-397)."""
+        assert 0 < tolConv <= 1, "tolConv must be between 0 and 1."
+        assert maxIter > 1, "Must be > 1."
+        if convOption != 0:
+            raise NotImplementedError("only convOption=0 (damage increment) runs on the device")
+        Niter, converged = 0, False
+        while not converged and Niter < maxIter:
+            Niter += 1
+            conv, dmax = self.iterate()
+            convIter = float(conv.item())
+            converged = tolConv == 1 or float(dmax.item()) == 0 or convIter <= tolConv
+        self.Niter, self.convIter = Niter, convIter
+        return self.u, self.d, converged
+
+    def Save_Iter(self):
+        """history update of the `History` solver, Simulations/_phasefield.py:623-625"""
+        if self.pfm.solver == "History":
+            self.psiP_old = self.psiP

@@ -190,6 +190,9 @@ int efb_pcg_update_xr(int64_t n, const double* rz, const double* pAp, const doub
 int efb_pcg_update_p(int64_t n, const double* rz_new, const double* rz_old, const double* z, const uint8_t* free_mask,
                      double* p, void* stream);
 
+/* send-buffer packing of the PCG halo exchange (row-sharded runs): dst[i] = src[idx[i]] */
+int efb_pack_f64(int64_t n, const int32_t* idx, const double* src, double* dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
