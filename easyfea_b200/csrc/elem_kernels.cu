@@ -62,18 +62,26 @@ static int launch_geometry(const efb_group* g, const GeomOut& o, cudaStream_t st
 
 // ---------------------------------------------------------------------------------------------------------
 // persistent: each CTA walks element batches blockIdx.x, blockIdx.x + gridDim.x, ...; the reference-element tables are
-// staged once per CTA, and for warp-local element types the warps of a CTA run their batches independently
-constexpr int kElasticThreads = 128;
+// staged once per CTA; several CTAs share an SM, so one CTA's gather/geometry phases overlap another's FP64 main loop
+template <int DIM, int NPE>
+constexpr int elastic_min_blocks() {
+    // aim at <= 112 registers per thread where the CTA is small enough for that to matter
+#ifndef EFB_ELASTIC_MINB96
+#define EFB_ELASTIC_MINB96 6
+#endif
+    return ElasticTile<DIM, NPE>::THREADS <= 96 ? EFB_ELASTIC_MINB96 : (ElasticTile<DIM, NPE>::THREADS <= 128 ? 4 : 1);
+}
 
 template <int DIM, int NPE, int CMODE>
-__global__ void __launch_bounds__(kElasticThreads) k_elastic(GroupView g, CMat C2, const double* C, double scale, double* out, int EPB,
-                                                              long long nblk) {
-    extern __shared__ double smem[];
+__global__ void __launch_bounds__(ElasticTile<DIM, NPE>::THREADS, elastic_min_blocks<DIM, NPE>())
+    k_elastic(GroupView g, CMat C2, const double* C, double scale, double* out, long long nblk) {
+    extern __shared__ __align__(16) double smem[];
     bool first = true;
     for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-        elastic_block<DIM, NPE, CMODE>(g, C2, C, scale, out, EPB, blk, blockDim.x, smem, first);
+        elastic_block<DIM, NPE, CMODE>(g, C2, C, scale, out, blk, blockDim.x, smem, first);
         first = false;
     }
+    if (ElasticTile<DIM, NPE>::kBulk && threadIdx.x == 0) bulk_store_wait_read();  // shared memory outlives the last copy
 }
 
 // CTAs that keep every SM full: resident CTAs per SM (occupancy query) x number of SMs
@@ -91,18 +99,15 @@ template <int DIM, int NPE, int CMODE>
 static int launch_elastic_mode(const efb_group* g, const CMat& C2, const double* C, double scale, double* out, cudaStream_t st) {
     constexpr int NS = StrainSize<DIM>::value;
     using SM = ElasticSmem<DIM, NPE>;
+    using Tile = ElasticTile<DIM, NPE>;
     const int extra = CMODE == 2 ? g->nPg * NS * NS : (CMODE == 1 ? NS * NS : 0);
-    const int TPE = ElasticTile<DIM, NPE>::TPE;
-    int EPB = kElasticThreads / TPE;
-    if (EPB < 1) EPB = 1;
-    while (EPB > 1 && SM(g->nPg, EPB, extra).total() * sizeof(double) > 100 * 1024) --EPB;
-    const SM sm(g->nPg, EPB, extra);
+    const SM sm(g->nPg, Tile::EPB, extra);
     const size_t bytes = sizeof(double) * sm.total();
     if (ensure_smem(k_elastic<DIM, NPE, CMODE>, bytes)) return 1;
-    const long long nblk = (g->Ne + EPB - 1) / EPB;
+    const long long nblk = (g->Ne + Tile::EPB - 1) / Tile::EPB;
     if (nblk == 0) return 0;
-    const long long grid = persistent_grid(k_elastic<DIM, NPE, CMODE>, EPB * TPE, bytes, nblk);
-    k_elastic<DIM, NPE, CMODE><<<(unsigned)grid, EPB * TPE, bytes, st>>>(view_of(g), C2, C, scale, out, EPB, nblk);
+    const long long grid = persistent_grid(k_elastic<DIM, NPE, CMODE>, Tile::THREADS, bytes, nblk);
+    k_elastic<DIM, NPE, CMODE><<<(unsigned)grid, Tile::THREADS, bytes, st>>>(view_of(g), C2, C, scale, out, nblk);
     return check_launch("efb_elastic_Ke");
 }
 

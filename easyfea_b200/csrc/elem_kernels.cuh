@@ -236,14 +236,20 @@ EFB_D void geometry_block(const GroupView& g, const GeomOut& o, int EPB, long lo
 // ---------------------------------------------------------------------------------------------------------
 // O1: K_e = scale * sum_p wJ B^T C B                                   Operators/Bilinear.py:62-79
 //
-// Thread (a, h) of an element owns the DIM rows of node a and the columns of NB = NPE/CSPLIT nodes (chunk h), i.e.
-// DIM*NB*DIM accumulators.  With S = diag(1,..,1, 1/sqrt2,..) the Kelvin-Mandel operator is B = S G, G holding the plain
-// gradients (DIM non-zeros per column), so K_e = sum_p w G^T (S C S) G: the kernel receives C2 = S C S.  Per Gauss
-// point a thread forms bc[i][:] = w G[:, (a,i)]^T C2 once (3 DIM NS flops) and then spends exactly DIM FMAs per
-// accumulator; the only shared-memory traffic of the inner loop is one broadcast read of the NB column-node gradients.
-// Geometry is one phase: thread p of an element takes Gauss point p — F, det, F^-1 stay in registers and only
-// w|det F| and the physical gradients go to shared memory.  A homogeneous C2 (mode 0) is a kernel argument (constant
-// bank); per-element / per-Gauss-point C is staged in shared memory, scaled to C2 on the way.
+// With S = diag(1,..,1, 1/sqrt2,..) the Kelvin-Mandel operator is B = S G, G holding the plain gradients (DIM non-zeros
+// per column), so K_e = sum_p w G^T (S C S) G: the kernel receives C2 = S C S.
+//
+// Work decomposition ("component per warp, row per thread"): a group of DIM*CS warps handles EPW = 32/NPE elements.
+// Warp (i, h) of the group owns, for every element of the group, the rows (a, i) of K_e — one row per lane (el, a) —
+// restricted to the NB = NPE/CS column nodes of chunk h: NB*DIM accumulators per thread (24 for HEXA8, <= 30 always).
+// The row component i is warp-uniform, so the structure of B (which strain rows a displacement component feeds) is
+// resolved at compile time per warp and a homogeneous C2 is read as constant-bank operands.  Per Gauss point a thread
+// forms bc[:] = w G[:, (a,i)]^T C2 (DIM*NS FMAs) and then spends exactly DIM FMAs per accumulator; the only
+// shared-memory traffic of the inner loop is the broadcast read of the column-node gradients.
+// Geometry (G2-G6) is one task per (element, Gauss point): F, det, F^-1 stay in registers, only w|det F| and the
+// physical gradients go to shared memory.  Finished rows are staged in shared memory in the exact K_e layout and leave
+// the SM as ONE bulk asynchronous copy (TMA, cp.async.bulk) per batch, so the FP64 warps never wait on store queues.
+// Per-element / per-Gauss-point C is staged in shared memory, scaled to C2 on the way.
 // ---------------------------------------------------------------------------------------------------------
 struct CMat {
     double v[36];
@@ -269,28 +275,32 @@ inline void prescale_C(CMat& C) {
 
 template <int DIM, int NPE>
 struct ElasticTile {
-    // columns are split so that a thread keeps at most ~81 accumulators
-#ifndef EFB_HEXA8_CSPLIT
-#define EFB_HEXA8_CSPLIT 1
-#endif
-    static constexpr int CSPLIT =
-        (DIM == 2) ? 1 : (NPE == 8 ? EFB_HEXA8_CSPLIT : NPE == 27 ? 3 : NPE == 20 ? 4 : NPE == 18 ? 2 : NPE == 15 ? 3 : NPE == 10 ? 2 : 1);
-    static constexpr int NB = NPE / CSPLIT;
-    static constexpr int TPE = NPE * CSPLIT;
-    static_assert(NB * CSPLIT == NPE, "CSPLIT must divide NPE");
+    static constexpr int NDOF = DIM * NPE;
+    static constexpr int CS = (NDOF <= 32) ? 1 : ((NPE == 15 || NPE == 27) ? 3 : 2);  // column chunks
+    static constexpr int NB = NPE / CS;                                              // column nodes per thread
+    static constexpr int EPW = 32 / NPE;                                             // elements per warp
+    static constexpr int WPG = DIM * CS;                                             // warps per group
+    static constexpr int G = (WPG <= 2) ? 2 : 1;                                     // groups per CTA
+    static constexpr int EPB = G * EPW;                                              // elements per CTA batch
+    static constexpr int THREADS = G * WPG * 32;
+    static constexpr bool kBulk = (NDOF * NDOF) % 2 == 0;  // bulk copies move multiples of 16 bytes
+    static_assert(NB * CS == NPE, "CS must divide NPE");
+    static_assert(EPW >= 1, "an element needs at most one warp of lanes");
 };
 
 // shared-memory map of the stiffness kernel (offsets in doubles)
 template <int DIM, int NPE>
 struct ElasticSmem {
     static constexpr int GS = (DIM == 3) ? 4 : 2;     // doubles per node in gN (3D padded to 4: two 16-byte loads)
-    static constexpr int TS = (DIM * NPE) | 1;        // odd stride of one Gauss point in the dN table: the threads of an
-                                                      // element read different Gauss points without bank conflicts
+    static constexpr int TS = (DIM * NPE) | 1;        // odd stride of one Gauss point in the dN table: the geometry tasks of
+                                                      // a warp read different Gauss points without bank conflicts
     static constexpr int GPS = NPE * GS + 2;          // stride of one Gauss point in gN (same reason, keeps 16-byte alignment)
+    static constexpr int KE = DIM * NPE * DIM * NPE;  // one staged element matrix
     int nPg, EPB, extra;
     EFB_HD ElasticSmem(int nPg_, int EPB_, int extra_) : nPg(nPg_), EPB(EPB_), extra(extra_) {}
-    EFB_HD int off_dN() const { return 0; }
-    EFB_HD int off_w() const { return nPg * TS; }
+    EFB_HD int off_stage() const { return 0; }  // first: 16-byte aligned for the bulk copy
+    EFB_HD int off_dN() const { return (EPB * KE + 1) & ~1; }
+    EFB_HD int off_w() const { return off_dN() + nPg * TS; }
     EFB_HD int tables_padded() const { return (off_w() + nPg + 1) & ~1; }
     EFB_HD int o_X() const { return 0; }
     EFB_HD int o_wJ() const { return NPE * DIM; }
@@ -305,22 +315,98 @@ struct ElasticSmem {
     EFB_HD double* elem(double* smem, int el) const { return smem + tables_padded() + el * per_elem(); }
 };
 
+// rows (a, I) x columns of nodes [b0, b0+NB): acc[b*DIM + j], all Gauss points
+template <int DIM, int NPE, int CMODE, int I>
+EFB_D void elastic_row(const CMat& C2const, const double* EFB_RESTRICT Cs, const double* EFB_RESTRICT wJ,
+                       const double* EFB_RESTRICT gN, int nPg, int a, int b0, double* EFB_RESTRICT acc) {
+    constexpr int NS = StrainSize<DIM>::value, NC = NS * NS;
+    using SM = ElasticSmem<DIM, NPE>;
+    constexpr int GS = SM::GS, GPS = SM::GPS, NB = ElasticTile<DIM, NPE>::NB;
+    EFB_UNROLL
+    for (int j = 0; j < NB * DIM; ++j) acc[j] = 0.0;
+    for (int p = 0; p < nPg; ++p) {
+        const double* gp = gN + p * GPS;
+        const double w = wJ[p];
+        // C2(s, r) of this Gauss point: constant bank (mode 0) or shared memory
+#define EFB_C(s_, r_) (CMODE == 0 ? C2const.v[(s_) * NS + (r_)] : Cs[(CMODE == 2 ? p * NC : 0) + (s_) * NS + (r_)])
+        double bc[NS];
+        if constexpr (DIM == 2) {
+            // G[:, (a,0)] = (gx, 0, gy); G[:, (a,1)] = (0, gy, gx)
+            const Pair ga = *reinterpret_cast<const Pair*>(gp + a * GS);
+            const double wx = w * ga.x, wy = w * ga.y;
+            EFB_UNROLL
+            for (int r = 0; r < NS; ++r) bc[r] = (I == 0) ? wx * EFB_C(0, r) + wy * EFB_C(2, r) : wy * EFB_C(1, r) + wx * EFB_C(2, r);
+            EFB_UNROLL
+            for (int b = 0; b < NB; ++b) {
+                const Pair gb = *reinterpret_cast<const Pair*>(gp + (b0 + b) * GS);
+                double s0 = acc[b * 2 + 0], s1 = acc[b * 2 + 1];
+                s0 += bc[0] * gb.x;
+                s0 += bc[2] * gb.y;
+                s1 += bc[1] * gb.y;
+                s1 += bc[2] * gb.x;
+                acc[b * 2 + 0] = s0;
+                acc[b * 2 + 1] = s1;
+            }
+        } else {
+            // G[:, (a,0)] = (gx,0,0,0,gz,gy); G[:, (a,1)] = (0,gy,0,gz,0,gx); G[:, (a,2)] = (0,0,gz,gy,gx,0)
+            const Pair gaxy = *reinterpret_cast<const Pair*>(gp + a * GS);
+            const double wx = w * gaxy.x, wy = w * gaxy.y, wz = w * gp[a * GS + 2];
+            EFB_UNROLL
+            for (int r = 0; r < NS; ++r) {
+                if constexpr (I == 0) bc[r] = wx * EFB_C(0, r) + wz * EFB_C(4, r) + wy * EFB_C(5, r);
+                if constexpr (I == 1) bc[r] = wy * EFB_C(1, r) + wz * EFB_C(3, r) + wx * EFB_C(5, r);
+                if constexpr (I == 2) bc[r] = wz * EFB_C(2, r) + wy * EFB_C(3, r) + wx * EFB_C(4, r);
+            }
+            EFB_UNROLL
+            for (int b = 0; b < NB; ++b) {
+                const Pair gxy = *reinterpret_cast<const Pair*>(gp + (b0 + b) * GS);
+                const double gx = gxy.x, gy = gxy.y, gz = gp[(b0 + b) * GS + 2];
+                double s0 = acc[b * 3 + 0], s1 = acc[b * 3 + 1], s2 = acc[b * 3 + 2];
+                s0 += bc[0] * gx;
+                s0 += bc[4] * gz;
+                s0 += bc[5] * gy;
+                s1 += bc[1] * gy;
+                s1 += bc[3] * gz;
+                s1 += bc[5] * gx;
+                s2 += bc[2] * gz;
+                s2 += bc[3] * gy;
+                s2 += bc[4] * gx;
+                acc[b * 3 + 0] = s0;
+                acc[b * 3 + 1] = s1;
+                acc[b * 3 + 2] = s2;
+            }
+        }
+#undef EFB_C
+    }
+}
+
+#ifdef __CUDACC__
+// shared -> global bulk asynchronous copy (TMA engine); `bytes` multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_store_issue(double* gdst, const double* ssrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+#endif
+
 template <int DIM, int NPE, int CMODE>
 EFB_D void elastic_block(const GroupView& g, const CMat& C2const, const double* EFB_RESTRICT C, double scale,
-                         double* EFB_RESTRICT out, int EPB, long long blockId, int nthreads, double* smem,
-                         bool load_tables = true) {
+                         double* EFB_RESTRICT out, long long blockId, int nthreads, double* smem, bool load_tables = true) {
     constexpr int NS = StrainSize<DIM>::value, NDOF = DIM * NPE, NC = NS * NS;
     using SM = ElasticSmem<DIM, NPE>;
     using Tile = ElasticTile<DIM, NPE>;
-    constexpr int GS = SM::GS, TS = SM::TS, GPS = SM::GPS;
-    constexpr int NB = Tile::NB, TPE = Tile::TPE;
+    constexpr int GS = SM::GS, TS = SM::TS, GPS = SM::GPS, KE = SM::KE;
+    constexpr int NB = Tile::NB, CS = Tile::CS, EPW = Tile::EPW, WPG = Tile::WPG, EPB = Tile::EPB;
     const int nPg = g.nPg;
     const int extra = CMODE == 2 ? nPg * NC : (CMODE == 1 ? NC : 0);
     const SM sm(nPg, EPB, extra);
     const long long e0 = blockId * EPB;
-    constexpr bool kWarpLocal = (32 % TPE == 0);  // an element never straddles two warps: warp barriers are enough
+    const int nvalid = (g.Ne - e0 < EPB) ? (int)(g.Ne - e0) : EPB;
     double* dNt = smem + sm.off_dN();
     double* wt = smem + sm.off_w();
+    double* stage = smem + sm.off_stage();
 
     if (load_tables) {
         EFB_PHASE(tid, nthreads) {
@@ -328,151 +414,107 @@ EFB_D void elastic_block(const GroupView& g, const CMat& C2const, const double* 
             for (int i = tid; i < nPg; i += nthreads) wt[i] = g.w_pg[i];
         }
     }
-    EFB_PHASE_E(tid, nthreads, kWarpLocal) {  // gather the nodal coordinates (and C)
-        const int el = tid / TPE, t = tid % TPE;
-        const long long e = e0 + el;
-        if (el < EPB && e < g.Ne) {
-            double* E = sm.elem(smem, el);
-            for (int a = t; a < NPE; a += TPE) {
-                const double* src = g.coord + (long long)g.connect[e * NPE + a] * g.coord_stride;
-                EFB_UNROLL
-                for (int d = 0; d < DIM; ++d) E[sm.o_X() + a * DIM + d] = src[d];
-            }
-            if (CMODE != 0) {
-                double* Cs = E + sm.o_extra();
-                const double* src = CMODE == 1 ? C + e * NC : C + e * (long long)(nPg * NC);
-                for (int i = t; i < extra; i += TPE) Cs[i] = src[i] * kelvin_factor<DIM>((i % NC) / NS, i % NS);
+    EFB_PHASE(tid, nthreads) {  // gather the nodal coordinates (and C)
+        for (int idx = tid; idx < nvalid * NPE; idx += nthreads) {
+            const int el = idx / NPE, a = idx - el * NPE;
+            const double* src = g.coord + (long long)g.connect[(e0 + el) * NPE + a] * g.coord_stride;
+            double* X = sm.elem(smem, el) + sm.o_X();
+            EFB_UNROLL
+            for (int d = 0; d < DIM; ++d) X[a * DIM + d] = src[d];
+        }
+        if (CMODE != 0) {
+            for (int idx = tid; idx < nvalid * extra; idx += nthreads) {
+                const int el = idx / extra, i = idx - el * extra;
+                const double* src = CMODE == 1 ? C + (e0 + el) * NC : C + (e0 + el) * (long long)(nPg * NC);
+                (sm.elem(smem, el) + sm.o_extra())[i] = src[i] * kelvin_factor<DIM>((i % NC) / NS, i % NS);
             }
         }
     }
-    EFB_PHASE_E(tid, nthreads, kWarpLocal) {  // G2-G6 per Gauss point, in registers    _group_elem.py:832-1105
-        const int el = tid / TPE, t = tid % TPE;
-        if (el < EPB && e0 + el < g.Ne) {
+    EFB_PHASE(tid, nthreads) {  // G2-G6, one task per (element, Gauss point), in registers    _group_elem.py:832-1105
+#ifdef __CUDACC__
+        if (Tile::kBulk && tid == 0) bulk_store_wait_read();  // the previous batch has left the staging buffer
+#endif
+        for (int task = tid; task < nvalid * nPg; task += nthreads) {
+            const int el = task / nPg, p = task - el * nPg;
             double* E = sm.elem(smem, el);
             const double* X = E + sm.o_X();
-            for (int p = t; p < nPg; p += TPE) {
-                const double* dNp = dNt + p * TS;
-                double F[DIM * DIM], Fi[DIM * DIM];
+            const double* dNp = dNt + p * TS;
+            double F[DIM * DIM], Fi[DIM * DIM];
+            EFB_UNROLL
+            for (int i = 0; i < DIM * DIM; ++i) F[i] = 0.0;
+            EFB_UNROLL
+            for (int n = 0; n < NPE; ++n) {  // F[r][c] = sum_n dN[p][r][n] x[n][c]
                 EFB_UNROLL
-                for (int i = 0; i < DIM * DIM; ++i) F[i] = 0.0;
-                EFB_UNROLL
-                for (int n = 0; n < NPE; ++n) {  // F[r][c] = sum_n dN[p][r][n] x[n][c]
+                for (int r = 0; r < DIM; ++r)
                     EFB_UNROLL
-                    for (int r = 0; r < DIM; ++r)
-                        EFB_UNROLL
-                        for (int c = 0; c < DIM; ++c) F[r * DIM + c] += dNp[r * NPE + n] * X[n * DIM + c];
-                }
-                const double det = det_inv<DIM>(F, Fi);
-                E[sm.o_wJ() + p] = scale * (fabs(det) * wt[p]);
-                double* gp = E + sm.o_gN() + p * GPS;
+                    for (int c = 0; c < DIM; ++c) F[r * DIM + c] += dNp[r * NPE + n] * X[n * DIM + c];
+            }
+            const double det = det_inv<DIM>(F, Fi);
+            E[sm.o_wJ() + p] = scale * (fabs(det) * wt[p]);
+            double* gp = E + sm.o_gN() + p * GPS;
+            EFB_UNROLL
+            for (int a = 0; a < NPE; ++a) {  // gN[a][d] = sum_k Fi[d][k] dN[p][k][a]
                 EFB_UNROLL
-                for (int a = 0; a < NPE; ++a) {  // gN[a][d] = sum_k Fi[d][k] dN[p][k][a]
+                for (int d = 0; d < DIM; ++d) {
+                    double s = 0.0;
                     EFB_UNROLL
-                    for (int d = 0; d < DIM; ++d) {
-                        double s = 0.0;
-                        EFB_UNROLL
-                        for (int k = 0; k < DIM; ++k) s += Fi[d * DIM + k] * dNp[k * NPE + a];
-                        gp[a * GS + d] = s;
-                    }
+                    for (int k = 0; k < DIM; ++k) s += Fi[d * DIM + k] * dNp[k * NPE + a];
+                    gp[a * GS + d] = s;
                 }
             }
         }
     }
-    EFB_PHASE_E(tid, nthreads, kWarpLocal) {
-        const int el = tid / TPE, t = tid % TPE;
-        const long long e = e0 + el;
-        if (el < EPB && e < g.Ne) {
+    EFB_PHASE(tid, nthreads) {  // contraction: warp (i, h), lane (el, a)
+        const int warp = tid >> 5, lane = tid & 31;
+        const int grp = warp / WPG, wg = warp - grp * WPG;
+        const int i = wg / CS, h = wg - i * CS;
+        const int elw = lane / NPE, a = lane - elw * NPE;
+        const int el = grp * EPW + elw;
+        if (elw < EPW && el < nvalid) {
             const double* E = sm.elem(smem, el);
             const double* wJ = E + sm.o_wJ();
             const double* gN = E + sm.o_gN();
             const double* Cs = E + sm.o_extra();
-            const int a = t % NPE, b0 = (t / NPE) * NB;
-            double acc[DIM][NB * DIM];
-            EFB_UNROLL
-            for (int i = 0; i < DIM; ++i)
-                EFB_UNROLL
-                for (int j = 0; j < NB * DIM; ++j) acc[i][j] = 0.0;
-            for (int p = 0; p < nPg; ++p) {
-                const double* gp = gN + p * GPS;
-                const double w = wJ[p];
-                // C2(s, r) of this Gauss point: constant bank (mode 0) or shared memory
-#define EFB_C(s_, r_) (CMODE == 0 ? C2const.v[(s_) * NS + (r_)] : Cs[(CMODE == 2 ? p * NC : 0) + (s_) * NS + (r_)])
-                double bc[DIM][NS];
-                if constexpr (DIM == 2) {
-                    // G[:, (a,0)] = (gx, 0, gy); G[:, (a,1)] = (0, gy, gx)
-                    const double wx = w * gp[a * GS], wy = w * gp[a * GS + 1];
-                    EFB_UNROLL
-                    for (int r = 0; r < NS; ++r) {
-                        bc[0][r] = wx * EFB_C(0, r) + wy * EFB_C(2, r);
-                        bc[1][r] = wy * EFB_C(1, r) + wx * EFB_C(2, r);
-                    }
-                    EFB_UNROLL
-                    for (int b = 0; b < NB; ++b) {
-                        const Pair gb = *reinterpret_cast<const Pair*>(gp + (b0 + b) * GS);
-                        EFB_UNROLL
-                        for (int i = 0; i < 2; ++i) {
-                            double s0 = acc[i][b * 2 + 0], s1 = acc[i][b * 2 + 1];
-                            s0 += bc[i][0] * gb.x;
-                            s0 += bc[i][2] * gb.y;
-                            s1 += bc[i][1] * gb.y;
-                            s1 += bc[i][2] * gb.x;
-                            acc[i][b * 2 + 0] = s0;
-                            acc[i][b * 2 + 1] = s1;
-                        }
-                    }
-                } else {
-                    // G[:, (a,0)] = (gx,0,0,0,gz,gy); G[:, (a,1)] = (0,gy,0,gz,0,gx); G[:, (a,2)] = (0,0,gz,gy,gx,0)
-                    const double wx = w * gp[a * GS], wy = w * gp[a * GS + 1], wz = w * gp[a * GS + 2];
-                    EFB_UNROLL
-                    for (int r = 0; r < NS; ++r) {
-                        bc[0][r] = wx * EFB_C(0, r) + wz * EFB_C(4, r) + wy * EFB_C(5, r);
-                        bc[1][r] = wy * EFB_C(1, r) + wz * EFB_C(3, r) + wx * EFB_C(5, r);
-                        bc[2][r] = wz * EFB_C(2, r) + wy * EFB_C(3, r) + wx * EFB_C(4, r);
-                    }
-                    EFB_UNROLL
-                    for (int b = 0; b < NB; ++b) {
-                        const Pair gxy = *reinterpret_cast<const Pair*>(gp + (b0 + b) * GS);
-                        const double gx = gxy.x, gy = gxy.y, gz = gp[(b0 + b) * GS + 2];
-                        EFB_UNROLL
-                        for (int i = 0; i < 3; ++i) {
-                            double s0 = acc[i][b * 3 + 0], s1 = acc[i][b * 3 + 1], s2 = acc[i][b * 3 + 2];
-                            s0 += bc[i][0] * gx;
-                            s0 += bc[i][4] * gz;
-                            s0 += bc[i][5] * gy;
-                            s1 += bc[i][1] * gy;
-                            s1 += bc[i][3] * gz;
-                            s1 += bc[i][5] * gx;
-                            s2 += bc[i][2] * gz;
-                            s2 += bc[i][3] * gy;
-                            s2 += bc[i][4] * gx;
-                            acc[i][b * 3 + 0] = s0;
-                            acc[i][b * 3 + 1] = s1;
-                            acc[i][b * 3 + 2] = s2;
-                        }
-                    }
-                }
-#undef EFB_C
+            const int b0 = h * NB;
+            double acc[NB * DIM];
+            if (i == 0) elastic_row<DIM, NPE, CMODE, 0>(C2const, Cs, wJ, gN, nPg, a, b0, acc);
+            if (i == 1) elastic_row<DIM, NPE, CMODE, 1>(C2const, Cs, wJ, gN, nPg, a, b0, acc);
+            if constexpr (DIM == 3) {
+                if (i == 2) elastic_row<DIM, NPE, CMODE, 2>(C2const, Cs, wJ, gN, nPg, a, b0, acc);
             }
-            // rows (a,i) of K_e, columns of the NB nodes of this chunk: NB*DIM contiguous doubles per row
-            double* dst = out + e * (long long)(NDOF * NDOF) + (long long)(a * DIM) * NDOF + b0 * DIM;
+            // row (a,i) of K_e, columns of the NB nodes of this chunk: NB*DIM contiguous doubles
+            double* dst = stage + el * KE + (a * DIM + i) * NDOF + b0 * DIM;
             constexpr bool kVec = (NDOF % 2 == 0) && ((NB * DIM) % 2 == 0);
-            EFB_UNROLL
-            for (int i = 0; i < DIM; ++i) {
-                if constexpr (kVec) {
-                    EFB_UNROLL
-                    for (int j = 0; j < NB * DIM; j += 2) {
-                        Pair v;
-                        v.x = acc[i][j];
-                        v.y = acc[i][j + 1];
-                        *reinterpret_cast<Pair*>(dst + i * NDOF + j) = v;
-                    }
-                } else {
-                    EFB_UNROLL
-                    for (int j = 0; j < NB * DIM; ++j) dst[i * NDOF + j] = acc[i][j];
+            if constexpr (kVec) {
+                EFB_UNROLL
+                for (int j = 0; j < NB * DIM; j += 2) {
+                    Pair v;
+                    v.x = acc[j];
+                    v.y = acc[j + 1];
+                    *reinterpret_cast<Pair*>(dst + j) = v;
                 }
+            } else {
+                EFB_UNROLL
+                for (int j = 0; j < NB * DIM; ++j) dst[j] = acc[j];
             }
         }
+#ifdef __CUDACC__
+        // every writer orders its generic-proxy stores before the async proxy reads them (then the phase barrier)
+        if constexpr (Tile::kBulk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
     }
+    // the batch's element matrices are contiguous in `out`
+    double* gdst = out + e0 * (long long)KE;
+#ifdef __CUDACC__
+    if constexpr (Tile::kBulk) {
+        if (threadIdx.x == 0) bulk_store_issue(gdst, stage, (unsigned)(nvalid * KE * sizeof(double)));
+    } else {
+        for (int idx = threadIdx.x; idx < nvalid * KE; idx += nthreads) gdst[idx] = stage[idx];
+        __syncthreads();
+    }
+#else
+    for (int idx = 0; idx < nvalid * KE; ++idx) gdst[idx] = stage[idx];
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -549,3 +549,84 @@ def assemble_replay(datas, inv, nnz):
     """csr.data = bincount(inv, weights=concat(data)), `__Assemble_csr`, _simu.py:1037,1055 (ordered sum)."""
     data = np.concatenate([np.asarray(d).ravel() for d in datas])
     return np.bincount(inv, weights=data, minlength=nnz)
+
+
+# =========================================================================================================
+# consumers: Dirichlet solve and the staggered phase-field loop
+#                          EasyFEA/Simulations/Solvers.py:502-553, Simulations/_phasefield.py:300-432, 444-578
+# =========================================================================================================
+def solve_dirichlet(A, b, dofs_known, x_known):
+    """x with x[known] prescribed: A_uu x_u = b_u - A_uk x_k (`__Solver_1`, Solvers.py:502-553), direct solve like the
+    reference's default `scipy` solver (`spsolve`)."""
+    import scipy.sparse.linalg as spla
+
+    n = A.shape[0]
+    known = np.zeros(n, bool)
+    known[dofs_known] = True
+    x = np.zeros(n)
+    x[dofs_known] = x_known
+    free = ~known
+    rhs = b[free] - (A[free] @ x)
+    x[free] = spla.spsolve(A[free][:, free].tocsc(), rhs)
+    return x
+
+
+class StaggeredOracle:
+    """`Simulations.PhaseField` reduced to what the staggered loop does on ONE element group (History solver, AT1/AT2)."""
+
+    def __init__(self, coords, connect, dN_rigi, w_rigi, N_rigi, dN_mass, w_mass, N_mass, mat, split, regu, Gc, l0, thickness=1.0):
+        import scipy.sparse as sp
+
+        self.sp = sp
+        dim = mat.dim
+        self.dim, self.mat, self.split, self.regu, self.Gc, self.l0 = dim, mat, split, regu, Gc, l0
+        self.connect, self.Nn = connect, coords.shape[0]
+        self.geo_r = geometry(coords[connect][:, :, :dim], dN_rigi, w_rigi)
+        self.geo_m = geometry(coords[connect][:, :, :dim], dN_mass, w_mass)
+        self.N_r, self.N_m = N_rigi, N_mass
+        self.thickness = thickness if dim == 2 else 1.0
+        self.u, self.d = np.zeros(self.Nn * dim), np.zeros(self.Nn)
+        self.psiP, self.psiP_old = None, None
+        self.map_u = csr_map([connect], dim, self.Nn * dim, True)
+        self.map_d = csr_map([connect], 1, self.Nn, True)
+        self.bc_u, self.bc_d = ([], []), ([], [])
+
+    def Bc_Init(self):
+        self.bc_u, self.bc_d = ([], []), ([], [])
+
+    def add_dirichlet(self, nodes, values, components, problemType="elastic"):
+        dofs, vals = self.bc_d if problemType == "damage" else self.bc_u
+        dn = 1 if problemType == "damage" else self.dim
+        for v, c in zip(values, components):
+            dofs.append(np.asarray(nodes) * dn + c)
+            vals.append(np.full(len(nodes), float(v)))
+
+    def _csr(self, Xe, m, n):
+        inv, indices, indptr, nnz = m
+        return self.sp.csr_matrix((assemble_replay([Xe], inv, nnz), indices, indptr), shape=(n, n))
+
+    def iterate(self):
+        dim = self.dim
+        u_e = locate_sol_e(self.u, self.connect, dim)
+        Ke, Fe, self.psiP = pf_damage_system(self.geo_m, self.N_m, self.mat, self.split, self.regu, self.Gc, self.l0, u_e,
+                                             self.psiP_old)
+        Kd = self._csr(Ke * self.thickness, self.map_d, self.Nn)
+        Fd = np.bincount(self.connect.ravel(), weights=(Fe[..., 0] * self.thickness).ravel(), minlength=self.Nn)
+        d_n = self.d
+        self.d = solve_dirichlet(Kd, Fd, np.concatenate(self.bc_d[0]), np.concatenate(self.bc_d[1]))
+        Ke = pf_elastic_Ke(self.geo_r, self.N_r, self.mat, self.split, u_e, self.d[self.connect]) * self.thickness
+        Ku = self._csr(Ke, self.map_u, self.Nn * dim)
+        self.u = solve_dirichlet(Ku, np.zeros(self.Nn * dim), np.concatenate(self.bc_u[0]), np.concatenate(self.bc_u[1]))
+        return np.max(np.abs(self.d - d_n))
+
+    def Solve(self, tolConv=1.0, maxIter=500):
+        Niter, converged = 0, False
+        while not converged and Niter < maxIter:
+            Niter += 1
+            conv = self.iterate()
+            converged = tolConv == 1 or self.d.max() == 0 or conv <= tolConv
+        self.Niter = Niter
+        return self.u, self.d, converged
+
+    def Save_Iter(self):
+        self.psiP_old = self.psiP

@@ -53,7 +53,8 @@ extern "C" int hc_geometry(const efb_group* g, double* F, double* detF, double* 
 template <int D, int N, int CMODE>
 static void run_elastic(const efb_group* g, const double* C, double scale, double* out) {
     constexpr int NS = StrainSize<D>::value;
-    const int TPE = ElasticTile<D, N>::TPE, EPB = epb_for(TPE);
+    using Tile = ElasticTile<D, N>;
+    const int EPB = Tile::EPB;
     ElasticSmem<D, N> sm(g->nPg, EPB, CMODE == 2 ? g->nPg * NS * NS : (CMODE == 1 ? NS * NS : 0));
     std::vector<double> smem(sm.total());
     CMat Cc;
@@ -63,7 +64,7 @@ static void run_elastic(const efb_group* g, const double* C, double scale, doubl
         prescale_C<D>(Cc);
     }
     for (long long b = 0; b * EPB < g->Ne; ++b)  // tables are staged by the first batch only, like the persistent kernel
-        elastic_block<D, N, CMODE>(view_of(g), Cc, C, scale, out, EPB, b, EPB * TPE, smem.data(), b == 0);
+        elastic_block<D, N, CMODE>(view_of(g), Cc, C, scale, out, b, Tile::THREADS, smem.data(), b == 0);
 }
 
 extern "C" int hc_elastic_Ke(const efb_group* g, const double* C, int C_mode, double scale, double* out) {
