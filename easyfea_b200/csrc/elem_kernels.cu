@@ -1,4 +1,6 @@
 // C-ABI entry points of the element kernels: launch configuration + (dim, nPe) dispatch.
+#include <cuda.h>
+
 #include "common.cuh"
 #include "elem_kernels.cuh"
 
@@ -61,27 +63,165 @@ static int launch_geometry(const efb_group* g, const GeomOut& o, cudaStream_t st
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// persistent: each CTA walks element batches blockIdx.x, blockIdx.x + gridDim.x, ...; the reference-element tables are
-// staged once per CTA; several CTAs share an SM, so one CTA's gather/geometry phases overlap another's FP64 main loop
+// Warp-specialised persistent kernel.  CTA = NCW consumer warps (the contraction, pure FP64 + broadcast LDS) + one
+// producer warp (gather of connectivity/coordinates/C and the per-Gauss-point geometry), decoupled by two geometry
+// buffers in shared memory and four named barriers (full[b] / empty[b]): the producer runs up to two batches ahead, so
+// the global-load latency of the gather and the serial inverse-Jacobian chain never stall the FP64 warps.
+// Which warp of the CTA plays the producer ROTATES with a per-SM launch counter: warps map to the four SM sub-partitions
+// by warp id % 4, and each sub-partition has its own FP64 pipe, so co-resident CTAs must not all park their producer
+// (or, with 3 consumer warps, their idle slot) on the same sub-partition.
+// A consumer warp stages its finished rows in its own shared-memory tile and writes them with ONE TMA tensor store
+// (box = NB*DIM columns x NPE nodes x EPW elements of the view K_e[e][a][i][col]); the only synchronisation it needs for
+// that is its own bulk-group wait, so consumer warps never wait for each other.
+// Each CTA walks batches blockIdx.x, blockIdx.x + gridDim.x, ...
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+enum { kBarFull = 1, kBarEmpty = 3, kBarConsumers = 5 };  // ids 1,2 / 3,4 / 5 (0 is __syncthreads)
+
+__device__ unsigned int g_sm_launch_counter[1024];  // per-SM CTA arrival counter (only its value mod #warps matters)
+
+__device__ __forceinline__ void tma_store_tile_4d(const CUtensorMap* map, const double* ssrc, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+                 "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+template <int DIM, int NPE>
+constexpr int elastic_threads() {
+    return ElasticTile<DIM, NPE>::THREADS + 32;
+}
+
 template <int DIM, int NPE>
 constexpr int elastic_min_blocks() {
-    // aim at <= 112 registers per thread where the CTA is small enough for that to matter
-#ifndef EFB_ELASTIC_MINB96
-#define EFB_ELASTIC_MINB96 6
+#ifndef EFB_ELASTIC_MINB
+#define EFB_ELASTIC_MINB 4
 #endif
-    return ElasticTile<DIM, NPE>::THREADS <= 96 ? EFB_ELASTIC_MINB96 : (ElasticTile<DIM, NPE>::THREADS <= 128 ? 4 : 1);
+    return elastic_threads<DIM, NPE>() <= 160 ? EFB_ELASTIC_MINB : 1;
 }
 
 template <int DIM, int NPE, int CMODE>
-__global__ void __launch_bounds__(ElasticTile<DIM, NPE>::THREADS, elastic_min_blocks<DIM, NPE>())
-    k_elastic(GroupView g, CMat C2, const double* C, double scale, double* out, long long nblk) {
-    extern __shared__ __align__(16) double smem[];
-    bool first = true;
-    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-        elastic_block<DIM, NPE, CMODE>(g, C2, C, scale, out, blk, blockDim.x, smem, first);
-        first = false;
+__global__ void __launch_bounds__(elastic_threads<DIM, NPE>(), elastic_min_blocks<DIM, NPE>())
+    k_elastic(GroupView g, CMat C2, const double* __restrict__ C, double scale, double* __restrict__ out, long long nblk,
+              const __grid_constant__ CUtensorMap out_map) {
+    extern __shared__ __align__(128) double smem[];
+    constexpr int NS = StrainSize<DIM>::value, NC = NS * NS;
+    using SM = ElasticSmem<DIM, NPE>;
+    using Tile = ElasticTile<DIM, NPE>;
+    constexpr int TS = SM::TS, KE = SM::KE, EPB = Tile::EPB, EPW = Tile::EPW, NB = Tile::NB, CS = Tile::CS, WPG = Tile::WPG;
+    constexpr int NCT = Tile::THREADS, NT = NCT + 32, NW = NT / 32;  // consumer threads, all threads, warps
+    const int nPg = g.nPg;
+    const int extra = CMODE == 2 ? nPg * NC : (CMODE == 1 ? NC : 0);
+    const SM sm(nPg, EPB, extra);
+    double* dNt = smem + sm.off_dN();
+    double* wt = smem + sm.off_w();
+    double* stage = smem + sm.off_stage();
+    const int buf_stride = EPB * sm.per_elem();
+    double* bufs = sm.elem(smem, 0);
+    __shared__ int s_rot;
+
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        s_rot = (int)(atomicAdd(&g_sm_launch_counter[smid & 1023], 1u) % NW);
     }
-    if (ElasticTile<DIM, NPE>::kBulk && threadIdx.x == 0) bulk_store_wait_read();  // shared memory outlives the last copy
+    for (int i = threadIdx.x; i < nPg * DIM * NPE; i += NT) dNt[(i / (DIM * NPE)) * TS + i % (DIM * NPE)] = g.dN_pg[i];
+    for (int i = threadIdx.x; i < nPg; i += NT) wt[i] = g.w_pg[i];
+    __syncthreads();
+    // role of this warp: roles 0..NW-2 are the consumer warps (i, h) of elastic_contract, role NW-1 is the producer
+    const int lane = threadIdx.x & 31;
+    const int role = ((threadIdx.x >> 5) + NW - s_rot) % NW;
+    const int tid = role * 32 + lane;  // virtual thread id
+
+    if (role == NW - 1) {
+        // ---------------- producer warp ----------------
+        int k = 0;
+        for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x, ++k) {
+            const int b = k & 1;
+            if (k >= 2) named_sync(kBarEmpty + b, NT);  // consumers have finished reading buffer b (batch k-2)
+            double* E0 = bufs + b * buf_stride;
+            const long long e0 = blk * EPB;
+            const int nvalid = (g.Ne - e0 < EPB) ? (int)(g.Ne - e0) : EPB;
+            elastic_gather<DIM, NPE, CMODE>(g, sm, C, e0, nvalid, E0, lane, 32);
+            __syncwarp();
+            for (int task = lane; task < nvalid * nPg; task += 32)
+                elastic_geometry_task<DIM, NPE>(sm, dNt, wt, scale, E0 + (task / nPg) * sm.per_elem(), task % nPg);
+            __threadfence_block();
+            named_arrive(kBarFull + b, NT);
+        }
+    } else {
+        // ---------------- consumer warps ----------------
+        const int grp = role / WPG, wg = role - grp * WPG;
+        const int ci = wg / CS, ch = wg - ci * CS;  // row component and column chunk of this warp
+        int k = 0;
+        for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x, ++k) {
+            const int b = k & 1;
+            const double* E0 = bufs + b * buf_stride;
+            const long long e0 = blk * EPB;
+            const int nvalid = (g.Ne - e0 < EPB) ? (int)(g.Ne - e0) : EPB;
+            if constexpr (Tile::kTensor) {
+                if (lane == 0) bulk_store_wait_read();  // my previous tile has left shared memory
+                __syncwarp();
+                named_sync(kBarFull + b, NT);  // geometry of batch k is in buffer b
+                elastic_contract<DIM, NPE, CMODE, true>(sm, C2, nPg, nvalid, E0, stage, tid);
+                named_arrive(kBarEmpty + b, NT);  // buffer b may be refilled
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my generic-proxy stores -> async proxy
+                __syncwarp();
+                if (lane == 0 && grp * EPW < nvalid)  // elements past Ne are clipped by the tensor map bounds
+                    tma_store_tile_4d(&out_map, stage + role * Tile::WARP_TILE, ch * NB * DIM, ci, 0, (int)(e0 + grp * EPW));
+            } else {
+                double* gdst = out + e0 * (long long)KE;
+                named_sync(kBarFull + b, NT);
+                elastic_contract<DIM, NPE, CMODE, false>(sm, C2, nPg, nvalid, E0, stage, tid);
+                named_arrive(kBarEmpty + b, NT);
+                named_sync(kBarConsumers, NCT);
+                for (int idx = tid; idx < nvalid * KE; idx += NCT) gdst[idx] = stage[idx];
+                named_sync(kBarConsumers, NCT);
+            }
+        }
+        if (Tile::kTensor && lane == 0) bulk_store_wait_read();  // shared memory outlives the last copy
+    }
+}
+
+// 4-D tensor map of the output viewed as K_e[e][a][i][col] (innermost first: col, i, a, e) with the store box of one warp
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+template <int DIM, int NPE>
+static int make_out_map(CUtensorMap* map, double* out, long long Ne) {
+    using Tile = ElasticTile<DIM, NPE>;
+    memset(map, 0, sizeof(*map));
+    if (!Tile::kTensor) return 0;
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return 1;
+    }
+    constexpr cuuint64_t NDOF = DIM * NPE;
+    const cuuint64_t gdim[4] = {NDOF, (cuuint64_t)DIM, (cuuint64_t)NPE, (cuuint64_t)Ne};
+    const cuuint64_t gstride[3] = {NDOF * 8, DIM * NDOF * 8, NDOF * NDOF * 8};  // bytes, dims 1..3
+    const cuuint32_t box[4] = {(cuuint32_t)(Tile::NB * DIM), 1, (cuuint32_t)NPE, (cuuint32_t)Tile::EPW};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, out, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return 1;
+    }
+    return 0;
 }
 
 // CTAs that keep every SM full: resident CTAs per SM (occupancy query) x number of SMs
@@ -102,12 +242,15 @@ static int launch_elastic_mode(const efb_group* g, const CMat& C2, const double*
     using Tile = ElasticTile<DIM, NPE>;
     const int extra = CMODE == 2 ? g->nPg * NS * NS : (CMODE == 1 ? NS * NS : 0);
     const SM sm(g->nPg, Tile::EPB, extra);
-    const size_t bytes = sizeof(double) * sm.total();
+    const size_t bytes = sizeof(double) * sm.total2();
     if (ensure_smem(k_elastic<DIM, NPE, CMODE>, bytes)) return 1;
     const long long nblk = (g->Ne + Tile::EPB - 1) / Tile::EPB;
     if (nblk == 0) return 0;
-    const long long grid = persistent_grid(k_elastic<DIM, NPE, CMODE>, Tile::THREADS, bytes, nblk);
-    k_elastic<DIM, NPE, CMODE><<<(unsigned)grid, Tile::THREADS, bytes, st>>>(view_of(g), C2, C, scale, out, nblk);
+    constexpr int NT = elastic_threads<DIM, NPE>();
+    CUtensorMap map;
+    if (make_out_map<DIM, NPE>(&map, out, g->Ne)) return 1;
+    const long long grid = persistent_grid(k_elastic<DIM, NPE, CMODE>, NT, bytes, nblk);
+    k_elastic<DIM, NPE, CMODE><<<(unsigned)grid, NT, bytes, st>>>(view_of(g), C2, C, scale, out, nblk, map);
     return check_launch("efb_elastic_Ke");
 }
 

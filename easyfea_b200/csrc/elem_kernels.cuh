@@ -284,6 +284,11 @@ struct ElasticTile {
     static constexpr int EPB = G * EPW;                                              // elements per CTA batch
     static constexpr int THREADS = G * WPG * 32;
     static constexpr bool kBulk = (NDOF * NDOF) % 2 == 0;  // bulk copies move multiples of 16 bytes
+    // TMA tensor store of a warp's rows: box (NB*DIM cols, 1 component, NPE nodes, EPW elements) of the 4-D view
+    // K_e[e][a][i][col]; needs 16-byte multiples for the box row and the global strides
+    static constexpr bool kTensor = (NB * DIM) % 2 == 0 && NDOF % 2 == 0;
+    static constexpr int WARP_TILE = (EPW * NPE * NB * DIM + 15) & ~15;  // doubles staged per consumer warp (128-byte multiple)
+    static constexpr int STAGE = (G * WPG * WARP_TILE > EPB * NDOF * NDOF) ? G * WPG * WARP_TILE : EPB * NDOF * NDOF;
     static_assert(NB * CS == NPE, "CS must divide NPE");
     static_assert(EPW >= 1, "an element needs at most one warp of lanes");
 };
@@ -299,7 +304,7 @@ struct ElasticSmem {
     int nPg, EPB, extra;
     EFB_HD ElasticSmem(int nPg_, int EPB_, int extra_) : nPg(nPg_), EPB(EPB_), extra(extra_) {}
     EFB_HD int off_stage() const { return 0; }  // first: 16-byte aligned for the bulk copy
-    EFB_HD int off_dN() const { return (EPB * KE + 1) & ~1; }
+    EFB_HD int off_dN() const { return (ElasticTile<DIM, NPE>::STAGE + 1) & ~1; }
     EFB_HD int off_w() const { return off_dN() + nPg * TS; }
     EFB_HD int tables_padded() const { return (off_w() + nPg + 1) & ~1; }
     EFB_HD int o_X() const { return 0; }
@@ -312,6 +317,7 @@ struct ElasticSmem {
         return (n % 4 == 2) ? n : n + 2;
     }
     EFB_HD int total() const { return tables_padded() + EPB * per_elem(); }
+    EFB_HD int total2() const { return tables_padded() + 2 * EPB * per_elem(); }  // two geometry buffers (pipelined kernel)
     EFB_HD double* elem(double* smem, int el) const { return smem + tables_padded() + el * per_elem(); }
 };
 
@@ -391,14 +397,118 @@ __device__ __forceinline__ void bulk_store_issue(double* gdst, const double* ssr
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 #endif
 
+// ---- the three stages of one batch of EPB elements, shared by the phase-structured body (host emulation) and the
+// ---- warp-specialised device kernel.  `E0` = first per-element record of the geometry buffer in use.
+
+// gather: nodal coordinates (and C, scaled to C2) of the batch -> shared memory; executed by `nth` cooperating threads
+template <int DIM, int NPE, int CMODE>
+EFB_D void elastic_gather(const GroupView& g, const ElasticSmem<DIM, NPE>& sm, const double* EFB_RESTRICT C, long long e0,
+                          int nvalid, double* E0, int t, int nth) {
+    constexpr int NS = StrainSize<DIM>::value, NC = NS * NS;
+    const int nPg = g.nPg, extra = sm.extra, pe = sm.per_elem();
+    for (int idx = t; idx < nvalid * NPE; idx += nth) {
+        const int el = idx / NPE, a = idx - el * NPE;
+        const double* src = g.coord + (long long)g.connect[(e0 + el) * NPE + a] * g.coord_stride;
+        double* X = E0 + el * pe + sm.o_X();
+        EFB_UNROLL
+        for (int d = 0; d < DIM; ++d) X[a * DIM + d] = src[d];
+    }
+    if (CMODE != 0) {
+        for (int idx = t; idx < nvalid * extra; idx += nth) {
+            const int el = idx / extra, i = idx - el * extra;
+            const double* src = CMODE == 1 ? C + (e0 + el) * NC : C + (e0 + el) * (long long)(nPg * NC);
+            (E0 + el * pe + sm.o_extra())[i] = src[i] * kelvin_factor<DIM>((i % NC) / NS, i % NS);
+        }
+    }
+}
+
+// G2-G6 for one (element, Gauss point), in registers                    _group_elem.py:832-1105
+template <int DIM, int NPE>
+EFB_D void elastic_geometry_task(const ElasticSmem<DIM, NPE>& sm, const double* dNt, const double* wt, double scale, double* E,
+                                 int p) {
+    using SM = ElasticSmem<DIM, NPE>;
+    constexpr int GS = SM::GS, TS = SM::TS, GPS = SM::GPS;
+    const double* X = E + sm.o_X();
+    const double* dNp = dNt + p * TS;
+    double F[DIM * DIM], Fi[DIM * DIM];
+    EFB_UNROLL
+    for (int i = 0; i < DIM * DIM; ++i) F[i] = 0.0;
+    EFB_UNROLL
+    for (int n = 0; n < NPE; ++n) {  // F[r][c] = sum_n dN[p][r][n] x[n][c]
+        EFB_UNROLL
+        for (int r = 0; r < DIM; ++r)
+            EFB_UNROLL
+            for (int c = 0; c < DIM; ++c) F[r * DIM + c] += dNp[r * NPE + n] * X[n * DIM + c];
+    }
+    const double det = det_inv<DIM>(F, Fi);
+    E[sm.o_wJ() + p] = scale * (fabs(det) * wt[p]);
+    double* gp = E + sm.o_gN() + p * GPS;
+    EFB_UNROLL
+    for (int a = 0; a < NPE; ++a) {  // gN[a][d] = sum_k Fi[d][k] dN[p][k][a]
+        EFB_UNROLL
+        for (int d = 0; d < DIM; ++d) {
+            double s = 0.0;
+            EFB_UNROLL
+            for (int k = 0; k < DIM; ++k) s += Fi[d * DIM + k] * dNp[k * NPE + a];
+            gp[a * GS + d] = s;
+        }
+    }
+}
+
+// contraction of consumer thread `tid` (warp (i, h), lane (el, a)): one row of K_e into the staging buffer
+// WARP_STAGE: the warp's rows go to its own dense tile [elw][a][NB*DIM] (source box of the TMA tensor store) instead of the
+// K_e layout
+template <int DIM, int NPE, int CMODE, bool WARP_STAGE = false>
+EFB_D void elastic_contract(const ElasticSmem<DIM, NPE>& sm, const CMat& C2const, int nPg, int nvalid, const double* E0,
+                            double* stage, int tid) {
+    using SM = ElasticSmem<DIM, NPE>;
+    using Tile = ElasticTile<DIM, NPE>;
+    constexpr int NDOF = DIM * NPE, KE = SM::KE;
+    constexpr int NB = Tile::NB, CS = Tile::CS, EPW = Tile::EPW, WPG = Tile::WPG;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int grp = warp / WPG, wg = warp - grp * WPG;
+    const int i = wg / CS, h = wg - i * CS;
+    const int elw = lane / NPE, a = lane - elw * NPE;
+    const int el = grp * EPW + elw;
+    if (elw < EPW && el < nvalid) {
+        const double* E = E0 + el * sm.per_elem();
+        const double* wJ = E + sm.o_wJ();
+        const double* gN = E + sm.o_gN();
+        const double* Cs = E + sm.o_extra();
+        const int b0 = h * NB;
+        double acc[NB * DIM];
+        if (i == 0) elastic_row<DIM, NPE, CMODE, 0>(C2const, Cs, wJ, gN, nPg, a, b0, acc);
+        if (i == 1) elastic_row<DIM, NPE, CMODE, 1>(C2const, Cs, wJ, gN, nPg, a, b0, acc);
+        if constexpr (DIM == 3) {
+            if (i == 2) elastic_row<DIM, NPE, CMODE, 2>(C2const, Cs, wJ, gN, nPg, a, b0, acc);
+        }
+        // row (a,i) of K_e, columns of the NB nodes of this chunk: NB*DIM contiguous doubles
+        double* dst = WARP_STAGE ? stage + warp * Tile::WARP_TILE + (elw * NPE + a) * (NB * DIM)
+                                 : stage + el * KE + (a * DIM + i) * NDOF + b0 * DIM;
+        constexpr bool kVec = (NDOF % 2 == 0) && ((NB * DIM) % 2 == 0);
+        if constexpr (kVec) {
+            EFB_UNROLL
+            for (int j = 0; j < NB * DIM; j += 2) {
+                Pair v;
+                v.x = acc[j];
+                v.y = acc[j + 1];
+                *reinterpret_cast<Pair*>(dst + j) = v;
+            }
+        } else {
+            EFB_UNROLL
+            for (int j = 0; j < NB * DIM; ++j) dst[j] = acc[j];
+        }
+    }
+}
+
+// phase-structured body: every stage ends with a CTA barrier (this is what tests/hostcheck emulates)
 template <int DIM, int NPE, int CMODE>
 EFB_D void elastic_block(const GroupView& g, const CMat& C2const, const double* EFB_RESTRICT C, double scale,
                          double* EFB_RESTRICT out, long long blockId, int nthreads, double* smem, bool load_tables = true) {
-    constexpr int NS = StrainSize<DIM>::value, NDOF = DIM * NPE, NC = NS * NS;
+    constexpr int NS = StrainSize<DIM>::value, NC = NS * NS;
     using SM = ElasticSmem<DIM, NPE>;
     using Tile = ElasticTile<DIM, NPE>;
-    constexpr int GS = SM::GS, TS = SM::TS, GPS = SM::GPS, KE = SM::KE;
-    constexpr int NB = Tile::NB, CS = Tile::CS, EPW = Tile::EPW, WPG = Tile::WPG, EPB = Tile::EPB;
+    constexpr int TS = SM::TS, KE = SM::KE, EPB = Tile::EPB;
     const int nPg = g.nPg;
     const int extra = CMODE == 2 ? nPg * NC : (CMODE == 1 ? NC : 0);
     const SM sm(nPg, EPB, extra);
@@ -407,6 +517,7 @@ EFB_D void elastic_block(const GroupView& g, const CMat& C2const, const double* 
     double* dNt = smem + sm.off_dN();
     double* wt = smem + sm.off_w();
     double* stage = smem + sm.off_stage();
+    double* E0 = sm.elem(smem, 0);
 
     if (load_tables) {
         EFB_PHASE(tid, nthreads) {
@@ -414,107 +525,16 @@ EFB_D void elastic_block(const GroupView& g, const CMat& C2const, const double* 
             for (int i = tid; i < nPg; i += nthreads) wt[i] = g.w_pg[i];
         }
     }
-    EFB_PHASE(tid, nthreads) {  // gather the nodal coordinates (and C)
-        for (int idx = tid; idx < nvalid * NPE; idx += nthreads) {
-            const int el = idx / NPE, a = idx - el * NPE;
-            const double* src = g.coord + (long long)g.connect[(e0 + el) * NPE + a] * g.coord_stride;
-            double* X = sm.elem(smem, el) + sm.o_X();
-            EFB_UNROLL
-            for (int d = 0; d < DIM; ++d) X[a * DIM + d] = src[d];
-        }
-        if (CMODE != 0) {
-            for (int idx = tid; idx < nvalid * extra; idx += nthreads) {
-                const int el = idx / extra, i = idx - el * extra;
-                const double* src = CMODE == 1 ? C + (e0 + el) * NC : C + (e0 + el) * (long long)(nPg * NC);
-                (sm.elem(smem, el) + sm.o_extra())[i] = src[i] * kelvin_factor<DIM>((i % NC) / NS, i % NS);
-            }
-        }
+    EFB_PHASE(tid, nthreads) { elastic_gather<DIM, NPE, CMODE>(g, sm, C, e0, nvalid, E0, tid, nthreads); }
+    EFB_PHASE(tid, nthreads) {
+        for (int task = tid; task < nvalid * nPg; task += nthreads)
+            elastic_geometry_task<DIM, NPE>(sm, dNt, wt, scale, E0 + (task / nPg) * sm.per_elem(), task % nPg);
     }
-    EFB_PHASE(tid, nthreads) {  // G2-G6, one task per (element, Gauss point), in registers    _group_elem.py:832-1105
-#ifdef __CUDACC__
-        if (Tile::kBulk && tid == 0) bulk_store_wait_read();  // the previous batch has left the staging buffer
-#endif
-        for (int task = tid; task < nvalid * nPg; task += nthreads) {
-            const int el = task / nPg, p = task - el * nPg;
-            double* E = sm.elem(smem, el);
-            const double* X = E + sm.o_X();
-            const double* dNp = dNt + p * TS;
-            double F[DIM * DIM], Fi[DIM * DIM];
-            EFB_UNROLL
-            for (int i = 0; i < DIM * DIM; ++i) F[i] = 0.0;
-            EFB_UNROLL
-            for (int n = 0; n < NPE; ++n) {  // F[r][c] = sum_n dN[p][r][n] x[n][c]
-                EFB_UNROLL
-                for (int r = 0; r < DIM; ++r)
-                    EFB_UNROLL
-                    for (int c = 0; c < DIM; ++c) F[r * DIM + c] += dNp[r * NPE + n] * X[n * DIM + c];
-            }
-            const double det = det_inv<DIM>(F, Fi);
-            E[sm.o_wJ() + p] = scale * (fabs(det) * wt[p]);
-            double* gp = E + sm.o_gN() + p * GPS;
-            EFB_UNROLL
-            for (int a = 0; a < NPE; ++a) {  // gN[a][d] = sum_k Fi[d][k] dN[p][k][a]
-                EFB_UNROLL
-                for (int d = 0; d < DIM; ++d) {
-                    double s = 0.0;
-                    EFB_UNROLL
-                    for (int k = 0; k < DIM; ++k) s += Fi[d * DIM + k] * dNp[k * NPE + a];
-                    gp[a * GS + d] = s;
-                }
-            }
-        }
+    EFB_PHASE(tid, nthreads) { elastic_contract<DIM, NPE, CMODE>(sm, C2const, nPg, nvalid, E0, stage, tid); }
+    EFB_PHASE(tid, nthreads) {  // the batch's element matrices are contiguous in `out`
+        double* gdst = out + e0 * (long long)KE;
+        for (int idx = tid; idx < nvalid * KE; idx += nthreads) gdst[idx] = stage[idx];
     }
-    EFB_PHASE(tid, nthreads) {  // contraction: warp (i, h), lane (el, a)
-        const int warp = tid >> 5, lane = tid & 31;
-        const int grp = warp / WPG, wg = warp - grp * WPG;
-        const int i = wg / CS, h = wg - i * CS;
-        const int elw = lane / NPE, a = lane - elw * NPE;
-        const int el = grp * EPW + elw;
-        if (elw < EPW && el < nvalid) {
-            const double* E = sm.elem(smem, el);
-            const double* wJ = E + sm.o_wJ();
-            const double* gN = E + sm.o_gN();
-            const double* Cs = E + sm.o_extra();
-            const int b0 = h * NB;
-            double acc[NB * DIM];
-            if (i == 0) elastic_row<DIM, NPE, CMODE, 0>(C2const, Cs, wJ, gN, nPg, a, b0, acc);
-            if (i == 1) elastic_row<DIM, NPE, CMODE, 1>(C2const, Cs, wJ, gN, nPg, a, b0, acc);
-            if constexpr (DIM == 3) {
-                if (i == 2) elastic_row<DIM, NPE, CMODE, 2>(C2const, Cs, wJ, gN, nPg, a, b0, acc);
-            }
-            // row (a,i) of K_e, columns of the NB nodes of this chunk: NB*DIM contiguous doubles
-            double* dst = stage + el * KE + (a * DIM + i) * NDOF + b0 * DIM;
-            constexpr bool kVec = (NDOF % 2 == 0) && ((NB * DIM) % 2 == 0);
-            if constexpr (kVec) {
-                EFB_UNROLL
-                for (int j = 0; j < NB * DIM; j += 2) {
-                    Pair v;
-                    v.x = acc[j];
-                    v.y = acc[j + 1];
-                    *reinterpret_cast<Pair*>(dst + j) = v;
-                }
-            } else {
-                EFB_UNROLL
-                for (int j = 0; j < NB * DIM; ++j) dst[j] = acc[j];
-            }
-        }
-#ifdef __CUDACC__
-        // every writer orders its generic-proxy stores before the async proxy reads them (then the phase barrier)
-        if constexpr (Tile::kBulk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#endif
-    }
-    // the batch's element matrices are contiguous in `out`
-    double* gdst = out + e0 * (long long)KE;
-#ifdef __CUDACC__
-    if constexpr (Tile::kBulk) {
-        if (threadIdx.x == 0) bulk_store_issue(gdst, stage, (unsigned)(nvalid * KE * sizeof(double)));
-    } else {
-        for (int idx = threadIdx.x; idx < nvalid * KE; idx += nthreads) gdst[idx] = stage[idx];
-        __syncthreads();
-    }
-#else
-    for (int idx = 0; idx < nvalid * KE; ++idx) gdst[idx] = stage[idx];
-#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------
