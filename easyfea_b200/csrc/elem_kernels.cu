@@ -1,6 +1,4 @@
 // C-ABI entry points of the element kernels: launch configuration + (dim, nPe) dispatch.
-#include <cuda.h>
-
 #include "common.cuh"
 #include "elem_kernels.cuh"
 
@@ -63,30 +61,36 @@ static int launch_geometry(const efb_group* g, const GeomOut& o, cudaStream_t st
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Warp-specialised persistent kernel.  CTA = NCW consumer warps (the contraction, pure FP64 + broadcast LDS) + one
+// Warp-specialised persistent kernel.  CTA = NCW consumer warps (the contraction: FP64 FMAs fed by broadcast LDS) + one
 // producer warp (gather of connectivity/coordinates/C and the per-Gauss-point geometry), decoupled by two geometry
 // buffers in shared memory and four named barriers (full[b] / empty[b]): the producer runs up to two batches ahead, so
 // the global-load latency of the gather and the serial inverse-Jacobian chain never stall the FP64 warps.
 // Which warp of the CTA plays the producer ROTATES with a per-SM launch counter: warps map to the four SM sub-partitions
-// by warp id % 4, and each sub-partition has its own FP64 pipe, so co-resident CTAs must not all park their producer
-// (or, with 3 consumer warps, their idle slot) on the same sub-partition.
-// A consumer warp stages its finished rows in its own shared-memory tile and writes them with ONE TMA tensor store
-// (box = NB*DIM columns x NPE nodes x EPW elements of the view K_e[e][a][i][col]); the only synchronisation it needs for
-// that is its own bulk-group wait, so consumer warps never wait for each other.
+// by warp id % 4 and each sub-partition has its own FP64 pipe, so co-resident CTAs must not all park their producer on
+// the same sub-partition.
+// A consumer lane stages its DIM finished rows in its own padded (bank-conflict-free) shared-memory tile and sends them
+// to HBM with bulk asynchronous copies (TMA engine, cp.async.bulk): the rows of one node are contiguous in K_e, so one
+// copy per lane (CS == 1) or per row (CS > 1) is enough, and the only synchronisation is the lane's own bulk-group wait —
+// consumer warps never wait for each other and never sit on store queues.
 // Each CTA walks batches blockIdx.x, blockIdx.x + gridDim.x, ...
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-enum { kBarFull = 1, kBarEmpty = 3, kBarConsumers = 5 };  // ids 1,2 / 3,4 / 5 (0 is __syncthreads)
+enum { kBarFull = 1, kBarEmpty = 3 };  // ids 1,2 / 3,4 (0 is __syncthreads)
 
 __device__ unsigned int g_sm_launch_counter[1024];  // per-SM CTA arrival counter (only its value mod #warps matters)
 
-__device__ __forceinline__ void tma_store_tile_4d(const CUtensorMap* map, const double* ssrc, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
-                 "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
                  : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async16(double* sdst, const double* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <int DIM, int NPE>
 constexpr int elastic_threads() {
@@ -96,27 +100,26 @@ constexpr int elastic_threads() {
 template <int DIM, int NPE>
 constexpr int elastic_min_blocks() {
 #ifndef EFB_ELASTIC_MINB
-#define EFB_ELASTIC_MINB 4
+#define EFB_ELASTIC_MINB 2
 #endif
-    return elastic_threads<DIM, NPE>() <= 160 ? EFB_ELASTIC_MINB : 1;
+    return EFB_ELASTIC_MINB;
 }
 
 template <int DIM, int NPE, int CMODE>
 __global__ void __launch_bounds__(elastic_threads<DIM, NPE>(), elastic_min_blocks<DIM, NPE>())
-    k_elastic(GroupView g, CMat C2, const double* __restrict__ C, double scale, double* __restrict__ out, long long nblk,
-              const __grid_constant__ CUtensorMap out_map) {
+    k_elastic(GroupView g, CMat C2, const double* __restrict__ C, double scale, double* __restrict__ out, long long nblk) {
     extern __shared__ __align__(128) double smem[];
-    constexpr int NS = StrainSize<DIM>::value, NC = NS * NS;
+    constexpr int NS = StrainSize<DIM>::value, NC = NS * NS, NDOF = DIM * NPE;
     using SM = ElasticSmem<DIM, NPE>;
     using Tile = ElasticTile<DIM, NPE>;
-    constexpr int TS = SM::TS, KE = SM::KE, EPB = Tile::EPB, EPW = Tile::EPW, NB = Tile::NB, CS = Tile::CS, WPG = Tile::WPG;
+    constexpr int TS = SM::TS, KE = SM::KE, EPB = Tile::EPB, NB = Tile::NB, CS = Tile::CS;
     constexpr int NCT = Tile::THREADS, NT = NCT + 32, NW = NT / 32;  // consumer threads, all threads, warps
+    constexpr int ROW = NB * DIM;                                    // doubles of one row piece
     const int nPg = g.nPg;
     const int extra = CMODE == 2 ? nPg * NC : (CMODE == 1 ? NC : 0);
     const SM sm(nPg, EPB, extra);
     double* dNt = smem + sm.off_dN();
     double* wt = smem + sm.off_w();
-    double* stage = smem + sm.off_stage();
     const int buf_stride = EPB * sm.per_elem();
     double* bufs = sm.elem(smem, 0);
     __shared__ int s_rot;
@@ -129,99 +132,126 @@ __global__ void __launch_bounds__(elastic_threads<DIM, NPE>(), elastic_min_block
     for (int i = threadIdx.x; i < nPg * DIM * NPE; i += NT) dNt[(i / (DIM * NPE)) * TS + i % (DIM * NPE)] = g.dN_pg[i];
     for (int i = threadIdx.x; i < nPg; i += NT) wt[i] = g.w_pg[i];
     __syncthreads();
-    // role of this warp: roles 0..NW-2 are the consumer warps (i, h) of elastic_contract, role NW-1 is the producer
+    // role of this warp: roles 0..NW-2 are the consumer warps, role NW-1 is the producer
     const int lane = threadIdx.x & 31;
     const int role = ((threadIdx.x >> 5) + NW - s_rot) % NW;
     const int tid = role * 32 + lane;  // virtual thread id
 
     if (role == NW - 1) {
         // ---------------- producer warp ----------------
+        // two-level software pipeline of the gather: node ids of batch k+2 and coordinates of batch k+1 are in flight
+        // (in registers) while the geometry of batch k is computed
+        constexpr int NLOAD = (EPB * NPE + 31) / 32;  // nodes per lane and batch
+        int nid[NLOAD];
+        double xc[NLOAD][DIM];
+        const long long stride = gridDim.x;
+        auto load_ids = [&](long long blk) {
+            const long long e0 = blk * EPB;
+            EFB_UNROLL
+            for (int q = 0; q < NLOAD; ++q) {
+                const long long i = e0 * NPE + lane + 32 * q;
+                nid[q] = (blk < nblk && lane + 32 * q < EPB * NPE && i < g.Ne * NPE) ? g.connect[i] : -1;
+            }
+        };
+        auto load_coords = [&]() {
+            EFB_UNROLL
+            for (int q = 0; q < NLOAD; ++q) {
+                if (nid[q] >= 0) {
+                    const double* src = g.coord + (long long)nid[q] * g.coord_stride;
+                    EFB_UNROLL
+                    for (int d = 0; d < DIM; ++d) xc[q][d] = src[d];
+                }
+            }
+        };
+        load_ids(blockIdx.x);
+        load_coords();                      // coordinates of batch 0
+        load_ids(blockIdx.x + stride);      // ids of batch 1
         int k = 0;
-        for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x, ++k) {
+        for (long long blk = blockIdx.x; blk < nblk; blk += stride, ++k) {
             const int b = k & 1;
             if (k >= 2) named_sync(kBarEmpty + b, NT);  // consumers have finished reading buffer b (batch k-2)
             double* E0 = bufs + b * buf_stride;
             const long long e0 = blk * EPB;
             const int nvalid = (g.Ne - e0 < EPB) ? (int)(g.Ne - e0) : EPB;
-            elastic_gather<DIM, NPE, CMODE>(g, sm, C, e0, nvalid, E0, lane, 32);
+            if (CMODE != 0) {  // raw C of the batch: 16 bytes per asynchronous copy, no register staging
+                if ((extra & 1) == 0) {
+                    const int per = extra / 2;  // 16-byte pieces per element
+                    for (int idx = lane; idx < nvalid * per; idx += 32) {
+                        const int el = idx / per, i = idx - el * per;
+                        cp_async16(E0 + el * sm.per_elem() + sm.o_extra() + 2 * i, C + (e0 + el) * (long long)extra + 2 * i);
+                    }
+                } else {  // an odd number of doubles per element (2D, ns*ns = 9): pieces are not 16-byte aligned
+                    elastic_gather_C<DIM, NPE>(sm, C, e0, nvalid, E0, lane, 32);
+                }
+            }
+            EFB_UNROLL
+            for (int q = 0; q < NLOAD; ++q) {  // coordinates of batch k: registers -> shared memory
+                const int idx = lane + 32 * q;
+                if (idx < nvalid * NPE) {
+                    const int el = idx / NPE, a = idx - el * NPE;
+                    double* X = E0 + el * sm.per_elem() + sm.o_X();
+                    EFB_UNROLL
+                    for (int d = 0; d < DIM; ++d) X[a * DIM + d] = xc[q][d];
+                }
+            }
+            load_coords();                  // batch k+1 (its ids arrived during the previous iteration)
+            load_ids(blk + 2 * stride);     // batch k+2
             __syncwarp();
             for (int task = lane; task < nvalid * nPg; task += 32)
                 elastic_geometry_task<DIM, NPE>(sm, dNt, wt, scale, E0 + (task / nPg) * sm.per_elem(), task % nPg);
+            if (CMODE != 0) cp_async_wait_all();
             __threadfence_block();
             named_arrive(kBarFull + b, NT);
         }
     } else {
         // ---------------- consumer warps ----------------
-        const int grp = role / WPG, wg = role - grp * WPG;
-        const int ci = wg / CS, ch = wg - ci * CS;  // row component and column chunk of this warp
+        double* my_stage = smem + sm.off_stage() + tid * Tile::LANE_STAGE;
         int k = 0;
         for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x, ++k) {
             const int b = k & 1;
             const double* E0 = bufs + b * buf_stride;
             const long long e0 = blk * EPB;
             const int nvalid = (g.Ne - e0 < EPB) ? (int)(g.Ne - e0) : EPB;
-            if constexpr (Tile::kTensor) {
-                if (lane == 0) bulk_store_wait_read();  // my previous tile has left shared memory
-                __syncwarp();
-                named_sync(kBarFull + b, NT);  // geometry of batch k is in buffer b
-                elastic_contract<DIM, NPE, CMODE, true>(sm, C2, nPg, nvalid, E0, stage, tid);
-                named_arrive(kBarEmpty + b, NT);  // buffer b may be refilled
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my generic-proxy stores -> async proxy
-                __syncwarp();
-                if (lane == 0 && grp * EPW < nvalid)  // elements past Ne are clipped by the tensor map bounds
-                    tma_store_tile_4d(&out_map, stage + role * Tile::WARP_TILE, ch * NB * DIM, ci, 0, (int)(e0 + grp * EPW));
-            } else {
-                double* gdst = out + e0 * (long long)KE;
-                named_sync(kBarFull + b, NT);
-                elastic_contract<DIM, NPE, CMODE, false>(sm, C2, nPg, nvalid, E0, stage, tid);
-                named_arrive(kBarEmpty + b, NT);
-                named_sync(kBarConsumers, NCT);
-                for (int idx = tid; idx < nvalid * KE; idx += NCT) gdst[idx] = stage[idx];
-                named_sync(kBarConsumers, NCT);
+            int el, a, b0;
+            const bool mine = elastic_owner<DIM, NPE>(tid, nvalid, el, a, b0);
+            named_sync(kBarFull + b, NT);  // geometry of batch k is in buffer b
+            double acc[DIM][ROW];
+            if (mine) {
+                const double* E = E0 + el * sm.per_elem();
+                elastic_rows<DIM, NPE, CMODE>(C2, E + sm.o_extra(), E + sm.o_wJ(), E + sm.o_gN(), nPg, a, b0, acc);
+            }
+            named_arrive(kBarEmpty + b, NT);  // buffer b may be refilled
+            if (mine) {
+                double* dst = out + (e0 + el) * (long long)KE + (long long)(a * DIM) * NDOF + b0 * DIM;
+                if constexpr (Tile::kBulk) {
+                    bulk_wait_read();  // my previous rows have left my staging tile
+                    EFB_UNROLL
+                    for (int i = 0; i < DIM; ++i)
+                        EFB_UNROLL
+                        for (int j = 0; j < ROW; j += 2) {
+                            Pair v;
+                            v.x = acc[i][j];
+                            v.y = acc[i][j + 1];
+                            *reinterpret_cast<Pair*>(my_stage + i * ROW + j) = v;
+                        }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my generic-proxy stores -> async proxy
+                    if constexpr (CS == 1) {
+                        bulk_store(dst, my_stage, DIM * ROW * sizeof(double));  // DIM full rows are contiguous in K_e
+                    } else {
+                        EFB_UNROLL
+                        for (int i = 0; i < DIM; ++i) bulk_store(dst + i * NDOF, my_stage + i * ROW, ROW * sizeof(double));
+                    }
+                    bulk_commit();
+                } else {
+                    EFB_UNROLL
+                    for (int i = 0; i < DIM; ++i)
+                        EFB_UNROLL
+                        for (int j = 0; j < ROW; ++j) dst[i * NDOF + j] = acc[i][j];
+                }
             }
         }
-        if (Tile::kTensor && lane == 0) bulk_store_wait_read();  // shared memory outlives the last copy
+        if (Tile::kBulk) bulk_wait_read();  // shared memory outlives the last copy
     }
-}
-
-// 4-D tensor map of the output viewed as K_e[e][a][i][col] (innermost first: col, i, a, e) with the store box of one warp
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
-template <int DIM, int NPE>
-static int make_out_map(CUtensorMap* map, double* out, long long Ne) {
-    using Tile = ElasticTile<DIM, NPE>;
-    memset(map, 0, sizeof(*map));
-    if (!Tile::kTensor) return 0;
-    EncodeTiledFn fn = encode_tiled_fn();
-    if (!fn) {
-        set_error("cuTensorMapEncodeTiled is not available from this driver");
-        return 1;
-    }
-    constexpr cuuint64_t NDOF = DIM * NPE;
-    const cuuint64_t gdim[4] = {NDOF, (cuuint64_t)DIM, (cuuint64_t)NPE, (cuuint64_t)Ne};
-    const cuuint64_t gstride[3] = {NDOF * 8, DIM * NDOF * 8, NDOF * NDOF * 8};  // bytes, dims 1..3
-    const cuuint32_t box[4] = {(cuuint32_t)(Tile::NB * DIM), 1, (cuuint32_t)NPE, (cuuint32_t)Tile::EPW};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, out, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
-        return 1;
-    }
-    return 0;
 }
 
 // CTAs that keep every SM full: resident CTAs per SM (occupancy query) x number of SMs
@@ -247,10 +277,8 @@ static int launch_elastic_mode(const efb_group* g, const CMat& C2, const double*
     const long long nblk = (g->Ne + Tile::EPB - 1) / Tile::EPB;
     if (nblk == 0) return 0;
     constexpr int NT = elastic_threads<DIM, NPE>();
-    CUtensorMap map;
-    if (make_out_map<DIM, NPE>(&map, out, g->Ne)) return 1;
     const long long grid = persistent_grid(k_elastic<DIM, NPE, CMODE>, NT, bytes, nblk);
-    k_elastic<DIM, NPE, CMODE><<<(unsigned)grid, NT, bytes, st>>>(view_of(g), C2, C, scale, out, nblk, map);
+    k_elastic<DIM, NPE, CMODE><<<(unsigned)grid, NT, bytes, st>>>(view_of(g), C2, C, scale, out, nblk);
     return check_launch("efb_elastic_Ke");
 }
 

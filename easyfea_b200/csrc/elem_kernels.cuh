@@ -237,19 +237,18 @@ EFB_D void geometry_block(const GroupView& g, const GeomOut& o, int EPB, long lo
 // O1: K_e = scale * sum_p wJ B^T C B                                   Operators/Bilinear.py:62-79
 //
 // With S = diag(1,..,1, 1/sqrt2,..) the Kelvin-Mandel operator is B = S G, G holding the plain gradients (DIM non-zeros
-// per column), so K_e = sum_p w G^T (S C S) G: the kernel receives C2 = S C S.
+// per column), so K_e = sum_p w G^T (S C S) G: a homogeneous C reaches the kernel as C2 = S C S in the constant bank;
+// per-element / per-Gauss-point C is staged raw in shared memory and the S factors are applied to the (few) row vectors.
 //
-// Work decomposition ("component per warp, row per thread"): a group of DIM*CS warps handles EPW = 32/NPE elements.
-// Warp (i, h) of the group owns, for every element of the group, the rows (a, i) of K_e — one row per lane (el, a) —
-// restricted to the NB = NPE/CS column nodes of chunk h: NB*DIM accumulators per thread (24 for HEXA8, <= 30 always).
-// The row component i is warp-uniform, so the structure of B (which strain rows a displacement component feeds) is
-// resolved at compile time per warp and a homogeneous C2 is read as constant-bank operands.  Per Gauss point a thread
-// forms bc[:] = w G[:, (a,i)]^T C2 (DIM*NS FMAs) and then spends exactly DIM FMAs per accumulator; the only
-// shared-memory traffic of the inner loop is the broadcast read of the column-node gradients.
-// Geometry (G2-G6) is one task per (element, Gauss point): F, det, F^-1 stay in registers, only w|det F| and the
-// physical gradients go to shared memory.  Finished rows are staged in shared memory in the exact K_e layout and leave
-// the SM as ONE bulk asynchronous copy (TMA, cp.async.bulk) per batch, so the FP64 warps never wait on store queues.
-// Per-element / per-Gauss-point C is staged in shared memory, scaled to C2 on the way.
+// Work decomposition: thread (el, a, h) owns the DIM rows of node a of element el, restricted to the NB = NPE/CS column
+// nodes of chunk h: DIM*NB*DIM accumulators in registers (72 for HEXA8, <= 81 always).  Per Gauss point the thread forms
+// bc[i][:] = w G[:, (a,i)]^T C2 once (3 DIM NS flops) and then spends exactly DIM FMAs per accumulator; the only
+// shared-memory traffic of the inner loop is one broadcast read of the NB column-node gradients, i.e. ~10 FP64 FMAs per
+// shared-memory wavefront, which keeps the kernel on the FP64 pipe instead of the shared-memory pipe (measured: with one
+// row per thread the same contraction is bound by shared-memory wavefronts, profiles/r1_ke_variants.md).
+// A warp holds EPW = 32/NPE elements of one chunk; a CTA has NCW consumer warps + one producer warp (elem_kernels.cu).
+// Geometry (G2-G6) is one producer task per (element, Gauss point): F, det, F^-1 stay in registers, only w|det F| and
+// the physical gradients go to shared memory.
 // ---------------------------------------------------------------------------------------------------------
 struct CMat {
     double v[36];
@@ -276,136 +275,150 @@ inline void prescale_C(CMat& C) {
 template <int DIM, int NPE>
 struct ElasticTile {
     static constexpr int NDOF = DIM * NPE;
-    static constexpr int CS = (NDOF <= 32) ? 1 : ((NPE == 15 || NPE == 27) ? 3 : 2);  // column chunks
-    static constexpr int NB = NPE / CS;                                              // column nodes per thread
-    static constexpr int EPW = 32 / NPE;                                             // elements per warp
-    static constexpr int WPG = DIM * CS;                                             // warps per group
-    static constexpr int G = (WPG <= 2) ? 2 : 1;                                     // groups per CTA
-    static constexpr int EPB = G * EPW;                                              // elements per CTA batch
-    static constexpr int THREADS = G * WPG * 32;
-    static constexpr bool kBulk = (NDOF * NDOF) % 2 == 0;  // bulk copies move multiples of 16 bytes
-    // TMA tensor store of a warp's rows: box (NB*DIM cols, 1 component, NPE nodes, EPW elements) of the 4-D view
-    // K_e[e][a][i][col]; needs 16-byte multiples for the box row and the global strides
-    static constexpr bool kTensor = (NB * DIM) % 2 == 0 && NDOF % 2 == 0;
-    static constexpr int WARP_TILE = (EPW * NPE * NB * DIM + 15) & ~15;  // doubles staged per consumer warp (128-byte multiple)
-    static constexpr int STAGE = (G * WPG * WARP_TILE > EPB * NDOF * NDOF) ? G * WPG * WARP_TILE : EPB * NDOF * NDOF;
+    // column chunks: a thread keeps DIM rows x NB column nodes, DIM*NB*DIM <= 81 accumulators
+    static constexpr int CS = (DIM * NPE * DIM <= 81) ? 1 : ((NPE % 4 == 0 && DIM * (NPE / 2) * DIM > 81) ? 4 : (NPE % 3 == 0 ? 3 : 2));
+    static constexpr int NB = NPE / CS;               // column nodes per thread
+    static constexpr int NACC = DIM * NB * DIM;       // accumulators per thread
+    static constexpr int EPW = 32 / NPE;              // elements per warp
+    static constexpr int G = (CS == 1) ? 3 : 1;       // element groups per CTA
+    static constexpr int NCW = G * CS;                // consumer warps
+    static constexpr int EPB = G * EPW;               // elements per CTA batch
+    static constexpr int THREADS = NCW * 32;          // consumer threads
+    // a lane's rows leave through bulk asynchronous copies when every piece is a 16-byte multiple at a 16-byte address
+    static constexpr bool kBulk = (NB * DIM) % 2 == 0 && NDOF % 2 == 0;
+    // per-lane staging tile: NACC doubles padded to an ODD number of 16-byte units -> conflict-free 128-bit stores
+    static constexpr int LANE_STAGE = 2 * ((((NACC + 1) / 2) | 1));
     static_assert(NB * CS == NPE, "CS must divide NPE");
+    static_assert(NACC <= 81, "too many accumulators per thread");
     static_assert(EPW >= 1, "an element needs at most one warp of lanes");
 };
 
 // shared-memory map of the stiffness kernel (offsets in doubles)
 template <int DIM, int NPE>
 struct ElasticSmem {
-    static constexpr int GS = (DIM == 3) ? 4 : 2;     // doubles per node in gN (3D padded to 4: two 16-byte loads)
+    static constexpr int GS = DIM;                    // doubles per node in gN (packed)
     static constexpr int TS = (DIM * NPE) | 1;        // odd stride of one Gauss point in the dN table: the geometry tasks of
                                                       // a warp read different Gauss points without bank conflicts
-    static constexpr int GPS = NPE * GS + 2;          // stride of one Gauss point in gN (same reason, keeps 16-byte alignment)
-    static constexpr int KE = DIM * NPE * DIM * NPE;  // one staged element matrix
+    static constexpr int GPS = (NPE * GS) | 1;        // odd stride of one Gauss point in gN (same reason)
+    static constexpr int KE = DIM * NPE * DIM * NPE;  // one element matrix
     int nPg, EPB, extra;
     EFB_HD ElasticSmem(int nPg_, int EPB_, int extra_) : nPg(nPg_), EPB(EPB_), extra(extra_) {}
-    EFB_HD int off_stage() const { return 0; }  // first: 16-byte aligned for the bulk copy
-    EFB_HD int off_dN() const { return (ElasticTile<DIM, NPE>::STAGE + 1) & ~1; }
+    EFB_HD int off_stage() const { return 0; }  // first: 16-byte aligned for the bulk copies
+    EFB_HD int stage_doubles() const { return ElasticTile<DIM, NPE>::NCW * 32 * ElasticTile<DIM, NPE>::LANE_STAGE; }
+    EFB_HD int off_dN() const { return (stage_doubles() + 1) & ~1; }
     EFB_HD int off_w() const { return off_dN() + nPg * TS; }
     EFB_HD int tables_padded() const { return (off_w() + nPg + 1) & ~1; }
     EFB_HD int o_X() const { return 0; }
     EFB_HD int o_wJ() const { return NPE * DIM; }
-    EFB_HD int o_gN() const { return (o_wJ() + nPg + 1) & ~1; }
-    EFB_HD int o_extra() const { return o_gN() + nPg * GPS; }
-    // stride = 2 (mod 4) doubles: the same field of the elements sharing a warp starts in distinct 16-byte bank groups
+    EFB_HD int o_gN() const { return o_wJ() + nPg; }
+    EFB_HD int o_extra() const { return (o_gN() + nPg * GPS + 1) & ~1; }  // 16-byte aligned (filled by cp.async)
+    // even stride (alignment of `extra`), not a multiple of 16 doubles: the same field of the elements sharing a warp
+    // starts in different banks
     EFB_HD int per_elem() const {
         int n = (o_extra() + extra + 1) & ~1;
-        return (n % 4 == 2) ? n : n + 2;
+        return (n % 16 == 0) ? n + 2 : n;
     }
     EFB_HD int total() const { return tables_padded() + EPB * per_elem(); }
     EFB_HD int total2() const { return tables_padded() + 2 * EPB * per_elem(); }  // two geometry buffers (pipelined kernel)
     EFB_HD double* elem(double* smem, int el) const { return smem + tables_padded() + el * per_elem(); }
 };
 
-// rows (a, I) x columns of nodes [b0, b0+NB): acc[b*DIM + j], all Gauss points
-template <int DIM, int NPE, int CMODE, int I>
-EFB_D void elastic_row(const CMat& C2const, const double* EFB_RESTRICT Cs, const double* EFB_RESTRICT wJ,
-                       const double* EFB_RESTRICT gN, int nPg, int a, int b0, double* EFB_RESTRICT acc) {
+// DIM rows of node a x columns of nodes [b0, b0+NB): acc[i][b*DIM + j], all Gauss points.  `Cs` = raw C of the element
+// (CMODE 1) or of its Gauss points (CMODE 2) in shared memory.
+template <int DIM, int NPE, int CMODE>
+EFB_D void elastic_rows(const CMat& C2const, const double* EFB_RESTRICT Cs, const double* EFB_RESTRICT wJ,
+                        const double* EFB_RESTRICT gN, int nPg, int a, int b0,
+                        double (&acc)[DIM][ElasticTile<DIM, NPE>::NB * DIM]) {
     constexpr int NS = StrainSize<DIM>::value, NC = NS * NS;
     using SM = ElasticSmem<DIM, NPE>;
     constexpr int GS = SM::GS, GPS = SM::GPS, NB = ElasticTile<DIM, NPE>::NB;
     EFB_UNROLL
-    for (int j = 0; j < NB * DIM; ++j) acc[j] = 0.0;
+    for (int i = 0; i < DIM; ++i)
+        EFB_UNROLL
+        for (int j = 0; j < NB * DIM; ++j) acc[i][j] = 0.0;
     for (int p = 0; p < nPg; ++p) {
         const double* gp = gN + p * GPS;
         const double w = wJ[p];
-        // C2(s, r) of this Gauss point: constant bank (mode 0) or shared memory
+        // C2(s, r) of this Gauss point: constant bank (mode 0), or raw C from shared memory with the Kelvin-Mandel factor
+        // of row s folded into the weights (fs) and that of column r applied to bc afterwards (fr)
 #define EFB_C(s_, r_) (CMODE == 0 ? C2const.v[(s_) * NS + (r_)] : Cs[(CMODE == 2 ? p * NC : 0) + (s_) * NS + (r_)])
-        double bc[NS];
+        constexpr double fs = (CMODE == 0) ? 1.0 : kInvSqrt2;
+        double bc[DIM][NS];
         if constexpr (DIM == 2) {
             // G[:, (a,0)] = (gx, 0, gy); G[:, (a,1)] = (0, gy, gx)
-            const Pair ga = *reinterpret_cast<const Pair*>(gp + a * GS);
-            const double wx = w * ga.x, wy = w * ga.y;
+            const double wx = w * gp[a * GS], wy = w * gp[a * GS + 1];
+            const double sx = fs * wx, sy = fs * wy;
             EFB_UNROLL
-            for (int r = 0; r < NS; ++r) bc[r] = (I == 0) ? wx * EFB_C(0, r) + wy * EFB_C(2, r) : wy * EFB_C(1, r) + wx * EFB_C(2, r);
+            for (int r = 0; r < NS; ++r) {
+                bc[0][r] = wx * EFB_C(0, r) + sy * EFB_C(2, r);
+                bc[1][r] = wy * EFB_C(1, r) + sx * EFB_C(2, r);
+            }
+            if (CMODE != 0) {
+                bc[0][2] *= kInvSqrt2;
+                bc[1][2] *= kInvSqrt2;
+            }
             EFB_UNROLL
             for (int b = 0; b < NB; ++b) {
-                const Pair gb = *reinterpret_cast<const Pair*>(gp + (b0 + b) * GS);
-                double s0 = acc[b * 2 + 0], s1 = acc[b * 2 + 1];
-                s0 += bc[0] * gb.x;
-                s0 += bc[2] * gb.y;
-                s1 += bc[1] * gb.y;
-                s1 += bc[2] * gb.x;
-                acc[b * 2 + 0] = s0;
-                acc[b * 2 + 1] = s1;
+                const double gx = gp[(b0 + b) * GS], gy = gp[(b0 + b) * GS + 1];
+                EFB_UNROLL
+                for (int i = 0; i < 2; ++i) {
+                    double s0 = acc[i][b * 2 + 0], s1 = acc[i][b * 2 + 1];
+                    s0 += bc[i][0] * gx;
+                    s0 += bc[i][2] * gy;
+                    s1 += bc[i][1] * gy;
+                    s1 += bc[i][2] * gx;
+                    acc[i][b * 2 + 0] = s0;
+                    acc[i][b * 2 + 1] = s1;
+                }
             }
         } else {
             // G[:, (a,0)] = (gx,0,0,0,gz,gy); G[:, (a,1)] = (0,gy,0,gz,0,gx); G[:, (a,2)] = (0,0,gz,gy,gx,0)
-            const Pair gaxy = *reinterpret_cast<const Pair*>(gp + a * GS);
-            const double wx = w * gaxy.x, wy = w * gaxy.y, wz = w * gp[a * GS + 2];
+            const double wx = w * gp[a * GS], wy = w * gp[a * GS + 1], wz = w * gp[a * GS + 2];
+            const double sx = fs * wx, sy = fs * wy, sz = fs * wz;
             EFB_UNROLL
             for (int r = 0; r < NS; ++r) {
-                if constexpr (I == 0) bc[r] = wx * EFB_C(0, r) + wz * EFB_C(4, r) + wy * EFB_C(5, r);
-                if constexpr (I == 1) bc[r] = wy * EFB_C(1, r) + wz * EFB_C(3, r) + wx * EFB_C(5, r);
-                if constexpr (I == 2) bc[r] = wz * EFB_C(2, r) + wy * EFB_C(3, r) + wx * EFB_C(4, r);
+                bc[0][r] = wx * EFB_C(0, r) + sz * EFB_C(4, r) + sy * EFB_C(5, r);
+                bc[1][r] = wy * EFB_C(1, r) + sz * EFB_C(3, r) + sx * EFB_C(5, r);
+                bc[2][r] = wz * EFB_C(2, r) + sy * EFB_C(3, r) + sx * EFB_C(4, r);
+            }
+            if (CMODE != 0) {
+                EFB_UNROLL
+                for (int i = 0; i < 3; ++i)
+                    EFB_UNROLL
+                    for (int r = 3; r < 6; ++r) bc[i][r] *= kInvSqrt2;
             }
             EFB_UNROLL
             for (int b = 0; b < NB; ++b) {
-                const Pair gxy = *reinterpret_cast<const Pair*>(gp + (b0 + b) * GS);
-                const double gx = gxy.x, gy = gxy.y, gz = gp[(b0 + b) * GS + 2];
-                double s0 = acc[b * 3 + 0], s1 = acc[b * 3 + 1], s2 = acc[b * 3 + 2];
-                s0 += bc[0] * gx;
-                s0 += bc[4] * gz;
-                s0 += bc[5] * gy;
-                s1 += bc[1] * gy;
-                s1 += bc[3] * gz;
-                s1 += bc[5] * gx;
-                s2 += bc[2] * gz;
-                s2 += bc[3] * gy;
-                s2 += bc[4] * gx;
-                acc[b * 3 + 0] = s0;
-                acc[b * 3 + 1] = s1;
-                acc[b * 3 + 2] = s2;
+                const double gx = gp[(b0 + b) * GS], gy = gp[(b0 + b) * GS + 1], gz = gp[(b0 + b) * GS + 2];
+                EFB_UNROLL
+                for (int i = 0; i < 3; ++i) {
+                    double s0 = acc[i][b * 3 + 0], s1 = acc[i][b * 3 + 1], s2 = acc[i][b * 3 + 2];
+                    s0 += bc[i][0] * gx;
+                    s0 += bc[i][4] * gz;
+                    s0 += bc[i][5] * gy;
+                    s1 += bc[i][1] * gy;
+                    s1 += bc[i][3] * gz;
+                    s1 += bc[i][5] * gx;
+                    s2 += bc[i][2] * gz;
+                    s2 += bc[i][3] * gy;
+                    s2 += bc[i][4] * gx;
+                    acc[i][b * 3 + 0] = s0;
+                    acc[i][b * 3 + 1] = s1;
+                    acc[i][b * 3 + 2] = s2;
+                }
             }
         }
 #undef EFB_C
     }
 }
 
-#ifdef __CUDACC__
-// shared -> global bulk asynchronous copy (TMA engine); `bytes` multiple of 16, both addresses 16-byte aligned
-__device__ __forceinline__ void bulk_store_issue(double* gdst, const double* ssrc, unsigned bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
-                 "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-#endif
-
-// ---- the three stages of one batch of EPB elements, shared by the phase-structured body (host emulation) and the
+// ---- the stages of one batch of EPB elements, shared by the phase-structured body (host emulation) and the
 // ---- warp-specialised device kernel.  `E0` = first per-element record of the geometry buffer in use.
 
-// gather: nodal coordinates (and C, scaled to C2) of the batch -> shared memory; executed by `nth` cooperating threads
-template <int DIM, int NPE, int CMODE>
-EFB_D void elastic_gather(const GroupView& g, const ElasticSmem<DIM, NPE>& sm, const double* EFB_RESTRICT C, long long e0,
-                          int nvalid, double* E0, int t, int nth) {
-    constexpr int NS = StrainSize<DIM>::value, NC = NS * NS;
-    const int nPg = g.nPg, extra = sm.extra, pe = sm.per_elem();
+// gather: nodal coordinates of the batch -> shared memory; executed by `nth` cooperating threads
+template <int DIM, int NPE>
+EFB_D void elastic_gather(const GroupView& g, const ElasticSmem<DIM, NPE>& sm, long long e0, int nvalid, double* E0, int t, int nth) {
+    const int pe = sm.per_elem();
     for (int idx = t; idx < nvalid * NPE; idx += nth) {
         const int el = idx / NPE, a = idx - el * NPE;
         const double* src = g.coord + (long long)g.connect[(e0 + el) * NPE + a] * g.coord_stride;
@@ -413,12 +426,16 @@ EFB_D void elastic_gather(const GroupView& g, const ElasticSmem<DIM, NPE>& sm, c
         EFB_UNROLL
         for (int d = 0; d < DIM; ++d) X[a * DIM + d] = src[d];
     }
-    if (CMODE != 0) {
-        for (int idx = t; idx < nvalid * extra; idx += nth) {
-            const int el = idx / extra, i = idx - el * extra;
-            const double* src = CMODE == 1 ? C + (e0 + el) * NC : C + (e0 + el) * (long long)(nPg * NC);
-            (E0 + el * pe + sm.o_extra())[i] = src[i] * kelvin_factor<DIM>((i % NC) / NS, i % NS);
-        }
+}
+
+// raw copy of the batch's C (per element: `extra` contiguous doubles) -> shared memory (host emulation / fallback)
+template <int DIM, int NPE>
+EFB_D void elastic_gather_C(const ElasticSmem<DIM, NPE>& sm, const double* EFB_RESTRICT C, long long e0, int nvalid, double* E0,
+                            int t, int nth) {
+    const int extra = sm.extra, pe = sm.per_elem();
+    for (int idx = t; idx < nvalid * extra; idx += nth) {
+        const int el = idx / extra, i = idx - el * extra;
+        (E0 + el * pe + sm.o_extra())[i] = C[(e0 + el) * (long long)extra + i];
     }
 }
 
@@ -455,60 +472,27 @@ EFB_D void elastic_geometry_task(const ElasticSmem<DIM, NPE>& sm, const double* 
     }
 }
 
-// contraction of consumer thread `tid` (warp (i, h), lane (el, a)): one row of K_e into the staging buffer
-// WARP_STAGE: the warp's rows go to its own dense tile [elw][a][NB*DIM] (source box of the TMA tensor store) instead of the
-// K_e layout
-template <int DIM, int NPE, int CMODE, bool WARP_STAGE = false>
-EFB_D void elastic_contract(const ElasticSmem<DIM, NPE>& sm, const CMat& C2const, int nPg, int nvalid, const double* E0,
-                            double* stage, int tid) {
-    using SM = ElasticSmem<DIM, NPE>;
+// which (element of the batch, node, column chunk) consumer thread `tid` owns; false if it owns nothing
+template <int DIM, int NPE>
+EFB_D bool elastic_owner(int tid, int nvalid, int& el, int& a, int& b0) {
     using Tile = ElasticTile<DIM, NPE>;
-    constexpr int NDOF = DIM * NPE, KE = SM::KE;
-    constexpr int NB = Tile::NB, CS = Tile::CS, EPW = Tile::EPW, WPG = Tile::WPG;
     const int warp = tid >> 5, lane = tid & 31;
-    const int grp = warp / WPG, wg = warp - grp * WPG;
-    const int i = wg / CS, h = wg - i * CS;
-    const int elw = lane / NPE, a = lane - elw * NPE;
-    const int el = grp * EPW + elw;
-    if (elw < EPW && el < nvalid) {
-        const double* E = E0 + el * sm.per_elem();
-        const double* wJ = E + sm.o_wJ();
-        const double* gN = E + sm.o_gN();
-        const double* Cs = E + sm.o_extra();
-        const int b0 = h * NB;
-        double acc[NB * DIM];
-        if (i == 0) elastic_row<DIM, NPE, CMODE, 0>(C2const, Cs, wJ, gN, nPg, a, b0, acc);
-        if (i == 1) elastic_row<DIM, NPE, CMODE, 1>(C2const, Cs, wJ, gN, nPg, a, b0, acc);
-        if constexpr (DIM == 3) {
-            if (i == 2) elastic_row<DIM, NPE, CMODE, 2>(C2const, Cs, wJ, gN, nPg, a, b0, acc);
-        }
-        // row (a,i) of K_e, columns of the NB nodes of this chunk: NB*DIM contiguous doubles
-        double* dst = WARP_STAGE ? stage + warp * Tile::WARP_TILE + (elw * NPE + a) * (NB * DIM)
-                                 : stage + el * KE + (a * DIM + i) * NDOF + b0 * DIM;
-        constexpr bool kVec = (NDOF % 2 == 0) && ((NB * DIM) % 2 == 0);
-        if constexpr (kVec) {
-            EFB_UNROLL
-            for (int j = 0; j < NB * DIM; j += 2) {
-                Pair v;
-                v.x = acc[j];
-                v.y = acc[j + 1];
-                *reinterpret_cast<Pair*>(dst + j) = v;
-            }
-        } else {
-            EFB_UNROLL
-            for (int j = 0; j < NB * DIM; ++j) dst[j] = acc[j];
-        }
-    }
+    const int grp = warp / Tile::CS, h = warp - grp * Tile::CS;
+    const int elw = lane / NPE;
+    a = lane - elw * NPE;
+    el = grp * Tile::EPW + elw;
+    b0 = h * Tile::NB;
+    return elw < Tile::EPW && el < nvalid;
 }
 
 // phase-structured body: every stage ends with a CTA barrier (this is what tests/hostcheck emulates)
 template <int DIM, int NPE, int CMODE>
 EFB_D void elastic_block(const GroupView& g, const CMat& C2const, const double* EFB_RESTRICT C, double scale,
                          double* EFB_RESTRICT out, long long blockId, int nthreads, double* smem, bool load_tables = true) {
-    constexpr int NS = StrainSize<DIM>::value, NC = NS * NS;
+    constexpr int NS = StrainSize<DIM>::value, NC = NS * NS, NDOF = DIM * NPE;
     using SM = ElasticSmem<DIM, NPE>;
     using Tile = ElasticTile<DIM, NPE>;
-    constexpr int TS = SM::TS, KE = SM::KE, EPB = Tile::EPB;
+    constexpr int TS = SM::TS, KE = SM::KE, EPB = Tile::EPB, NB = Tile::NB;
     const int nPg = g.nPg;
     const int extra = CMODE == 2 ? nPg * NC : (CMODE == 1 ? NC : 0);
     const SM sm(nPg, EPB, extra);
@@ -516,7 +500,6 @@ EFB_D void elastic_block(const GroupView& g, const CMat& C2const, const double* 
     const int nvalid = (g.Ne - e0 < EPB) ? (int)(g.Ne - e0) : EPB;
     double* dNt = smem + sm.off_dN();
     double* wt = smem + sm.off_w();
-    double* stage = smem + sm.off_stage();
     double* E0 = sm.elem(smem, 0);
 
     if (load_tables) {
@@ -525,15 +508,26 @@ EFB_D void elastic_block(const GroupView& g, const CMat& C2const, const double* 
             for (int i = tid; i < nPg; i += nthreads) wt[i] = g.w_pg[i];
         }
     }
-    EFB_PHASE(tid, nthreads) { elastic_gather<DIM, NPE, CMODE>(g, sm, C, e0, nvalid, E0, tid, nthreads); }
+    EFB_PHASE(tid, nthreads) {
+        elastic_gather<DIM, NPE>(g, sm, e0, nvalid, E0, tid, nthreads);
+        if (CMODE != 0) elastic_gather_C<DIM, NPE>(sm, C, e0, nvalid, E0, tid, nthreads);
+    }
     EFB_PHASE(tid, nthreads) {
         for (int task = tid; task < nvalid * nPg; task += nthreads)
             elastic_geometry_task<DIM, NPE>(sm, dNt, wt, scale, E0 + (task / nPg) * sm.per_elem(), task % nPg);
     }
-    EFB_PHASE(tid, nthreads) { elastic_contract<DIM, NPE, CMODE>(sm, C2const, nPg, nvalid, E0, stage, tid); }
-    EFB_PHASE(tid, nthreads) {  // the batch's element matrices are contiguous in `out`
-        double* gdst = out + e0 * (long long)KE;
-        for (int idx = tid; idx < nvalid * KE; idx += nthreads) gdst[idx] = stage[idx];
+    EFB_PHASE(tid, nthreads) {
+        int el, a, b0;
+        if (elastic_owner<DIM, NPE>(tid, nvalid, el, a, b0)) {
+            const double* E = E0 + el * sm.per_elem();
+            double acc[DIM][NB * DIM];
+            elastic_rows<DIM, NPE, CMODE>(C2const, E + sm.o_extra(), E + sm.o_wJ(), E + sm.o_gN(), nPg, a, b0, acc);
+            double* dst = out + (e0 + el) * (long long)KE + (long long)(a * DIM) * NDOF + b0 * DIM;
+            EFB_UNROLL
+            for (int i = 0; i < DIM; ++i)
+                EFB_UNROLL
+                for (int j = 0; j < NB * DIM; ++j) dst[i * NDOF + j] = acc[i][j];
+        }
     }
 }
 
