@@ -31,6 +31,18 @@ METRIC = "element Gauss-point evaluations/s (HEXA8 elastic K_e + CSR replay asse
 E_MOD, NU = 210000.0, 0.3
 
 
+def ncu_traffic(kernel: str, units: int):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/traffic.json), scaled from
+    the captured launch to `units` (elements / nodes) of the launch timed here; None when no capture is recorded."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            t = json.load(f)[kernel]
+        return (t["read_bytes"] + t["write_bytes"]) / t["units"] * units
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -251,10 +263,10 @@ def run_ours(args):
     ke_tflops = flops_ke / (t_ke * 1e-3) / 1e12
     if t_rp >= t_ke:
         roof = {"kernel": "k_replay_fast<3,8>", "bound": "hbm", "achieved": bytes_replay / (t_rp * 1e-3) / 1e9, "peak": peak,
-                "unit": "GB/s", "traffic": None}
+                "unit": "GB/s", "traffic": ncu_traffic("k_replay_fast<3,8>", part.n_owned)}
     else:
         roof = {"kernel": "k_elastic<3,8,0>", "bound": "hbm", "achieved": bytes_ke / (t_ke * 1e-3) / 1e9, "peak": peak,
-                "unit": "GB/s", "traffic": None,
+                "unit": "GB/s", "traffic": ncu_traffic("k_elastic<3,8,0>", Ne),
                 "note": "this kernel is FP64-FMA-pipe bound (AI 7.8 flop/B): see fp64_frac; tensor cores do not apply",
                 "fp64_tflops": ke_tflops, "fp64_peak_tflops": FP64_PEAK_TFLOPS, "fp64_frac": ke_tflops / FP64_PEAK_TFLOPS}
     roof["frac"] = roof["achieved"] / roof["peak"]
