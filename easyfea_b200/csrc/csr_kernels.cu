@@ -2,6 +2,9 @@
 #include "common.cuh"
 #include "csr_kernels.cuh"
 
+#include <stdlib.h>
+#include <string.h>
+
 namespace efb {
 
 static int make_table(GroupTable& T, int n_groups, const int32_t* const* connect, const double* const* data,
@@ -201,6 +204,414 @@ __global__ void __launch_bounds__(256) k_replay_fast(const double* data, long lo
     replay_node_fast<D, NPE, 4>(data, n, rowptr, qlist, adjptr, pos, smem + (size_t)warp * acc_per_warp, out);
 }
 
+// Pipelined form of the single-group replay: persistent warps walk nodes gw, gw + GW, ...; the row/adjacency pointers of
+// node k+2 and the element-row list of node k+1 are already in flight (in registers) while node k is accumulated, so the
+// only exposed latency per node is that of the K_e rows themselves, of which up to SB (all 8 of an interior HEXA8 node)
+// are requested at once.  The slot positions of a source are loaded once (lanes 0..NPE-1) and handed out by shuffles.
+// Accumulation order per slot is still ascending element-row index: bit-identical to np.bincount.
+template <int D, int NPE, int SB, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+    k_replay_pipe(const double* __restrict__ data, long long Nn, const long long* __restrict__ rowptr,
+                  const long long* __restrict__ qlist, const long long* __restrict__ adjptr, const int* __restrict__ pos,
+                  int acc_per_warp, double* __restrict__ out) {
+    extern __shared__ double smem[];
+    constexpr int NDOF = D * NPE, NV = D * NDOF, VPL = (NV + 31) / 32;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* acc = smem + (size_t)warp * acc_per_warp;
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp, GW = (long long)gridDim.x * (blockDim.x >> 5);
+
+    // lanes 0,1: rowptr[n], rowptr[n+1]; lanes 2,3: adjptr[n], adjptr[n+1]
+    auto load_meta = [&](long long n) -> long long {
+        if (n >= Nn || lane >= 4) return 0;
+        return lane < 2 ? rowptr[n + lane] : adjptr[n + lane - 2];
+    };
+    // static decomposition of this lane's values of a source: i = lane + 32k -> (row ii, column node b, component jj)
+    int v_row[VPL], v_b[VPL], v_jj[VPL];
+    EFB_UNROLL
+    for (int k = 0; k < VPL; ++k) {
+        const int i = lane + 32 * k, ii = i / NDOF, j = i - ii * NDOF;
+        v_row[k] = ii;
+        v_b[k] = (j / D) % NPE;  // % NPE keeps the shuffle source lane in range for the unused tail values
+        v_jj[k] = j % D;
+    }
+
+    long long m_cur = load_meta(gw);
+    long long m_nxt = load_meta(gw + GW);
+    long long s_begin = __shfl_sync(FULL, m_cur, 0), s_end = __shfl_sync(FULL, m_cur, 1);
+    long long a0 = __shfl_sync(FULL, m_cur, 2), a1 = __shfl_sync(FULL, m_cur, 3);
+    long long q_cur = (s_begin + lane < s_end) ? qlist[s_begin + lane] : 0;
+
+    for (long long n = gw; n < Nn; n += GW) {
+        // ---- prefetch: pointers of node k+2, element rows of node k+1
+        const long long m_fut = load_meta(n + 2 * GW);
+        const long long nb = __shfl_sync(FULL, m_nxt, 0), ne = __shfl_sync(FULL, m_nxt, 1);
+        const long long na0 = __shfl_sync(FULL, m_nxt, 2), na1 = __shfl_sync(FULL, m_nxt, 3);
+        const long long q_nxt = (nb + lane < ne) ? qlist[nb + lane] : 0;
+
+        // ---- node k
+        const int deg = (int)(a1 - a0), rowlen = D * deg, blk = D * rowlen;
+        const int cnt = (int)(s_end - s_begin);
+        for (int i = lane; i < blk; i += 32) acc[i] = 0.0;
+        __syncwarp();
+        for (int s0 = 0; s0 < cnt; s0 += SB) {
+            double v[SB][VPL];
+            int prl[SB];
+            EFB_UNROLL
+            for (int u = 0; u < SB; ++u) {
+                if (s0 + u < cnt) {  // warp-uniform
+                    const long long q = (s0 + u < 32) ? __shfl_sync(FULL, q_cur, s0 + u) : qlist[s_begin + s0 + u];
+                    const double* src = data + q * (long long)NV;
+                    EFB_UNROLL
+                    for (int k = 0; k < VPL; ++k)
+                        if (lane + 32 * k < NV) v[u][k] = src[lane + 32 * k];
+                    prl[u] = pos[q * NPE + (lane < NPE ? lane : 0)];
+                }
+            }
+            EFB_UNROLL
+            for (int u = 0; u < SB; ++u) {
+                if (s0 + u < cnt) {
+                    EFB_UNROLL
+                    for (int k = 0; k < VPL; ++k) {
+                        const int pb = __shfl_sync(FULL, prl[u], v_b[k]);
+                        if (lane + 32 * k < NV) acc[v_row[k] * rowlen + pb * D + v_jj[k]] += v[u][k];
+                    }
+                    __syncwarp();  // the next source may hit the same slots from other lanes
+                }
+            }
+        }
+        double* dst = out + (long long)D * D * a0;
+        for (int i = lane; i < blk; i += 32) dst[i] = acc[i];
+        __syncwarp();
+
+        // ---- rotate the pipeline
+        m_nxt = m_fut;
+        s_begin = nb; s_end = ne; a0 = na0; a1 = na1;
+        q_cur = q_nxt;
+    }
+}
+
+template <int D, int NPE, int SB, int MINB>
+static int launch_replay_pipe(const double* data, long long Nn, const long long* rowptr, const long long* qlist,
+                              const long long* adjptr, const int* pos, int max_deg, double* out, cudaStream_t st) {
+    const int warps = 8;
+    const int acc_per_warp = D * D * max_deg;
+    const size_t bytes = sizeof(double) * (size_t)acc_per_warp * warps;
+    auto kern = k_replay_pipe<D, NPE, SB, MINB>;
+    if (ensure_smem(kern, bytes)) return 1;
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, bytes) != cudaSuccess || per_sm < 1) per_sm = 1;
+    long long grid = (long long)sms * per_sm;
+    const long long need = (Nn + warps - 1) / warps;
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, warps * 32, bytes, st>>>(data, Nn, rowptr, qlist, adjptr, pos, acc_per_warp, out);
+    return check_launch("efb_csr_replay_matrix");
+}
+
+// Ring form of the single-group replay (the default): a warp owns kRingNodes consecutive nodes, hence one contiguous
+// range of the element-row list, and streams those K_e rows (+ their slot positions) through a ring of R slots in shared
+// memory with asynchronous copies (cp.async / LDGSTS: no registers held while the data is in flight).  One commit group
+// per source, `wait_group R-1` before a source is consumed and one refill issued after it, so R sources (R * 608 B for
+// HEXA8) are in flight per warp at all times, across node boundaries.  Accumulation order per slot is ascending
+// element-row index: bit-identical to np.bincount.
+#ifndef EFB_RING_NODES
+#define EFB_RING_NODES 64
+#endif
+#ifndef EFB_RING_BYTES
+#define EFB_RING_BYTES 5000
+#endif
+constexpr int kRingNodes = EFB_RING_NODES;
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async_piece(void* sdst, const void* gsrc) {
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc), "n"(BYTES)
+                     : "memory");
+}
+
+template <int D, int NPE>
+struct ReplayRing {
+    static constexpr int NDOF = D * NPE, NV = D * NDOF, VPL = (NV + 31) / 32;
+    static constexpr int PIECE = (NV % 2 == 0) ? 2 : 1;            // doubles per asynchronous copy
+    static constexpr int NP = NV / PIECE, PPL = (NP + 31) / 32;    // pieces per source, per lane
+    static constexpr int SLOT = (NV + (NPE + 1) / 2 + 1) & ~1;     // doubles per ring slot: values | positions (int32)
+    static constexpr int R0 = EFB_RING_BYTES / (SLOT * 8);
+    static constexpr int R = R0 < 3 ? 3 : (R0 > 24 ? 24 : R0);     // slots per warp (~5 KB: 8 HEXA8 rows; a deeper ring costs occupancy and is slower, profiles/README.md)
+};
+
+template <int D, int NPE>
+__global__ void __launch_bounds__(256)
+    k_replay_ring(const double* __restrict__ data, long long Nn, const long long* __restrict__ rowptr,
+                  const long long* __restrict__ qlist, const long long* __restrict__ adjptr, const int* __restrict__ pos,
+                  int acc_per_warp, double* __restrict__ out) {
+    extern __shared__ __align__(16) double smem[];
+    using RR = ReplayRing<D, NPE>;
+    constexpr int NDOF = RR::NDOF, NV = RR::NV, VPL = RR::VPL, PIECE = RR::PIECE, NP = RR::NP, PPL = RR::PPL, SLOT = RR::SLOT, R = RR::R;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per_warp = R * SLOT + ((acc_per_warp + 1) & ~1);
+    double* ring = smem + (size_t)warp * per_warp;
+    double* acc = ring + R * SLOT;
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    const long long n_lo = gw * kRingNodes;
+    if (n_lo >= Nn) return;
+    const long long n_hi = (n_lo + kRingNodes < Nn) ? n_lo + kRingNodes : Nn;
+    const long long s_lo = rowptr[n_lo], s_hi = rowptr[n_hi];
+
+    // static decomposition of this lane's values of a source: i = lane + 32k -> (row ii, column node b, component jj)
+    int v_row[VPL], v_b[VPL], v_jj[VPL];
+    EFB_UNROLL
+    for (int k = 0; k < VPL; ++k) {
+        const int i = lane + 32 * k, ii = i / NDOF, j = i - ii * NDOF;
+        v_row[k] = ii;
+        v_b[k] = (j / D) % NPE;
+        v_jj[k] = j % D;
+    }
+
+    // ---- producer side: element rows s_lo.. are requested in order; their ids travel in two 32-wide register chunks
+    long long si = s_lo, qbase = s_lo;
+    long long qa = (qbase + lane < s_hi) ? qlist[qbase + lane] : 0;
+    long long qb = (qbase + 32 + lane < s_hi) ? qlist[qbase + 32 + lane] : 0;
+    int islot = 0;
+    auto issue = [&]() {
+        if (si < s_hi) {  // warp-uniform
+            const long long q = __shfl_sync(FULL, qa, (int)(si - qbase));
+            double* slot = ring + islot * SLOT;
+            const double* src = data + q * (long long)NV;
+            EFB_UNROLL
+            for (int k = 0; k < PPL; ++k) {
+                const int piece = lane + 32 * k;
+                if (piece < NP) cp_async_piece<PIECE * 8>(slot + piece * PIECE, src + piece * PIECE);
+            }
+            if (lane < NPE) cp_async_piece<4>(reinterpret_cast<int*>(slot + NV) + lane, pos + q * NPE + lane);
+            ++si;
+            islot = (islot + 1 == R) ? 0 : islot + 1;
+            if (si - qbase == 32) {
+                qbase += 32;
+                qa = qb;
+                qb = (qbase + 32 + lane < s_hi) ? qlist[qbase + 32 + lane] : 0;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    EFB_UNROLL
+    for (int r = 0; r < R; ++r) issue();
+
+    // ---- consumer side: nodes in chunks of 31 (32 pointer entries per chunk, the next chunk's already in flight)
+    long long sc = s_lo;
+    int cslot = 0;
+    auto ptr_chunk = [&](const long long* ptr, long long nb) { return ptr[(nb + lane < n_hi) ? nb + lane : n_hi]; };
+    long long rp_n = ptr_chunk(rowptr, n_lo), ap_n = ptr_chunk(adjptr, n_lo);
+    for (long long nb = n_lo; nb < n_hi; nb += 31) {
+        const long long rp = rp_n, ap = ap_n;
+        if (nb + 31 < n_hi) {
+            rp_n = ptr_chunk(rowptr, nb + 31);
+            ap_n = ptr_chunk(adjptr, nb + 31);
+        }
+        const int nn = (n_hi - nb < 31) ? (int)(n_hi - nb) : 31;
+        for (int jn = 0; jn < nn; ++jn) {
+            const long long s_e = __shfl_sync(FULL, rp, jn + 1);
+            const long long a0 = __shfl_sync(FULL, ap, jn), a1 = __shfl_sync(FULL, ap, jn + 1);
+            const int deg = (int)(a1 - a0), rowlen = D * deg, blk = D * rowlen;
+            for (int i = lane; i < blk; i += 32) acc[i] = 0.0;
+            __syncwarp();
+            for (; sc < s_e; ++sc) {
+                asm volatile("cp.async.wait_group %0;" ::"n"(R - 1) : "memory");
+                __syncwarp();  // every lane's pieces of this source have landed
+                const double* slot = ring + cslot * SLOT;
+                const int* prow = reinterpret_cast<const int*>(slot + NV);
+                EFB_UNROLL
+                for (int k = 0; k < VPL; ++k)
+                    if (lane + 32 * k < NV) acc[v_row[k] * rowlen + prow[v_b[k]] * D + v_jj[k]] += slot[lane + 32 * k];
+                __syncwarp();  // slot consumed by all lanes; the next source may hit the same accumulators
+                cslot = (cslot + 1 == R) ? 0 : cslot + 1;
+                issue();
+            }
+            double* dst = out + (long long)D * D * a0;
+            for (int i = lane; i < blk; i += 32) dst[i] = acc[i];
+            __syncwarp();
+        }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+template <int D, int NPE>
+static int launch_replay_ring(const double* data, long long Nn, const long long* rowptr, const long long* qlist,
+                              const long long* adjptr, const int* pos, int max_deg, double* out, cudaStream_t st) {
+    using RR = ReplayRing<D, NPE>;
+    const int warps = 8;
+    const int acc_per_warp = D * D * max_deg;
+    const size_t bytes = sizeof(double) * (size_t)(RR::R * RR::SLOT + ((acc_per_warp + 1) & ~1)) * warps;
+    if (ensure_smem(k_replay_ring<D, NPE>, bytes)) return 1;
+    const long long nwarps = (Nn + kRingNodes - 1) / kRingNodes;
+    k_replay_ring<D, NPE><<<blocks_for(nwarps, warps), warps * 32, bytes, st>>>(data, Nn, rowptr, qlist, adjptr, pos, acc_per_warp, out);
+    return check_launch("efb_csr_replay_matrix");
+}
+
+// TMA form of the ring replay (element rows whose values and slot positions are both 16-byte multiples: HEXA8, TETRA4,
+// QUAD4/8, HEXA20): the ring is refilled by bulk asynchronous copies (cp.async.bulk, one for the K_e row and one for its
+// slot positions) issued by a single lane and completed on a per-slot mbarrier, so keeping R element rows in flight per
+// warp costs a handful of instructions per row instead of one cp.async per 16 bytes and lane.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int D, int NPE>
+struct ReplayTma {
+    static constexpr int NDOF = D * NPE, NV = D * NDOF, VPL = (NV + 31) / 32;
+    static constexpr bool ok = (NV * 8) % 16 == 0 && (NPE * 4) % 16 == 0;
+    static constexpr int SLOT = NV + NPE / 2;                      // doubles per ring slot: values | positions (int32)
+    static constexpr unsigned TX = NV * 8 + NPE * 4;               // bytes landing per slot
+    static constexpr int R0 = EFB_RING_BYTES / (SLOT * 8);
+    static constexpr int R = R0 < 3 ? 3 : (R0 > 24 ? 24 : R0);     // slots per warp (~5 KB: 8 HEXA8 rows; a deeper ring costs occupancy and is slower, profiles/README.md)
+};
+
+#ifndef EFB_REPLAY_MINB
+#define EFB_REPLAY_MINB 4
+#endif
+template <int D, int NPE>
+__global__ void __launch_bounds__(256, EFB_REPLAY_MINB)
+    k_replay_tma(const double* __restrict__ data, long long Nn, const long long* __restrict__ rowptr,
+                 const long long* __restrict__ qlist, const long long* __restrict__ adjptr, const int* __restrict__ pos,
+                 int acc_per_warp, double* __restrict__ out) {
+    extern __shared__ __align__(16) double smem[];
+    using RT = ReplayTma<D, NPE>;
+    constexpr int NDOF = RT::NDOF, NV = RT::NV, VPL = RT::VPL, SLOT = RT::SLOT, R = RT::R;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per_warp = R * SLOT + ((acc_per_warp + 1) & ~1) + ((R + 1) & ~1);  // ring | accumulators | mbarriers
+    double* ring = smem + (size_t)warp * per_warp;
+    double* acc = ring + R * SLOT;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(acc + ((acc_per_warp + 1) & ~1));
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    const long long n_lo = gw * kRingNodes;
+    if (n_lo >= Nn) return;
+    const long long n_hi = (n_lo + kRingNodes < Nn) ? n_lo + kRingNodes : Nn;
+    const long long s_lo = rowptr[n_lo], s_hi = rowptr[n_hi];
+
+    if (lane < R) mbar_init(bars + lane, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+
+    // this lane's values of a source: i = lane + 32k -> offset of (row ii, component jj) in a node block of row length 1,
+    // and the column node b whose slot position selects the column
+    int v_row[VPL], v_b[VPL], v_jj[VPL];
+    EFB_UNROLL
+    for (int k = 0; k < VPL; ++k) {
+        const int i = lane + 32 * k, ii = i / NDOF, j = i - ii * NDOF;
+        v_row[k] = ii;
+        v_b[k] = (j / D) % NPE;
+        v_jj[k] = j % D;
+    }
+
+    // ---- producer side (lane 0 issues): element rows s_lo.. in order, ids in two 32-wide register chunks
+    long long si = s_lo, qbase = s_lo;
+    long long qa = (qbase + lane < s_hi) ? qlist[qbase + lane] : 0;
+    long long qb = (qbase + 32 + lane < s_hi) ? qlist[qbase + 32 + lane] : 0;
+    int islot = 0;
+    auto issue = [&]() {
+        if (si < s_hi) {  // warp-uniform
+            const long long q = __shfl_sync(FULL, qa, (int)(si - qbase));
+            if (lane == 0) {
+                double* slot = ring + islot * SLOT;
+                mbar_expect_tx(bars + islot, RT::TX);
+                bulk_load(slot, data + q * (long long)NV, NV * 8, bars + islot);
+                bulk_load(slot + NV, pos + q * NPE, NPE * 4, bars + islot);
+            }
+            ++si;
+            islot = (islot + 1 == R) ? 0 : islot + 1;
+            if (si - qbase == 32) {
+                qbase += 32;
+                qa = qb;
+                qb = (qbase + 32 + lane < s_hi) ? qlist[qbase + 32 + lane] : 0;
+            }
+        }
+    };
+    EFB_UNROLL
+    for (int r = 0; r < R; ++r) issue();
+
+    // ---- consumer side
+    long long sc = s_lo;
+    int cslot = 0;
+    unsigned cphase = 0;
+    auto ptr_chunk = [&](const long long* ptr, long long nb) { return ptr[(nb + lane < n_hi) ? nb + lane : n_hi]; };
+    long long rp_n = ptr_chunk(rowptr, n_lo), ap_n = ptr_chunk(adjptr, n_lo);
+    for (long long nb = n_lo; nb < n_hi; nb += 31) {
+        const long long rp = rp_n, ap = ap_n;
+        if (nb + 31 < n_hi) {
+            rp_n = ptr_chunk(rowptr, nb + 31);
+            ap_n = ptr_chunk(adjptr, nb + 31);
+        }
+        const int nn = (n_hi - nb < 31) ? (int)(n_hi - nb) : 31;
+        for (int jn = 0; jn < nn; ++jn) {
+            const long long s_e = __shfl_sync(FULL, rp, jn + 1);
+            const long long a0 = __shfl_sync(FULL, ap, jn), a1 = __shfl_sync(FULL, ap, jn + 1);
+            const int deg = (int)(a1 - a0), rowlen = D * deg, blk = D * rowlen;
+            int base[VPL];  // accumulator offset of (row, component) for this node
+            EFB_UNROLL
+            for (int k = 0; k < VPL; ++k) base[k] = v_row[k] * rowlen + v_jj[k];
+            for (int i = lane; i < blk; i += 32) acc[i] = 0.0;
+            __syncwarp();
+            for (; sc < s_e; ++sc) {
+                mbar_wait(bars + cslot, cphase);  // the row and its positions have landed
+                const double* slot = ring + cslot * SLOT;
+                const int* prow = reinterpret_cast<const int*>(slot + NV);
+                EFB_UNROLL
+                for (int k = 0; k < VPL; ++k)
+                    if (lane + 32 * k < NV) acc[base[k] + prow[v_b[k]] * D] += slot[lane + 32 * k];
+                __syncwarp();  // slot consumed by all lanes; the next source may hit the same accumulators
+                if (++cslot == R) {
+                    cslot = 0;
+                    cphase ^= 1u;
+                }
+                issue();
+            }
+            double* dst = out + (long long)D * D * a0;
+            for (int i = lane; i < blk; i += 32) dst[i] = acc[i];
+            __syncwarp();
+        }
+    }
+}
+
+template <int D, int NPE>
+static int launch_replay_tma(const double* data, long long Nn, const long long* rowptr, const long long* qlist,
+                             const long long* adjptr, const int* pos, int max_deg, double* out, cudaStream_t st) {
+    using RT = ReplayTma<D, NPE>;
+    const int warps = 8;
+    const int acc_per_warp = D * D * max_deg;
+    const size_t bytes = sizeof(double) * (size_t)(RT::R * RT::SLOT + ((acc_per_warp + 1) & ~1) + ((RT::R + 1) & ~1)) * warps;
+    if (ensure_smem(k_replay_tma<D, NPE>, bytes)) return 1;
+    const long long nwarps = (Nn + kRingNodes - 1) / kRingNodes;
+    k_replay_tma<D, NPE><<<blocks_for(nwarps, warps), warps * 32, bytes, st>>>(data, Nn, rowptr, qlist, adjptr, pos, acc_per_warp, out);
+    return check_launch("efb_csr_replay_matrix");
+}
+
 template <int D, int NPE>
 static int launch_replay_fast(const double* data, long long Nn, const long long* rowptr, const long long* qlist,
                               const long long* adjptr, const int* pos, int max_deg, double* out, cudaStream_t st) {
@@ -355,14 +766,44 @@ extern "C" int efb_csr_replay_matrix(int n_groups, const double* const* data_hos
     if (make_table(T, n_groups, nullptr, data_host, Ne_host, nPe_host, dof_n)) return 1;
     if (Nn == 0) return 0;
     if (n_groups == 1) {  // single group with a compiled (dof_n, nPe): hoisted index math, batched loads
+        // EFB_REPLAY_KERNEL = fast | pipe | pipe8 | ring | tma (dev/tuning knob)
+        const char* env = getenv("EFB_REPLAY_KERNEL");
+        // default by the size of an element row (NV = dof_n^2 * nPe doubles), measured on B200 (profiles/README.md):
+        // small rows (TRI3, TETRA4) -> fast, mid-size rows (HEXA8) -> ring, large rows (HEXA20/27) -> pipe
+        const int nv = dof_n * dof_n * nPe_host[0];
+        const int form = env ? (!strcmp(env, "fast") ? 0 : (!strcmp(env, "pipe8") ? 2 : (!strcmp(env, "pipe") ? 1 : (!strcmp(env, "ring") ? 3 : 4))))
+                             : (nv < 48 ? 0 : (nv <= 128 ? 4 : 1));
+        const bool aligned = (reinterpret_cast<uintptr_t>(data_host[0]) & 15) == 0;
+#define EFB_PIPE(D, N, SB, MINB)                                                                                        \
+    return launch_replay_pipe<D, N, SB, MINB>(data_host[0], Nn, (const long long*)rowptr, (const long long*)qlist,     \
+                                              (const long long*)adjptr, pos, max_deg, data_out, as_stream(stream));
 #define EFB_FAST(D, N)                                                                                                 \
-    if (dof_n == D && nPe_host[0] == N)                                                                                \
-        return launch_replay_fast<D, N>(data_host[0], Nn, (const long long*)rowptr, (const long long*)qlist,           \
-                                        (const long long*)adjptr, pos, max_deg, data_out, as_stream(stream));
+    if (dof_n == D && nPe_host[0] == N) {                                                                              \
+        if (form == 0)                                                                                                 \
+            return launch_replay_fast<D, N>(data_host[0], Nn, (const long long*)rowptr, (const long long*)qlist,       \
+                                            (const long long*)adjptr, pos, max_deg, data_out, as_stream(stream));      \
+        if constexpr (ReplayTma<D, N>::ok) {                                                                           \
+            if (form == 4 && aligned && (reinterpret_cast<uintptr_t>(pos) & 15) == 0)                                  \
+                return launch_replay_tma<D, N>(data_host[0], Nn, (const long long*)rowptr, (const long long*)qlist,    \
+                                               (const long long*)adjptr, pos, max_deg, data_out, as_stream(stream));   \
+        }                                                                                                              \
+        if ((form == 3 || form == 4) && aligned)                                                                       \
+            return launch_replay_ring<D, N>(data_host[0], Nn, (const long long*)rowptr, (const long long*)qlist,       \
+                                            (const long long*)adjptr, pos, max_deg, data_out, as_stream(stream));      \
+        if constexpr (D * D * N > 128) {                                                                               \
+            EFB_PIPE(D, N, 2, 3)                                                                                       \
+        } else if constexpr (D * D * N <= 72) {                                                                        \
+            if (form == 2) { EFB_PIPE(D, N, 8, 2) }                                                                    \
+            EFB_PIPE(D, N, 4, 3)                                                                                       \
+        } else {                                                                                                       \
+            EFB_PIPE(D, N, 4, 3)                                                                                       \
+        }                                                                                                              \
+    }
         EFB_FAST(3, 8) EFB_FAST(3, 4) EFB_FAST(3, 10) EFB_FAST(3, 27) EFB_FAST(3, 20) EFB_FAST(3, 6)
         EFB_FAST(2, 3) EFB_FAST(2, 4) EFB_FAST(2, 6) EFB_FAST(2, 8) EFB_FAST(2, 9)
         EFB_FAST(1, 3) EFB_FAST(1, 4) EFB_FAST(1, 6) EFB_FAST(1, 8) EFB_FAST(1, 9) EFB_FAST(1, 10) EFB_FAST(1, 27) EFB_FAST(1, 20)
 #undef EFB_FAST
+#undef EFB_PIPE
     }
     const int warps = 8;
     const int acc_per_warp = dof_n * dof_n * max_deg;

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "elem_kernels.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace efb {
@@ -282,6 +283,170 @@ static int launch_elastic_mode(const efb_group* g, const CMat& C2, const double*
     return check_launch("efb_elastic_Ke");
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Warp-autonomous stiffness kernel for a homogeneous C (bodies and rationale: elem_kernels.cuh, ElasticWarp).
+// NW warps per CTA, no CTA barrier after the table load; warp `gw` walks batches gw, gw + GW, ...
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kWarpKernelWarps = 4;
+
+template <int DIM, int NPE, bool SYM, bool ORTHO>
+__global__ void __launch_bounds__(kWarpKernelWarps * 32, 2)
+    k_elastic_w(GroupView g, CMat C2, double scale, double* __restrict__ out, long long nbatch) {
+    extern __shared__ __align__(128) double smem[];
+    using W = ElasticWarp<DIM, NPE>;
+    using Tile = ElasticTile<DIM, NPE>;
+    constexpr int EPW = W::EPW, NDOF = W::NDOF, KE = W::KE, NW = kWarpKernelWarps;
+    const int nPg = g.nPg, rec = W::rec(nPg);
+    double* dNt = smem;
+    double* wt = smem + nPg * W::TS;
+    for (int i = threadIdx.x; i < nPg * DIM * NPE; i += NW * 32) dNt[(i / (DIM * NPE)) * W::TS + i % (DIM * NPE)] = g.dN_pg[i];
+    for (int i = threadIdx.x; i < nPg; i += NW * 32) wt[i] = g.w_pg[i];
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* stage = smem + W::tables(nPg) + warp * W::per_warp(nPg, SYM);
+    double* X = stage + (SYM ? W::STAGE_SYM : W::STAGE_LANE);
+    double* geo = X + W::XW;
+    const int el = lane / NPE, a = lane - el * NPE;
+    const long long gw = (long long)blockIdx.x * NW + warp, GW = (long long)gridDim.x * NW;
+
+    // gather pipeline: node id of batch k+2 and coordinates of batch k+1 are in flight while batch k is computed
+    int nid;
+    double xc[DIM];
+    auto load_id = [&](long long blk) {
+        const long long i = blk * (EPW * NPE) + lane;
+        nid = (lane < EPW * NPE && blk < nbatch && i < g.Ne * NPE) ? g.connect[i] : -1;
+    };
+    auto load_xc = [&]() {
+        if (nid >= 0) {
+            const double* src = g.coord + (long long)nid * g.coord_stride;
+            EFB_UNROLL
+            for (int d = 0; d < DIM; ++d) xc[d] = src[d];
+        }
+    };
+    load_id(gw);
+    load_xc();
+    load_id(gw + GW);
+
+    for (long long blk = gw; blk < nbatch; blk += GW) {
+        const long long e0 = blk * EPW;
+        const int nvalid = (g.Ne - e0 < EPW) ? (int)(g.Ne - e0) : EPW;
+        if (lane < nvalid * NPE) {
+            EFB_UNROLL
+            for (int d = 0; d < DIM; ++d) X[lane * DIM + d] = xc[d];
+        }
+        load_xc();               // batch k+1 (its ids arrived during the previous iteration)
+        load_id(blk + 2 * GW);   // batch k+2
+        __syncwarp();
+        for (int task = lane; task < nvalid * nPg; task += 32) {
+            const int te = task / nPg, p = task - te * nPg;
+            double* E = geo + te * rec;
+            warp_geometry_task<DIM, NPE>(X + te * NPE * DIM, dNt + p * W::TS, scale * wt[p], E + p, E + nPg + p * W::GPS);
+        }
+        __syncwarp();
+        const bool mine = el < nvalid;  // el < EPW holds for every lane below EPW*NPE
+        if constexpr (SYM) {
+            double acc[W::NBS][DIM][DIM];
+            if (mine) warp_rows_sym<DIM, NPE, ORTHO>(C2, geo + el * rec, nPg, a, acc);
+            if (mine && a == 0) bulk_wait_read();  // the previous copy of this element tile has left shared memory
+            __syncwarp();
+            if (mine) warp_store_sym<DIM, NPE>(acc, a, stage + el * W::ES);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (mine && a == 0) {
+                bulk_store(out + (e0 + el) * (long long)KE, stage + el * W::ES, KE * sizeof(double));
+                bulk_commit();
+            }
+        } else {
+            double acc[NPE][DIM][DIM];
+            if (mine) {
+                warp_rows_full<DIM, NPE, ORTHO>(C2, geo + el * rec, nPg, a, acc);
+                double* dst = out + (e0 + el) * (long long)KE + (long long)(a * DIM) * NDOF;
+                if constexpr (Tile::kBulk) {
+                    double* my_stage = stage + lane * Tile::LANE_STAGE;
+                    bulk_wait_read();
+                    EFB_UNROLL
+                    for (int i = 0; i < DIM; ++i)
+                        EFB_UNROLL
+                        for (int c = 0; c < NDOF; c += 2) {
+                            Pair v;
+                            v.x = acc[c / DIM][i][c % DIM];
+                            v.y = acc[(c + 1) / DIM][i][(c + 1) % DIM];
+                            *reinterpret_cast<Pair*>(my_stage + i * NDOF + c) = v;
+                        }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    bulk_store(dst, my_stage, DIM * NDOF * sizeof(double));
+                    bulk_commit();
+                } else {
+                    EFB_UNROLL
+                    for (int i = 0; i < DIM; ++i)
+                        EFB_UNROLL
+                        for (int c = 0; c < NDOF; ++c) dst[i * NDOF + c] = acc[c / DIM][i][c % DIM];
+                }
+            }
+        }
+    }
+    bulk_wait_read();  // shared memory outlives the last copy
+}
+
+// which form of the homogeneous-C kernel runs: EFB_ELASTIC_KERNEL = v6 | w | wsym | wortho overrides the default
+// (the fastest form the structure of C allows); dev/tuning knob, read at every call
+enum ElasticForm { kFormV6 = 0, kFormW = 1, kFormWSym = 2, kFormWSymOrtho = 3 };
+
+template <int DIM>
+static int elastic_form_for(const CMat& C2) {
+    constexpr int NS = StrainSize<DIM>::value;
+    bool sym = true, ortho = true;
+    for (int s = 0; s < NS; ++s)
+        for (int r = 0; r < NS; ++r) {
+            if (C2.v[s * NS + r] != C2.v[r * NS + s]) sym = false;
+            const bool structural_zero = (s != r) && (s >= DIM || r >= DIM);
+            if (structural_zero && C2.v[s * NS + r] != 0.0) ortho = false;
+        }
+    int form = sym ? (ortho ? kFormWSymOrtho : kFormWSym) : kFormW;
+    if (const char* env = getenv("EFB_ELASTIC_KERNEL")) {
+        if (!strcmp(env, "v6")) form = kFormV6;
+        else if (!strcmp(env, "w")) form = kFormW;
+        else if (!strcmp(env, "wsym") && sym) form = kFormWSym;
+        else if (!strcmp(env, "wortho") && sym && ortho) form = kFormWSymOrtho;
+    }
+    return form;
+}
+
+template <int DIM, int NPE, bool SYM, bool ORTHO>
+static int launch_elastic_w(const efb_group* g, const CMat& C2, double scale, double* out, cudaStream_t st) {
+    using W = ElasticWarp<DIM, NPE>;
+    const size_t bytes = sizeof(double) * (W::tables(g->nPg) + kWarpKernelWarps * W::per_warp(g->nPg, SYM));
+    if (ensure_smem(k_elastic_w<DIM, NPE, SYM, ORTHO>, bytes)) return 1;
+    const long long nbatch = (g->Ne + W::EPW - 1) / W::EPW;
+    if (nbatch == 0) return 0;
+    const long long nblk = (nbatch + kWarpKernelWarps - 1) / kWarpKernelWarps;
+    const long long grid = persistent_grid(k_elastic_w<DIM, NPE, SYM, ORTHO>, kWarpKernelWarps * 32, bytes, nblk);
+    k_elastic_w<DIM, NPE, SYM, ORTHO><<<(unsigned)grid, kWarpKernelWarps * 32, bytes, st>>>(view_of(g), C2, scale, out, nbatch);
+    return check_launch("efb_elastic_Ke");
+}
+
+// element types that have the warp-autonomous instantiations (FP64-bound, DIM rows x all columns in one thread)
+template <int DIM, int NPE>
+struct HasWarpKernel {
+    static constexpr bool value = (DIM == 3 && NPE == 8);
+};
+
+template <int DIM, int NPE>
+static int launch_elastic_const(const efb_group* g, const CMat& C2, const double* C, double scale, double* out, cudaStream_t st) {
+    if constexpr (HasWarpKernel<DIM, NPE>::value) {
+        if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+            switch (elastic_form_for<DIM>(C2)) {
+                case kFormW: return launch_elastic_w<DIM, NPE, false, false>(g, C2, scale, out, st);
+                case kFormWSym: return launch_elastic_w<DIM, NPE, true, false>(g, C2, scale, out, st);
+                case kFormWSymOrtho: return launch_elastic_w<DIM, NPE, true, true>(g, C2, scale, out, st);
+                default: break;
+            }
+        }
+    }
+    return launch_elastic_mode<DIM, NPE, 0>(g, C2, C, scale, out, st);
+}
+
 template <int DIM, int NPE>
 static int launch_elastic(const efb_group* g, const double* C, const double* C_host, int C_mode, double scale, double* out,
                           cudaStream_t st) {
@@ -301,7 +466,7 @@ static int launch_elastic(const efb_group* g, const double* C, const double* C_h
             }
         }
         prescale_C<DIM>(Cconst);  // Kelvin-Mandel C -> S C S (elem_kernels.cuh, O1)
-        return launch_elastic_mode<DIM, NPE, 0>(g, Cconst, C, scale, out, st);
+        return launch_elastic_const<DIM, NPE>(g, Cconst, C, scale, out, st);
     }
     if (C_mode == 1) return launch_elastic_mode<DIM, NPE, 1>(g, Cconst, C, scale, out, st);
     return launch_elastic_mode<DIM, NPE, 2>(g, Cconst, C, scale, out, st);

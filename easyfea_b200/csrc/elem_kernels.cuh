@@ -440,9 +440,10 @@ EFB_D void elastic_gather_C(const ElasticSmem<DIM, NPE>& sm, const double* EFB_R
 }
 
 // G2-G6 for one (element, Gauss point), in registers                    _group_elem.py:832-1105
+// (reference gradients cached in registers, all gN values formed before the first store: see warp_geometry_task)
 template <int DIM, int NPE>
-EFB_D void elastic_geometry_task(const ElasticSmem<DIM, NPE>& sm, const double* dNt, const double* wt, double scale, double* E,
-                                 int p) {
+EFB_D void elastic_geometry_task(const ElasticSmem<DIM, NPE>& sm, const double* EFB_RESTRICT dNt, const double* EFB_RESTRICT wt,
+                                 double scale, double* EFB_RESTRICT E, int p) {
     using SM = ElasticSmem<DIM, NPE>;
     constexpr int GS = SM::GS, TS = SM::TS, GPS = SM::GPS;
     const double* X = E + sm.o_X();
@@ -450,24 +451,59 @@ EFB_D void elastic_geometry_task(const ElasticSmem<DIM, NPE>& sm, const double* 
     double F[DIM * DIM], Fi[DIM * DIM];
     EFB_UNROLL
     for (int i = 0; i < DIM * DIM; ++i) F[i] = 0.0;
-    EFB_UNROLL
-    for (int n = 0; n < NPE; ++n) {  // F[r][c] = sum_n dN[p][r][n] x[n][c]
+    if constexpr (DIM * NPE <= 30) {
+        double dn[DIM][NPE];
         EFB_UNROLL
         for (int r = 0; r < DIM; ++r)
             EFB_UNROLL
-            for (int c = 0; c < DIM; ++c) F[r * DIM + c] += dNp[r * NPE + n] * X[n * DIM + c];
-    }
-    const double det = det_inv<DIM>(F, Fi);
-    E[sm.o_wJ() + p] = scale * (fabs(det) * wt[p]);
-    double* gp = E + sm.o_gN() + p * GPS;
-    EFB_UNROLL
-    for (int a = 0; a < NPE; ++a) {  // gN[a][d] = sum_k Fi[d][k] dN[p][k][a]
+            for (int n = 0; n < NPE; ++n) dn[r][n] = dNp[r * NPE + n];
         EFB_UNROLL
-        for (int d = 0; d < DIM; ++d) {
-            double s = 0.0;
+        for (int n = 0; n < NPE; ++n) {
             EFB_UNROLL
-            for (int k = 0; k < DIM; ++k) s += Fi[d * DIM + k] * dNp[k * NPE + a];
-            gp[a * GS + d] = s;
+            for (int r = 0; r < DIM; ++r)
+                EFB_UNROLL
+                for (int c = 0; c < DIM; ++c) F[r * DIM + c] += dn[r][n] * X[n * DIM + c];
+        }
+        const double det = det_inv<DIM>(F, Fi);
+        double gn[NPE][DIM];
+        EFB_UNROLL
+        for (int a = 0; a < NPE; ++a) {
+            EFB_UNROLL
+            for (int d = 0; d < DIM; ++d) {
+                double s = 0.0;
+                EFB_UNROLL
+                for (int k = 0; k < DIM; ++k) s += Fi[d * DIM + k] * dn[k][a];
+                gn[a][d] = s;
+            }
+        }
+        E[sm.o_wJ() + p] = scale * (fabs(det) * wt[p]);
+        double* gp = E + sm.o_gN() + p * GPS;
+        EFB_UNROLL
+        for (int a = 0; a < NPE; ++a)
+            EFB_UNROLL
+            for (int d = 0; d < DIM; ++d) gp[a * GS + d] = gn[a][d];
+    } else {  // high-order elements: too many reference gradients for the register file, stream them
+        EFB_UNROLL
+        for (int n = 0; n < NPE; ++n) {  // F[r][c] = sum_n dN[p][r][n] x[n][c]
+            EFB_UNROLL
+            for (int r = 0; r < DIM; ++r)
+                EFB_UNROLL
+                for (int c = 0; c < DIM; ++c) F[r * DIM + c] += dNp[r * NPE + n] * X[n * DIM + c];
+        }
+        const double det = det_inv<DIM>(F, Fi);
+        E[sm.o_wJ() + p] = scale * (fabs(det) * wt[p]);
+        double* gp = E + sm.o_gN() + p * GPS;
+        EFB_UNROLL
+        for (int a = 0; a < NPE; ++a) {  // gN[a][d] = sum_k Fi[d][k] dN[p][k][a]
+            double s[DIM];
+            EFB_UNROLL
+            for (int d = 0; d < DIM; ++d) {
+                s[d] = 0.0;
+                EFB_UNROLL
+                for (int k = 0; k < DIM; ++k) s[d] += Fi[d * DIM + k] * dNp[k * NPE + a];
+            }
+            EFB_UNROLL
+            for (int d = 0; d < DIM; ++d) gp[a * GS + d] = s[d];
         }
     }
 }
@@ -529,6 +565,295 @@ EFB_D void elastic_block(const GroupView& g, const CMat& C2const, const double* 
                 for (int j = 0; j < NB * DIM; ++j) dst[i * NDOF + j] = acc[i][j];
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// O1, homogeneous C, warp-autonomous form (elements whose DIM rows x all columns fit one thread, CS == 1).
+//
+// Every warp is its own pipeline: it gathers the EPW = 32/NPE elements of its batch (node ids / coordinates of the next
+// batches travel in registers while this one is computed), runs the EPW*nPg geometry tasks on its own lanes, contracts,
+// stages its element matrices in warp-private shared memory and ships them with bulk asynchronous copies.  Only warp
+// barriers: with 8 such warps per SM every sub-partition carries the same FP64 load and the phases of different warps
+// drift apart, so gather/geometry/store latency of one warp hides under the FMA stream of its neighbour.
+//
+// SYM (C == C^T, checked on the host): K_e is symmetric, K[b,a] = K[a,b]^T as DIM x DIM node blocks.  Lane (el, a)
+// computes the NBS = NPE/2 + 1 blocks (a, (a+t) mod NPE), t = 0..NPE/2 (a cyclic cover of the block upper triangle,
+// the same number of blocks on every lane), and writes both the block and its transpose into the element tile.
+// ORTHO (no normal/shear coupling and a diagonal shear block in C, e.g. isotropic or axis-aligned orthotropic): the
+// structurally zero products of bc and of the block update are not issued (7 instead of 9 FMAs per block row in 3D);
+// the skipped terms are exact zeros, so the result is bit-identical to the full update.
+// ---------------------------------------------------------------------------------------------------------
+template <int DIM, int NPE>
+struct ElasticWarp {
+    static constexpr int NDOF = DIM * NPE, KE = NDOF * NDOF;
+    static constexpr int EPW = 32 / NPE;                 // elements per warp batch
+    static constexpr int NBS = NPE / 2 + 1;              // node blocks per lane, symmetric scheme
+    static constexpr int NMIR = (NPE - 1) / 2;           // blocks t = 1..NMIR are mirrored (t = 0 and t = NPE/2 (even NPE) are not)
+    static constexpr int TS = (DIM * NPE) | 1;           // odd stride of one Gauss point in the dN table
+    static constexpr int GPS = (NPE * DIM) | 1;          // odd stride of one Gauss point in gN (== ElasticSmem::GPS)
+    static constexpr int XW = (EPW * NPE * DIM + 1) & ~1;  // coordinates of the batch
+    // strides = 8 (mod 16) doubles: the per-lane 8-byte accesses of two elements sharing a half-warp fall in
+    // complementary banks (HEXA8: 3b and 3b+8 (mod 16), b = 0..7, are 16 distinct bank pairs)
+    EFB_HD static constexpr int pad8(int n) { return n + ((8 - n % 16) + 16) % 16; }
+    static constexpr int ES = pad8(KE);                  // element tile of the staging area (symmetric scheme)
+    EFB_HD static int rec(int nPg) { return pad8(nPg + nPg * GPS); }  // per element: wJ[nPg] | gN[nPg][GPS]
+    static constexpr int STAGE_SYM = EPW * ES;
+    static constexpr int STAGE_LANE = 32 * ElasticTile<DIM, NPE>::LANE_STAGE;  // per-lane tiles (general scheme)
+    EFB_HD static int tables(int nPg) { return (nPg * TS + nPg + 1) & ~1; }
+    EFB_HD static int per_warp(int nPg, bool sym) { return (sym ? STAGE_SYM : STAGE_LANE) + XW + EPW * rec(nPg); }
+    static_assert(ElasticTile<DIM, NPE>::CS == 1, "warp-autonomous kernel: one thread must hold DIM full rows");
+};
+
+// G2-G6 of one (element, Gauss point): X (NPE x DIM) -> wJ, gN[a][d]       _group_elem.py:832-1105
+// The reference gradients of the Gauss point are read into registers once and serve both F and gN, and every gN value is
+// formed before the first store: the stores alias the loads as far as the compiler knows, and interleaving them
+// serialises the task on shared-memory latency (measured: 27 % of the kernel's samples, profiles/README.md).
+template <int DIM, int NPE>
+EFB_D void warp_geometry_task(const double* EFB_RESTRICT X, const double* EFB_RESTRICT dNp, double wscale,
+                              double* EFB_RESTRICT wJp, double* EFB_RESTRICT gp) {
+    double dn[DIM][NPE];
+    EFB_UNROLL
+    for (int r = 0; r < DIM; ++r)
+        EFB_UNROLL
+        for (int n = 0; n < NPE; ++n) dn[r][n] = dNp[r * NPE + n];
+    double F[DIM * DIM], Fi[DIM * DIM];
+    EFB_UNROLL
+    for (int i = 0; i < DIM * DIM; ++i) F[i] = 0.0;
+    EFB_UNROLL
+    for (int n = 0; n < NPE; ++n) {
+        double x[DIM];
+        EFB_UNROLL
+        for (int c = 0; c < DIM; ++c) x[c] = X[n * DIM + c];
+        EFB_UNROLL
+        for (int r = 0; r < DIM; ++r)
+            EFB_UNROLL
+            for (int c = 0; c < DIM; ++c) F[r * DIM + c] += dn[r][n] * x[c];
+    }
+    const double det = det_inv<DIM>(F, Fi);
+    double gn[NPE][DIM];
+    EFB_UNROLL
+    for (int a = 0; a < NPE; ++a) {
+        EFB_UNROLL
+        for (int d = 0; d < DIM; ++d) {
+            double s = 0.0;
+            EFB_UNROLL
+            for (int k = 0; k < DIM; ++k) s += Fi[d * DIM + k] * dn[k][a];
+            gn[a][d] = s;
+        }
+    }
+    *wJp = wscale * fabs(det);
+    EFB_UNROLL
+    for (int a = 0; a < NPE; ++a)
+        EFB_UNROLL
+        for (int d = 0; d < DIM; ++d) gp[a * DIM + d] = gn[a][d];
+}
+
+// bc[i][:] = w G[:, (a,i)]^T C2 for the DIM dof rows of node a (C2 = S C S, homogeneous)
+template <int DIM, bool ORTHO>
+EFB_D void warp_bc(const CMat& C2, double w, const double* ga, double (&bc)[DIM][StrainSize<DIM>::value]) {
+    constexpr int NS = StrainSize<DIM>::value;
+#define EFB_C2(s_, r_) C2.v[(s_) * NS + (r_)]
+    if constexpr (DIM == 2) {
+        const double wx = w * ga[0], wy = w * ga[1];
+        if constexpr (ORTHO) {
+            bc[0][0] = wx * EFB_C2(0, 0); bc[0][1] = wx * EFB_C2(0, 1); bc[0][2] = wy * EFB_C2(2, 2);
+            bc[1][0] = wy * EFB_C2(1, 0); bc[1][1] = wy * EFB_C2(1, 1); bc[1][2] = wx * EFB_C2(2, 2);
+        } else {
+            EFB_UNROLL
+            for (int r = 0; r < NS; ++r) {
+                bc[0][r] = wx * EFB_C2(0, r) + wy * EFB_C2(2, r);
+                bc[1][r] = wy * EFB_C2(1, r) + wx * EFB_C2(2, r);
+            }
+        }
+    } else {
+        const double wx = w * ga[0], wy = w * ga[1], wz = w * ga[2];
+        if constexpr (ORTHO) {
+            bc[0][0] = wx * EFB_C2(0, 0); bc[0][1] = wx * EFB_C2(0, 1); bc[0][2] = wx * EFB_C2(0, 2);
+            bc[0][3] = 0.0;               bc[0][4] = wz * EFB_C2(4, 4); bc[0][5] = wy * EFB_C2(5, 5);
+            bc[1][0] = wy * EFB_C2(1, 0); bc[1][1] = wy * EFB_C2(1, 1); bc[1][2] = wy * EFB_C2(1, 2);
+            bc[1][3] = wz * EFB_C2(3, 3); bc[1][4] = 0.0;               bc[1][5] = wx * EFB_C2(5, 5);
+            bc[2][0] = wz * EFB_C2(2, 0); bc[2][1] = wz * EFB_C2(2, 1); bc[2][2] = wz * EFB_C2(2, 2);
+            bc[2][3] = wy * EFB_C2(3, 3); bc[2][4] = wx * EFB_C2(4, 4); bc[2][5] = 0.0;
+        } else {
+            EFB_UNROLL
+            for (int r = 0; r < NS; ++r) {
+                bc[0][r] = wx * EFB_C2(0, r) + wz * EFB_C2(4, r) + wy * EFB_C2(5, r);
+                bc[1][r] = wy * EFB_C2(1, r) + wz * EFB_C2(3, r) + wx * EFB_C2(5, r);
+                bc[2][r] = wz * EFB_C2(2, r) + wy * EFB_C2(3, r) + wx * EFB_C2(4, r);
+            }
+        }
+    }
+#undef EFB_C2
+}
+
+// blk[i][j] += bc[i][:] . G[:, (b,j)] for one column node b with gradient gb
+template <int DIM, bool ORTHO>
+EFB_D void warp_block_update(const double (&bc)[DIM][StrainSize<DIM>::value], const double* gb, double (&blk)[DIM][DIM]) {
+    if constexpr (DIM == 2) {
+        const double gx = gb[0], gy = gb[1];
+        EFB_UNROLL
+        for (int i = 0; i < 2; ++i) {
+            double s0 = blk[i][0], s1 = blk[i][1];
+            s0 += bc[i][0] * gx;
+            s0 += bc[i][2] * gy;
+            s1 += bc[i][1] * gy;
+            s1 += bc[i][2] * gx;
+            blk[i][0] = s0;
+            blk[i][1] = s1;
+        }
+    } else {
+        const double gx = gb[0], gy = gb[1], gz = gb[2];
+        EFB_UNROLL
+        for (int i = 0; i < 3; ++i) {
+            double s0 = blk[i][0], s1 = blk[i][1], s2 = blk[i][2];
+            s0 += bc[i][0] * gx;
+            if (!(ORTHO && i == 1)) s0 += bc[i][4] * gz;
+            if (!(ORTHO && i == 2)) s0 += bc[i][5] * gy;
+            s1 += bc[i][1] * gy;
+            if (!(ORTHO && i == 0)) s1 += bc[i][3] * gz;
+            if (!(ORTHO && i == 2)) s1 += bc[i][5] * gx;
+            s2 += bc[i][2] * gz;
+            if (!(ORTHO && i == 0)) s2 += bc[i][3] * gy;
+            if (!(ORTHO && i == 1)) s2 += bc[i][4] * gx;
+            blk[i][0] = s0;
+            blk[i][1] = s1;
+            blk[i][2] = s2;
+        }
+    }
+}
+
+// general scheme: the DIM rows of node a against every column node (same association as elastic_rows, mode 0)
+template <int DIM, int NPE, bool ORTHO>
+EFB_D void warp_rows_full(const CMat& C2, const double* EFB_RESTRICT geoE, int nPg, int a, double (&acc)[NPE][DIM][DIM]) {
+    constexpr int NS = StrainSize<DIM>::value, GPS = ElasticWarp<DIM, NPE>::GPS;
+    EFB_UNROLL
+    for (int b = 0; b < NPE; ++b)
+        EFB_UNROLL
+        for (int i = 0; i < DIM; ++i)
+            EFB_UNROLL
+            for (int j = 0; j < DIM; ++j) acc[b][i][j] = 0.0;
+    for (int p = 0; p < nPg; ++p) {
+        const double* gp = geoE + nPg + p * GPS;
+        double bc[DIM][NS];
+        warp_bc<DIM, ORTHO>(C2, geoE[p], gp + a * DIM, bc);
+        EFB_UNROLL
+        for (int b = 0; b < NPE; ++b) warp_block_update<DIM, ORTHO>(bc, gp + b * DIM, acc[b]);
+    }
+}
+
+// symmetric scheme: blocks (a, (a+t) mod NPE), t = 0..NPE/2.  The operands are software-pipelined by hand: the own
+// gradient and weight of Gauss point p+1 and the column gradient of block t+1 are loaded while block t is accumulated
+// (block 0 is the diagonal block: its column gradient is the own gradient, no load).
+template <int DIM, int NPE, bool ORTHO>
+EFB_D void warp_rows_sym(const CMat& C2, const double* EFB_RESTRICT geoE, int nPg, int a,
+                         double (&acc)[ElasticWarp<DIM, NPE>::NBS][DIM][DIM]) {
+    constexpr int NS = StrainSize<DIM>::value, GPS = ElasticWarp<DIM, NPE>::GPS, NBS = ElasticWarp<DIM, NPE>::NBS;
+    EFB_UNROLL
+    for (int t = 0; t < NBS; ++t)
+        EFB_UNROLL
+        for (int i = 0; i < DIM; ++i)
+            EFB_UNROLL
+            for (int j = 0; j < DIM; ++j) acc[t][i][j] = 0.0;
+    int boff[NBS];  // offsets of the column nodes of this lane
+    EFB_UNROLL
+    for (int t = 0; t < NBS; ++t) {
+        int b = a + t;
+        if (b >= NPE) b -= NPE;
+        boff[t] = b * DIM;
+    }
+    const double* gp = geoE + nPg;
+    double w_n = geoE[0], ga_n[DIM];
+    EFB_UNROLL
+    for (int d = 0; d < DIM; ++d) ga_n[d] = gp[boff[0] + d];
+    for (int p = 0; p < nPg; ++p, gp += GPS) {
+        const double w = w_n;
+        double gb[DIM], gb_n[DIM];
+        EFB_UNROLL
+        for (int d = 0; d < DIM; ++d) gb[d] = ga_n[d];
+        if (NBS > 1) {
+            EFB_UNROLL
+            for (int d = 0; d < DIM; ++d) gb_n[d] = gp[boff[NBS > 1 ? 1 : 0] + d];
+        }
+        if (p + 1 < nPg) {
+            w_n = geoE[p + 1];
+            EFB_UNROLL
+            for (int d = 0; d < DIM; ++d) ga_n[d] = gp[GPS + boff[0] + d];
+        }
+        double bc[DIM][NS];
+        warp_bc<DIM, ORTHO>(C2, w, gb, bc);
+        EFB_UNROLL
+        for (int t = 0; t < NBS; ++t) {
+            warp_block_update<DIM, ORTHO>(bc, gb, acc[t]);
+            EFB_UNROLL
+            for (int d = 0; d < DIM; ++d) gb[d] = gb_n[d];
+            if (t + 2 < NBS) {
+                EFB_UNROLL
+                for (int d = 0; d < DIM; ++d) gb_n[d] = gp[boff[t + 2] + d];
+            }
+        }
+    }
+}
+
+// block (a, b) and its transpose (b, a) -> element tile (row-major NDOF x NDOF)
+template <int DIM, int NPE>
+EFB_D void warp_store_sym(const double (&acc)[ElasticWarp<DIM, NPE>::NBS][DIM][DIM], int a, double* tile) {
+    using W = ElasticWarp<DIM, NPE>;
+    EFB_UNROLL
+    for (int t = 0; t < W::NBS; ++t) {
+        int b = a + t;
+        if (b >= NPE) b -= NPE;
+        EFB_UNROLL
+        for (int i = 0; i < DIM; ++i)
+            EFB_UNROLL
+            for (int j = 0; j < DIM; ++j) tile[(a * DIM + i) * W::NDOF + b * DIM + j] = acc[t][i][j];
+        if (t >= 1 && t <= W::NMIR) {
+            EFB_UNROLL
+            for (int i = 0; i < DIM; ++i)
+                EFB_UNROLL
+                for (int j = 0; j < DIM; ++j) tile[(b * DIM + j) * W::NDOF + a * DIM + i] = acc[t][i][j];
+        }
+    }
+}
+
+// host-checkable composition of one warp batch (the device kernel runs the same stages with warp barriers and bulk copies
+// in between, elem_kernels.cu): `wmem` = the warp's shared memory, layout [stage | X | records]
+template <int DIM, int NPE, bool SYM, bool ORTHO>
+EFB_D void elastic_warp_batch_ref(const GroupView& g, const CMat& C2, double scale, double* EFB_RESTRICT out, long long blk,
+                                  const double* dNt, const double* wt, double* wmem) {
+    using W = ElasticWarp<DIM, NPE>;
+    const int nPg = g.nPg, rec = W::rec(nPg);
+    double* stage = wmem;
+    double* X = wmem + (SYM ? W::STAGE_SYM : W::STAGE_LANE);
+    double* geo = X + W::XW;
+    const long long e0 = blk * W::EPW;
+    const int nvalid = (g.Ne - e0 < W::EPW) ? (int)(g.Ne - e0) : W::EPW;
+    for (int lane = 0; lane < nvalid * NPE; ++lane) {
+        const double* src = g.coord + (long long)g.connect[e0 * NPE + lane] * g.coord_stride;
+        for (int d = 0; d < DIM; ++d) X[lane * DIM + d] = src[d];
+    }
+    for (int task = 0; task < nvalid * nPg; ++task) {
+        const int el = task / nPg, p = task - el * nPg;
+        double* E = geo + el * rec;
+        warp_geometry_task<DIM, NPE>(X + el * NPE * DIM, dNt + p * W::TS, scale * wt[p], E + p, E + nPg + p * W::GPS);
+    }
+    for (int lane = 0; lane < nvalid * NPE; ++lane) {
+        const int el = lane / NPE, a = lane - el * NPE;
+        double* dst = out + (e0 + el) * (long long)W::KE;
+        if constexpr (SYM) {
+            double acc[W::NBS][DIM][DIM];
+            warp_rows_sym<DIM, NPE, ORTHO>(C2, geo + el * rec, nPg, a, acc);
+            warp_store_sym<DIM, NPE>(acc, a, stage + el * W::ES);
+        } else {
+            double acc[NPE][DIM][DIM];
+            warp_rows_full<DIM, NPE, ORTHO>(C2, geo + el * rec, nPg, a, acc);
+            for (int i = 0; i < DIM; ++i)
+                for (int b = 0; b < NPE; ++b)
+                    for (int j = 0; j < DIM; ++j) dst[(a * DIM + i) * W::NDOF + b * DIM + j] = acc[b][i][j];
+        }
+    }
+    if constexpr (SYM)
+        for (int el = 0; el < nvalid; ++el)
+            for (int i = 0; i < W::KE; ++i) out[(e0 + el) * (long long)W::KE + i] = stage[el * W::ES + i];
 }
 
 // ---------------------------------------------------------------------------------------------------------

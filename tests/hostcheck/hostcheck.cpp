@@ -80,6 +80,36 @@ extern "C" int hc_elastic_Ke(const efb_group* g, const double* C, int C_mode, do
     return 2;
 }
 
+// warp-autonomous homogeneous-C forms (elem_kernels.cuh, ElasticWarp): form 1 = general, 2 = symmetric, 3 = symmetric + ortho
+template <int D, int N, bool SYM, bool ORTHO>
+static void run_elastic_warp(const efb_group* g, const double* C, double scale, double* out) {
+    constexpr int NS = StrainSize<D>::value;
+    using W = ElasticWarp<D, N>;
+    CMat Cc;
+    memset(&Cc, 0, sizeof(Cc));
+    memcpy(Cc.v, C, sizeof(double) * NS * NS);
+    prescale_C<D>(Cc);
+    const GroupView v = view_of(g);
+    std::vector<double> tab(W::tables(g->nPg)), wmem(W::per_warp(g->nPg, SYM));
+    for (int i = 0; i < g->nPg * D * N; ++i) tab[(i / (D * N)) * W::TS + i % (D * N)] = g->dN_pg[i];
+    for (int i = 0; i < g->nPg; ++i) tab[g->nPg * W::TS + i] = g->w_pg[i];
+    for (long long b = 0; b * W::EPW < g->Ne; ++b)
+        elastic_warp_batch_ref<D, N, SYM, ORTHO>(v, Cc, scale, out, b, tab.data(), tab.data() + g->nPg * W::TS, wmem.data());
+}
+
+extern "C" int hc_elastic_Ke_warp(const efb_group* g, const double* C, int form, double scale, double* out) {
+#define X(D, N)                                                                  \
+    if (g->dim == D && g->nPe == N) {                                            \
+        if (form == 1) run_elastic_warp<D, N, false, false>(g, C, scale, out);   \
+        else if (form == 2) run_elastic_warp<D, N, true, false>(g, C, scale, out); \
+        else run_elastic_warp<D, N, true, true>(g, C, scale, out);               \
+        return 0;                                                                \
+    }
+    X(2, 3) X(2, 4) X(2, 6) X(2, 9) X(3, 4) X(3, 8)
+#undef X
+    return 2;
+}
+
 extern "C" int hc_scalar(const efb_group* g, const double* r, int r_mode, double r_scalar, int has_r, const double* A, int A_mode,
                          const double* k, int k_mode, double k_scalar, int has_k, const double* f, int f_mode, double f_scalar,
                          int has_f, int dof_n, double scale, double* Ke, double* Fe, int f_keep_axis) {

@@ -52,6 +52,33 @@ def test_elastic_Ke(hostcheck, elemType, C_mode):
     assert rel_err(out, ref) < TOL
 
 
+@pytest.mark.parametrize("elemType", ["TRI3", "QUAD4", "TRI6", "QUAD9", "TETRA4", "HEXA8"])
+@pytest.mark.parametrize("form", [1, 2, 3])
+def test_elastic_Ke_warp_forms(hostcheck, elemType, form):
+    """Warp-autonomous homogeneous-C forms: general, symmetric (cyclic block cover + mirrored stores), symmetric + ortho
+    (structural zeros of C skipped) — the same bodies the device kernel `k_elastic_w` runs."""
+    rng = np.random.default_rng(5)
+    coords, connect = make_mesh(elemType)
+    g, keep, tab = host_group(elemType, coords, connect, "rigi")
+    dim, nPe, Ne = g.dim, g.nPe, g.Ne
+    ns = 3 if dim == 2 else 6
+    C = orc.IsoMaterial(dim, 210000.0, 0.3).C.copy()
+    if form == 1:  # arbitrary, non-symmetric
+        C = C * rng.uniform(0.5, 2.0, C.shape) + rng.uniform(-1e4, 1e4, C.shape)
+    elif form == 2:  # symmetric, fully populated
+        R = rng.uniform(-2e4, 2e4, C.shape)
+        C = C + R + R.T
+    else:  # orthotropic pattern: distinct normal block and shear moduli
+        C[:dim, :dim] *= np.array(rng.uniform(0.5, 2.0, (dim, dim)) + 0.0)
+        C[:dim, :dim] = 0.5 * (C[:dim, :dim] + C[:dim, :dim].T)
+        C[np.arange(dim, ns), np.arange(dim, ns)] *= rng.uniform(0.5, 2.0, ns - dim)
+    C = np.ascontiguousarray(C)
+    out = np.full((Ne, nPe * dim, nPe * dim), np.nan)
+    assert hostcheck.hc_elastic_Ke_warp(ctypes.byref(g), p(C), I(form), D(1.5), p(out)) == 0
+    ref = 1.5 * orc.linearized_elasticity(_geo(elemType, coords, connect, tab), C)
+    assert rel_err(out, ref) < TOL
+
+
 @pytest.mark.parametrize("elemType", list(ELEM_CASES))
 @pytest.mark.parametrize("mt", ["rigi", "mass"])
 def test_scalar_operators(hostcheck, elemType, mt):
