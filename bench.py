@@ -346,7 +346,7 @@ def pcg_leg(args, g, part, pat, data, world, dist):
     n, d = args.n, 3
     nrows = part.n_owned * d
     nz = int(pat.indptr[nrows].item())
-    K = DeviceCsr(pat.indptr[:nrows + 1], pat.indices[:nz], data[:nz], (nrows, part.n_local * d))
+    K = DeviceCsr(pat.indptr[:nrows + 1], pat.indices[:nz], data[:nz], (nrows, part.n_local * d), pat.node_graph)
     comm = None
     if world > 1:
         part.plan_exchange()

@@ -79,10 +79,14 @@ class NodeGraph:
 
 
 class DeviceCsr:
-    """CSR matrix resident on the device (`indptr`, `indices`, `data` torch tensors)."""
+    """CSR matrix resident on the device (`indptr`, `indices`, `data` torch tensors).
 
-    def __init__(self, indptr, indices, data, shape):
+    `node_graph = (adjptr, adj, dof_n)` is set for matrices assembled here: the dof rows of a node are one contiguous
+    block whose column structure is the node adjacency, which the solver's SpMV reads instead of `indices`."""
+
+    def __init__(self, indptr, indices, data, shape, node_graph=None):
         self.indptr, self.indices, self.data, self.shape = indptr, indices, data, tuple(shape)
+        self.node_graph = node_graph
 
     @property
     def nnz(self) -> int:
@@ -165,8 +169,14 @@ class CsrPattern:
         self.last_dense = dense
         return out
 
+    @property
+    def node_graph(self):
+        """(adjptr, adj, dof_n) of a matrix pattern whose rows are all node rows (no Lagrange rows), else None"""
+        g = self.graph
+        return (g.adjptr, g.adj, self.dof_n) if self.isMatrix and self.Ndof == g.Nn * self.dof_n else None
+
     def assemble(self, datas) -> DeviceCsr:
-        return DeviceCsr(self.indptr, self.indices, self.replay(datas), self.shape)
+        return DeviceCsr(self.indptr, self.indices, self.replay(datas), self.shape, self.node_graph)
 
     def inv_map(self) -> torch.Tensor:
         """The reference's `inv` array (int32, entry order k), for API parity / tests."""

@@ -56,6 +56,72 @@ __global__ void __launch_bounds__(kRedThreads)
     }
 }
 
+// Node-block form of the SpMV for matrices assembled by this library: the dof rows of node n are stored as one
+// contiguous D x (D*deg) block (csr_kernels.cuh), so the column structure is the NODE adjacency (adjptr/adj, one int32 per
+// D x D block instead of one index per coefficient: 9x less index traffic in 3D) and every gathered x value serves the D
+// rows of the block.  LPN lanes cooperate on one node; lane l takes columns l, l + LPN, ... of all D rows (coalesced).
+template <int D, int LPN>
+__global__ void __launch_bounds__(kRedThreads)
+    k_spmv_node(long long n_nodes, const long long* __restrict__ adjptr, const int* __restrict__ adj, const double* __restrict__ data,
+                const double* __restrict__ x, long long x_row_offset, const unsigned char* __restrict__ row_mask, double* __restrict__ y,
+                double* __restrict__ dot_partials) {
+    __shared__ double red[kRedThreads];
+    const int lane = threadIdx.x % LPN;
+    constexpr int NPB = kRedThreads / LPN;  // nodes per CTA per pass
+    double local = 0.0;
+    for (long long base = (long long)blockIdx.x * NPB; base < n_nodes; base += (long long)gridDim.x * NPB) {
+        const long long n = base + threadIdx.x / LPN;
+        const bool live = n < n_nodes;
+        double s[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) s[i] = 0.0;
+        if (live) {
+            const long long a0 = adjptr[n];
+            const int rowlen = D * (int)(adjptr[n + 1] - a0);
+            const double* blk = data + (long long)D * D * a0;
+            const int* cols = adj + a0;
+#pragma unroll 3
+            for (int l = lane; l < rowlen; l += LPN) {
+                const int c = l / D, j = l - c * D;
+                const double xv = x[(long long)cols[c] * D + j];
+#pragma unroll
+                for (int i = 0; i < D; ++i) s[i] += blk[i * rowlen + l] * xv;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int off = LPN / 2; off > 0; off >>= 1) s[i] += __shfl_down_sync(0xffffffffu, s[i], off, LPN);
+        if (live && lane == 0) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                const long long r = n * D + i;
+                const double v = (!row_mask || row_mask[r]) ? s[i] : 0.0;
+                y[r] = v;
+                if (dot_partials) local += x[x_row_offset + r] * v;
+            }
+        }
+    }
+    if (dot_partials) {
+        const double tot = block_sum(local, red);
+        if (threadIdx.x == 0) dot_partials[blockIdx.x] = tot;
+    }
+}
+
+template <int D>
+static int launch_spmv_node(long long n_nodes, const long long* adjptr, const int* adj, const double* data, const double* x,
+                            long long x_row_offset, const unsigned char* row_mask, double* y, double* partials, int lpn, cudaStream_t st) {
+#define EFB_SPMVN(L) k_spmv_node<D, L><<<kRedBlocks, kRedThreads, 0, st>>>(n_nodes, adjptr, adj, data, x, x_row_offset, row_mask, y, partials)
+    switch (lpn) {
+        case 4: EFB_SPMVN(4); break;
+        case 8: EFB_SPMVN(8); break;
+        case 16: EFB_SPMVN(16); break;
+        default: EFB_SPMVN(32); break;
+    }
+#undef EFB_SPMVN
+    return check_launch("efb_spmv_nodeblock");
+}
+
 __global__ void __launch_bounds__(kRedThreads) k_dot(long long n, const double* __restrict__ a, const double* __restrict__ b,
                                                      double* __restrict__ partials) {
     __shared__ double red[kRedThreads];
@@ -200,6 +266,21 @@ extern "C" int efb_spmv_csr(int64_t nrows, int index_bytes, const void* indptr, 
         return launch_spmv<long long>(nrows, indptr, indices, data, x, x_row_offset, row_mask, y, dot_partials, lanes_per_row,
                                       as_stream(stream));
     set_error("efb_spmv_csr: index_bytes must be 4 or 8");
+    return 1;
+}
+
+extern "C" int efb_spmv_nodeblock(int64_t n_nodes, int dof_n, const int64_t* adjptr, const int32_t* adj, const double* data,
+                                  const double* x, int64_t x_row_offset, const uint8_t* row_mask, double* y, double* dot_partials,
+                                  int lanes_per_node, void* stream) {
+    if (n_nodes == 0) return 0;
+    const long long* ap = (const long long*)adjptr;
+    switch (dof_n) {
+        case 1: return launch_spmv_node<1>(n_nodes, ap, adj, data, x, x_row_offset, row_mask, y, dot_partials, lanes_per_node, as_stream(stream));
+        case 2: return launch_spmv_node<2>(n_nodes, ap, adj, data, x, x_row_offset, row_mask, y, dot_partials, lanes_per_node, as_stream(stream));
+        case 3: return launch_spmv_node<3>(n_nodes, ap, adj, data, x, x_row_offset, row_mask, y, dot_partials, lanes_per_node, as_stream(stream));
+        default: break;
+    }
+    set_error("efb_spmv_nodeblock: dof_n must be 1, 2 or 3, got %d", dof_n);
     return 1;
 }
 

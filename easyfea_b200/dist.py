@@ -231,7 +231,7 @@ class ShardedGroup:
         if not hasattr(pat, "_nnz_owned"):
             pat._nnz_owned = int(pat.indptr[nrows].item())
         nz = pat._nnz_owned
-        return DeviceCsr(pat.indptr[:nrows + 1], pat.indices[:nz], data[:nz], (nrows, part.n_local * d))
+        return DeviceCsr(pat.indptr[:nrows + 1], pat.indices[:nz], data[:nz], (nrows, part.n_local * d), pat.node_graph)
 
     def owned_vector(self, Fe, dof_n: int):
         """dense owned part (n_owned*dof_n) of the assembled element vectors `Fe` (Ne_loc, ndof)"""

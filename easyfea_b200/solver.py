@@ -29,6 +29,13 @@ def spmv(A: DeviceCsr, x: torch.Tensor, y: torch.Tensor = None, row_offset: int 
     nrows = A.indptr.numel() - 1
     if y is None:
         y = dv.empty((nrows,))
+    ng = getattr(A, "node_graph", None)
+    if ng is not None and ng[2] in (1, 2, 3) and nrows % ng[2] == 0:
+        adjptr, adj, d = ng  # node-block product: the column structure is read from the node adjacency
+        n_nodes = nrows // d
+        _lib.call("efb_spmv_nodeblock", n_nodes, d, dv.ptr(adjptr), dv.ptr(adj), dv.ptr(A.data), dv.ptr(x), int(row_offset),
+                  dv.ptr(mask), dv.ptr(y), dv.ptr(partials), lanes_per_row(A.nnz, nrows), dv.stream_ptr())
+        return y
     _lib.call("efb_spmv_csr", nrows, A.index_bytes, dv.ptr(A.indptr), dv.ptr(A.indices), dv.ptr(A.data), dv.ptr(x), int(row_offset),
               dv.ptr(mask), dv.ptr(y), dv.ptr(partials), lanes_per_row(A.nnz, nrows), dv.stream_ptr())
     return y

@@ -47,11 +47,11 @@ class LocalSystem:
         data = pat.replay([Xe], n_nodes=self.n_owned)
         nrows = self.n_owned * d
         if self.n_owned == self.n_local:
-            return DeviceCsr(pat.indptr, pat.indices, data, (nrows, nrows))
+            return DeviceCsr(pat.indptr, pat.indices, data, (nrows, nrows), pat.node_graph)
         if not hasattr(pat, "_nnz_owned"):
             pat._nnz_owned = int(pat.indptr[nrows].item())
         nz = pat._nnz_owned
-        return DeviceCsr(pat.indptr[:nrows + 1], pat.indices[:nz], data[:nz], (nrows, self.n_local * d))
+        return DeviceCsr(pat.indptr[:nrows + 1], pat.indices[:nz], data[:nz], (nrows, self.n_local * d), pat.node_graph)
 
     def vector(self, Fe, dof_n: int) -> torch.Tensor:
         d = int(dof_n)

@@ -174,6 +174,11 @@ int efb_pcg_partials_size(void);
 int efb_spmv_csr(int64_t nrows, int index_bytes, const void* indptr, const void* indices, const double* data,
                  const double* x, int64_t x_row_offset, const uint8_t* row_mask, double* y, double* dot_partials,
                  int lanes_per_row, void* stream);
+/* same product for a matrix assembled by efb_csr_replay_matrix, read through the node adjacency it was built from
+ * (adjptr/adj of the pattern): y = A x over the dof rows of nodes [0, n_nodes); x, row_mask, dot_partials as above */
+int efb_spmv_nodeblock(int64_t n_nodes, int dof_n, const int64_t* adjptr, const int32_t* adj, const double* data,
+                       const double* x, int64_t x_row_offset, const uint8_t* row_mask, double* y, double* dot_partials,
+                       int lanes_per_node, void* stream);
 int efb_csr_diagonal(int64_t nrows, int64_t row_offset, int index_bytes, const void* indptr, const void* indices,
                      const double* data, double* diag, void* stream);
 int efb_pcg_inv_diag(int64_t n, const double* diag, const uint8_t* free_mask, double* out, void* stream);

@@ -63,6 +63,23 @@ def main():
         t = timeit(lambda: pat.replay([Ke], out=data), reps)
         out["replay_ms"] = t
         out["replay_GBps"] = (Ne * ndof * ndof * 8 + Ne * dg.nPe**2 * 4 + pat.nnz * 8) / t / 1e6
+    if os.environ.get("TUNE_SPMV", "0") == "1":
+        from easyfea_b200 import solver
+        from easyfea_b200.assembly import DeviceCsr
+        A = pat.assemble([Ke])
+        x = torch.randn(A.shape[1], dtype=torch.float64, device="cuda")
+        y = dv.empty((A.shape[0],))
+        mask = torch.ones(A.shape[0], dtype=torch.uint8, device="cuda")
+        partials = dv.empty((4096,))
+        out["spmv_node_ms"] = timeit(lambda: solver.spmv(A, x, y, 0, mask, partials), reps)
+        B = DeviceCsr(A.indptr, A.indices, A.data, A.shape)
+        out["spmv_csr_ms"] = timeit(lambda: solver.spmv(B, x, y, 0, mask, partials), reps)
+        out["spmv_bytes_GB"] = (A.nnz * 8 + A.nnz // dim**2 * 4 + A.shape[0] * 24) / 1e9
+        out["spmv_node_GBps"] = out["spmv_bytes_GB"] / out["spmv_node_ms"] * 1e3
+        diag = dv.empty((A.shape[0],))
+        from easyfea_b200 import _lib
+        out["diag_ms"] = timeit(lambda: _lib.call("efb_csr_diagonal", A.shape[0], 0, A.index_bytes, dv.ptr(A.indptr), dv.ptr(A.indices),
+                                                  dv.ptr(A.data), dv.ptr(diag), dv.stream_ptr()), 3)
     print(json.dumps(out), flush=True)
 
 

@@ -147,3 +147,35 @@ def test_pcg_elastic_cube(efb):
     xd = spla.spsolve(Ks[free][:, free].tocsc(), rhs)
     assert np.linalg.norm(x[free] - xd) / np.linalg.norm(xd) < 1e-6
     assert np.array_equal(x[known], x0[known])
+
+
+@pytest.mark.parametrize("elemType,dof_n", [("HEXA8", 3), ("TETRA4", 3), ("TRI3", 2), ("TRI3", 1), ("QUAD9", 2), ("HEXA27", 1)])
+def test_spmv_nodeblock_matches_scipy(efb, elemType, dof_n):
+    """The solver's node-block SpMV (column structure read from the node adjacency) against scipy's CSR product, with a
+    row mask and the fused x.y partials; also against the library's plain CSR SpMV on the same matrix."""
+    import torch
+
+    from easyfea_b200 import _lib
+    from easyfea_b200 import device as dv
+    from easyfea_b200.assembly import DeviceCsr
+
+    rng = np.random.default_rng(11)
+    coords, connect = make_mesh(elemType)
+    g = efb.mesh.ElemGroup(elemType, connect, coords, all_nodes_used=True)
+    Nn = coords.shape[0]
+    ndof = connect.shape[1] * dof_n
+    Xe = rng.standard_normal((connect.shape[0], ndof, ndof))
+    A = efb.asm.Assembler().Assemble_csr({g: Xe}, dof_n, Nn * dof_n, True, as_device=True)
+    assert A.node_graph is not None
+    x = rng.standard_normal(Nn * dof_n)
+    mask = (rng.uniform(size=Nn * dof_n) > 0.2).astype(np.uint8)
+    ref = (A.to_scipy() @ x) * mask
+    xd, md = dv.to_device(x), dv.to_device(mask)
+    partials = dv.empty((_lib.load().efb_pcg_partials_size(),))
+    y = efb.solver.spmv(A, xd, mask=md, partials=partials)
+    assert rel_err(y.cpu().numpy(), ref) < 1e-13
+    nblk = partials.numel() // 2
+    assert abs(float(partials[:nblk].sum()) - float(x @ ref)) <= 1e-10 * np.abs(x * ref).sum()
+    y_csr = efb.solver.spmv(DeviceCsr(A.indptr, A.indices, A.data, A.shape), xd, mask=md)
+    assert rel_err(y.cpu().numpy(), y_csr.cpu().numpy()) < 1e-13
+    assert np.array_equal(y.cpu().numpy()[mask == 0], np.zeros(int((mask == 0).sum())))
