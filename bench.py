@@ -365,25 +365,33 @@ def pcg_leg(args, g, part, pat, data, world, dist):
     iters = args.pcg_iters
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    solver.pcg(K, b, x0=x0, free_mask=free, tol=1e-30, maxiter=5, check_every=5, comm=comm)  # warm-up
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0.record()
-    x, info = solver.pcg(K, b, x0=x0, free_mask=free, tol=1e-30, maxiter=iters, check_every=iters, comm=comm)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device=data.device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    per = ms / info["iterations"]
-    bytes_it = nz * 12 + nrows * (4 + 12 * 8)
+
+    def timed(fused):
+        solver.pcg(K, b, x0=x0, free_mask=free, tol=1e-30, maxiter=5, check_every=5, comm=comm, fused=fused)  # warm-up
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        x, info = solver.pcg(K, b, x0=x0, free_mask=free, tol=1e-30, maxiter=iters, check_every=iters, comm=comm, fused=fused)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device=data.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / info["iterations"], info
+
+    per, info = timed(True)
+    per_unfused, info_u = timed(False)
+    bytes_it = nz * 8 + (nz // 9) * 4 + nrows * (4 + 12 * 8)  # node-block SpMV: one int32 per 3x3 block
     return {"iterations_timed": info["iterations"], "ms_per_iter": per, "rel_residual_after": info["rel_residual"],
+            "ms_per_iter_unfused": per_unfused, "rel_residual_after_unfused": info_u["rel_residual"],
             "GBps_per_gpu": bytes_it / (per * 1e-3) / 1e9, "dofs_per_gpu": nrows, "nnz_per_gpu": nz,
             "halo_bytes_per_exchange": 0 if comm is None else comm.bytes_per_exchange,
-            "note": "setup (diagonal, reference norm, initial residual: 3 extra SpMVs) is inside the timed region"}
+            "note": "fused: 3 kernels per iteration, reductions and halo pushes through peer memory inside the kernels "
+                    "(efb_pcg_iterate); unfused: one kernel per vector operation and, when sharded, NCCL send/recv + 2 all-reduces "
+                    "per iteration.  Setup (diagonal, reference norm, initial residual: 3 extra SpMVs) is inside the timed region"}
 
 
 def phase_field_leg(args, rank, world, dist):
@@ -411,6 +419,7 @@ def phase_field_leg(args, rank, world, dist):
     pfm = phasefield.PhaseFieldModel(phasefield.IsotropicMaterial(2, 210e9, 0.3, planeStress=False, thickness=1.0), "Miehe",
                                      "AT2", 2.7e3, l0)
     simu = staggered.PhaseFieldStaggered(sysm, pfm, pcg_tol=1e-8, pcg_maxiter=args.pf_maxiter)
+    simu.pcg_fused = not args.pf_unfused
     x, y = lattice[nodes, 0], lattice[nodes, 1]
     tol = 1e-12
     loc = np.arange(nodes.size)
@@ -437,6 +446,7 @@ def phase_field_leg(args, rank, world, dist):
                         f"{world} GPU(s)", "s_per_iter": ms / its / 1e3, "iterations_timed": its,
             "pcg_iters_damage": simu.info["damage"]["iterations"], "pcg_iters_elastic": simu.info["elastic"]["iterations"],
             "pcg_converged": bool(simu.info["damage"]["converged"] and simu.info["elastic"]["converged"]),
+            "pcg_fused": bool(simu.pcg_fused),
             "last_damage_increment": float(conv.item()), "max_damage": float(dmax.item())}
 
 
@@ -482,7 +492,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=200, help="cells per side of the owned HEXA8 cube (200 -> 8.0 M elements)")
+    ap.add_argument("--n", "--cells", dest="n", type=int, default=200, help="cells per side of the owned HEXA8 cube (200 -> 8.0 M elements)")
     ap.add_argument("--cpu-sample", type=int, default=32, help="cells per side of the CPU sample (32 -> 32 768 elements)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
@@ -492,6 +502,7 @@ def main():
     ap.add_argument("--pf-n", type=int, default=1000, help="TRI3 cells per side (1000 -> 2.0 M elements, config 3)")
     ap.add_argument("--pf-iters", type=int, default=2)
     ap.add_argument("--pf-maxiter", type=int, default=20000)
+    ap.add_argument("--pf-unfused", action="store_true", help="phase-field solves with the NCCL/kernel-per-operation PCG loop")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -30,6 +30,26 @@ class EfbPfMaterial(ctypes.Structure):
                 ("inv_sqrtC", c_f64 * 36)]
 
 
+MAX_RANKS = 8  # EFB_MAX_RANKS
+
+
+class EfbPcgSystem(ctypes.Structure):
+    """`efb_pcg_system` of include/easyfea_b200.h"""
+
+    _fields_ = [("nrows", c_i64), ("kind", c_i32), ("index_bytes", c_i32), ("dof_n", c_i32), ("lanes", c_i32), ("indptr", c_vp),
+                ("indices", c_vp), ("data", c_vp), ("free_mask", c_vp), ("inv_diag", c_vp), ("x", c_vp), ("r", c_vp), ("z", c_vp),
+                ("Ap", c_vp), ("partials", c_vp)]
+
+
+class EfbPcgPeer(ctypes.Structure):
+    """`efb_pcg_peer` of include/easyfea_b200.h"""
+
+    _fields_ = [("world", c_i32), ("rank", c_i32), ("n_send", c_i32), ("n_recv", c_i32), ("send_rank", c_i32 * MAX_RANKS),
+                ("recv_rank", c_i32 * MAX_RANKS), ("send_ptr", c_i64 * (MAX_RANKS + 1)), ("send_dst", c_i64 * MAX_RANKS),
+                ("base", c_vp * MAX_RANKS), ("pbuf_off", (c_i64 * 2) * MAX_RANKS), ("send_idx", c_vp), ("ar_seq", ctypes.c_uint64),
+                ("halo_seq", ctypes.c_uint64)]
+
+
 _GP = ctypes.POINTER(EfbGroup)
 _PP = ctypes.POINTER(c_vp)
 _I64P = ctypes.POINTER(c_i64)
@@ -70,6 +90,14 @@ SIGNATURES = {
     "efb_pcg_update_xr": [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "efb_pcg_update_p": [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "efb_pack_f64": [c_i64, c_vp, c_vp, c_vp, c_vp],
+    "efb_pcg_ctrl_bytes": [],
+    "efb_pcg_ctrl_layout": [_I32P],
+    "efb_pcg_iterate": [ctypes.POINTER(EfbPcgSystem), ctypes.POINTER(EfbPcgPeer), ctypes.c_int, c_i64, c_vp],
+    "efb_peer_alloc": [c_i64, _PP],
+    "efb_peer_free": [c_vp],
+    "efb_peer_export": [c_vp, c_vp],
+    "efb_peer_open": [c_vp, _PP],
+    "efb_peer_close": [c_vp],
     "efb_pcg_partials_size": [],
     "efb_version": [],
     "efb_device_count": [],

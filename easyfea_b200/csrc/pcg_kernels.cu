@@ -4,6 +4,9 @@
 // All scalars (r.z, p.Ap, ...) stay on the device; every dot product is a fixed-order two-stage reduction
 // (per-CTA partials in a fixed grid, then one CTA), hence deterministic.  Dirichlet dofs are handled by masking
 // (projected CG): the search direction is zero on constrained rows, so A_UU is never extracted.
+#include <stddef.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace efb {
@@ -24,13 +27,11 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return s;
 }
 
-// y[r] = sum_k data[k] x[indices[k]] for local rows; LPR lanes cooperate on one row; optional partial of x_row . y
+// y[r] = sum_k data[k] x[indices[k]] for local rows; LPR lanes cooperate on one row; returns the thread's part of x_row . y
 template <class IDX, int LPR>
-__global__ void __launch_bounds__(kRedThreads)
-    k_spmv(long long nrows, const IDX* __restrict__ indptr, const IDX* __restrict__ indices, const double* __restrict__ data,
-           const double* __restrict__ x, long long x_row_offset, const unsigned char* __restrict__ row_mask, double* __restrict__ y,
-           double* __restrict__ dot_partials) {
-    __shared__ double red[kRedThreads];
+__device__ __forceinline__ double spmv_rows(long long nrows, const IDX* __restrict__ indptr, const IDX* __restrict__ indices,
+                                            const double* __restrict__ data, const double* __restrict__ x, long long x_row_offset,
+                                            const unsigned char* __restrict__ row_mask, double* __restrict__ y, bool want_dot) {
     const int lane = threadIdx.x % LPR;
     constexpr int RPB = kRedThreads / LPR;  // rows per CTA per pass
     double local = 0.0;
@@ -47,9 +48,19 @@ __global__ void __launch_bounds__(kRedThreads)
         for (int off = LPR / 2; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off, LPR);
         if (live && lane == 0) {
             y[r] = s;
-            if (dot_partials) local += x[x_row_offset + r] * s;
+            if (want_dot) local += x[x_row_offset + r] * s;
         }
     }
+    return local;
+}
+
+template <class IDX, int LPR>
+__global__ void __launch_bounds__(kRedThreads)
+    k_spmv(long long nrows, const IDX* __restrict__ indptr, const IDX* __restrict__ indices, const double* __restrict__ data,
+           const double* __restrict__ x, long long x_row_offset, const unsigned char* __restrict__ row_mask, double* __restrict__ y,
+           double* __restrict__ dot_partials) {
+    __shared__ double red[kRedThreads];
+    const double local = spmv_rows<IDX, LPR>(nrows, indptr, indices, data, x, x_row_offset, row_mask, y, dot_partials != nullptr);
     if (dot_partials) {
         const double tot = block_sum(local, red);
         if (threadIdx.x == 0) dot_partials[blockIdx.x] = tot;
@@ -61,11 +72,9 @@ __global__ void __launch_bounds__(kRedThreads)
 // D x D block instead of one index per coefficient: 9x less index traffic in 3D) and every gathered x value serves the D
 // rows of the block.  LPN lanes cooperate on one node; lane l takes columns l, l + LPN, ... of all D rows (coalesced).
 template <int D, int LPN>
-__global__ void __launch_bounds__(kRedThreads)
-    k_spmv_node(long long n_nodes, const long long* __restrict__ adjptr, const int* __restrict__ adj, const double* __restrict__ data,
-                const double* __restrict__ x, long long x_row_offset, const unsigned char* __restrict__ row_mask, double* __restrict__ y,
-                double* __restrict__ dot_partials) {
-    __shared__ double red[kRedThreads];
+__device__ __forceinline__ double spmv_nodes(long long n_nodes, const long long* __restrict__ adjptr, const int* __restrict__ adj,
+                                             const double* __restrict__ data, const double* __restrict__ x, long long x_row_offset,
+                                             const unsigned char* __restrict__ row_mask, double* __restrict__ y, bool want_dot) {
     const int lane = threadIdx.x % LPN;
     constexpr int NPB = kRedThreads / LPN;  // nodes per CTA per pass
     double local = 0.0;
@@ -98,10 +107,20 @@ __global__ void __launch_bounds__(kRedThreads)
                 const long long r = n * D + i;
                 const double v = (!row_mask || row_mask[r]) ? s[i] : 0.0;
                 y[r] = v;
-                if (dot_partials) local += x[x_row_offset + r] * v;
+                if (want_dot) local += x[x_row_offset + r] * v;
             }
         }
     }
+    return local;
+}
+
+template <int D, int LPN>
+__global__ void __launch_bounds__(kRedThreads)
+    k_spmv_node(long long n_nodes, const long long* __restrict__ adjptr, const int* __restrict__ adj, const double* __restrict__ data,
+                const double* __restrict__ x, long long x_row_offset, const unsigned char* __restrict__ row_mask, double* __restrict__ y,
+                double* __restrict__ dot_partials) {
+    __shared__ double red[kRedThreads];
+    const double local = spmv_nodes<D, LPN>(n_nodes, adjptr, adj, data, x, x_row_offset, row_mask, y, dot_partials != nullptr);
     if (dot_partials) {
         const double tot = block_sum(local, red);
         if (threadIdx.x == 0) dot_partials[blockIdx.x] = tot;
@@ -250,6 +269,258 @@ static int launch_spmv(long long nrows, const void* indptr, const void* indices,
     return check_launch("efb_spmv_csr");
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused PCG iterations with peer-memory communication (include/easyfea_b200.h, efb_pcg_iterate)
+// ---------------------------------------------------------------------------------------------------------------
+struct PcgCtrl {
+    unsigned long long ar_flag[EFB_MAX_RANKS];    // [src] = number of reductions rank `src` has published here
+    unsigned long long halo_flag[EFB_MAX_RANKS];  // [src] = number of halo pushes rank `src` has completed into this region
+    double ar_val[2][EFB_MAX_RANKS][2];           // [seq & 1][src][quantity]
+    unsigned int ticket[4];                       // local: last-CTA detection, one counter per kernel
+    unsigned int error;                           // local: 1 = a wait timed out (peer lost); drains every later wait
+    unsigned int pad_[3];
+    double rz[2];                                 // local: r.z of iteration it in rz[it & 1]
+    double pAp;
+    double rr;                                    // local: r.r after the last finished iteration
+};
+constexpr int kCtrlBytes = 1024;
+static_assert(sizeof(PcgCtrl) <= kCtrlBytes, "control block");
+constexpr long long kSpinTimeoutCycles = 6000000000LL;  // ~3 s at 1.9 GHz: a lost peer must not hang the GPU
+
+#ifndef EFB_PCG_VARIANT
+#define EFB_PCG_VARIANT 0  // dev timing variants (scripts/build_variant.sh): 1 no CTA fence, 2 gpu scope, 3 no publish
+#endif
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+#if EFB_PCG_VARIANT == 2
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+#else
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+#endif
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+#if EFB_PCG_VARIANT == 2
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#else
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ void fence_sys() {
+#if EFB_PCG_VARIANT == 2
+    __threadfence();
+#else
+    __threadfence_system();
+#endif
+}
+
+// one thread: wait until *flag >= want (flags are monotonic); false when the wait was abandoned
+__device__ bool spin_until(const unsigned long long* flag, unsigned long long want, PcgCtrl* own) {
+    if (ld_acquire_sys(flag) >= want) return true;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < want) {
+        if (*(volatile unsigned int*)&own->error) return false;
+        if (clock64() - t0 > kSpinTimeoutCycles) {
+            atomicExch(&own->error, 1u);
+            return false;
+        }
+        __nanosleep(40);
+    }
+    return true;
+}
+
+// every CTA: wait for the `world` contributions of reduction number `seq` (1-based) and add them in rank order
+// (lane q of warp 0 waits for rank q; the sum over ranks is a fixed-order loop, identical on every rank)
+template <int M>
+__device__ __forceinline__ void gather_reduction(const efb_pcg_peer& P, PcgCtrl* own, unsigned long long seq, double (&out)[M],
+                                                 double* sh) {
+    if (threadIdx.x < EFB_MAX_RANKS) {
+        const int q = threadIdx.x;
+        if (q < P.world) {
+            spin_until(&own->ar_flag[q], seq, own);
+            const int buf = (int)((seq - 1) & 1);
+#pragma unroll
+            for (int m = 0; m < M; ++m) sh[q * M + m] = *(volatile double*)&own->ar_val[buf][q][m];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        double acc = 0.0;
+        for (int q = 0; q < P.world; ++q) acc += sh[q * M + m];
+        out[m] = acc;
+    }
+    __syncthreads();
+}
+
+// every CTA hands in its partial(s); the last one to arrive folds all of them in fixed order and stores the result into
+// every rank's control block, then raises the flags (reduction number `seq`, 1-based).  Returns true in the last CTA.
+template <int M>
+__device__ __forceinline__ bool publish_reduction(const efb_pcg_peer& P, PcgCtrl* own, double* __restrict__ partials,
+                                                  const double (&mine)[M], int ticket_id, unsigned long long seq, double* red,
+                                                  double (&total)[M]) {
+    __shared__ bool is_last;
+#if EFB_PCG_VARIANT == 3
+    return false;
+#endif
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) partials[m * kRedBlocks + blockIdx.x] = mine[m];
+#if EFB_PCG_VARIANT != 1
+        __threadfence();
+#endif
+        is_last = atomicAdd(&own->ticket[ticket_id], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        double s = 0.0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += kRedThreads) s += __ldcg(&partials[m * kRedBlocks + b]);
+        total[m] = block_sum(s, red);
+    }
+    if (threadIdx.x == 0) {
+        const int buf = (int)((seq - 1) & 1);
+        for (int q = 0; q < P.world; ++q) {
+            PcgCtrl* c = (PcgCtrl*)P.base[q];
+#pragma unroll
+            for (int m = 0; m < M; ++m) *(volatile double*)&c->ar_val[buf][P.rank][m] = total[m];
+        }
+        fence_sys();
+        for (int q = 0; q < P.world; ++q) st_release_sys(&((PcgCtrl*)P.base[q])->ar_flag[P.rank], seq);
+        own->ticket[ticket_id] = 0;
+    }
+    return true;
+}
+
+struct SpmvArgs {  // host-side bundle only; the kernels take plain __restrict__ pointers (alias analysis, load batching)
+    long long n;  // rows (CSR) or nodes (node blocks)
+    const void* indptr;
+    const void* indices;
+    const double* data;
+    const unsigned char* mask;
+    double* Ap;
+    double* partials;
+};
+
+// (1) Ap = A p_it with the p.Ap partials; waits for the neighbours' halo entries of p_it first
+template <int KIND, int A, int B>  // KIND 0: CSR, A = index bytes, B = lanes per row; KIND 1: node blocks, A = dof_n, B = lanes per node
+__global__ void __launch_bounds__(kRedThreads)
+    k_pcg_spmv(long long n, const void* __restrict__ indptr, const void* __restrict__ indices, const double* __restrict__ data,
+               const double* __restrict__ p, const unsigned char* __restrict__ mask, double* __restrict__ Ap,
+               double* __restrict__ partials, efb_pcg_peer P, unsigned long long ar_done, unsigned long long halo_done) {
+    // ar_done / halo_done: reductions / halo pushes published before this iteration (P.ar_seq + 2 k, P.halo_seq + k)
+    __shared__ double red[kRedThreads];
+    PcgCtrl* own = (PcgCtrl*)P.base[P.rank];
+    if (P.n_recv > 0) {
+        if (threadIdx.x == 0)
+            for (int i = 0; i < P.n_recv; ++i) spin_until(&own->halo_flag[P.recv_rank[i]], halo_done, own);
+        __syncthreads();
+    }
+    double local;
+    if constexpr (KIND == 0) {
+        if constexpr (A == 4)
+            local = spmv_rows<int, B>(n, (const int*)indptr, (const int*)indices, data, p, 0, mask, Ap, true);
+        else
+            local = spmv_rows<long long, B>(n, (const long long*)indptr, (const long long*)indices, data, p, 0, mask, Ap, true);
+    } else {
+        local = spmv_nodes<A, B>(n, (const long long*)indptr, (const int*)indices, data, p, 0, mask, Ap, true);
+    }
+    double mine[1] = {block_sum(local, red)}, total[1];
+    publish_reduction<1>(P, own, partials, mine, 0, ar_done + 1ull, red, total);
+}
+
+// (2) alpha = r.z / p.Ap ; x += alpha p ; r -= alpha Ap ; z = M^-1 r ; publishes (r.z, r.r)
+__global__ void __launch_bounds__(kRedThreads)
+    k_pcg_update_xr(long long n, const double* __restrict__ p, double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
+                    const double* __restrict__ Ap, const double* __restrict__ inv_diag, const unsigned char* __restrict__ mask,
+                    double* __restrict__ partials, efb_pcg_peer P, long long it, unsigned long long ar_done) {
+    __shared__ double red[kRedThreads];
+    PcgCtrl* own = (PcgCtrl*)P.base[P.rank];
+    double pAp[1];
+    gather_reduction<1>(P, own, ar_done + 1ull, pAp, red);
+    const double alpha = own->rz[it & 1] / pAp[0];
+    double s_rz = 0.0, s_rr = 0.0;
+    for (long long i = (long long)blockIdx.x * kRedThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kRedThreads) {
+        if (mask && !mask[i]) continue;
+        x[i] += alpha * p[i];
+        const double ri = r[i] - alpha * Ap[i];
+        r[i] = ri;
+        const double zi = ri * inv_diag[i];
+        z[i] = zi;
+        s_rz += ri * zi;
+        s_rr += ri * ri;
+    }
+    double mine[2], total[2];
+    mine[0] = block_sum(s_rz, red);
+    mine[1] = block_sum(s_rr, red);
+    publish_reduction<2>(P, own, partials, mine, 1, ar_done + 2ull, red, total);
+}
+
+// (3) beta = (r.z)_new / (r.z)_old ; p_{it+1} = z + beta p_it into the other p buffer, interface entries also into the
+// neighbours' halo segments; the last CTA records the scalars and raises the neighbours' halo flags
+__global__ void __launch_bounds__(kRedThreads)
+    k_pcg_update_p(long long n, const double* __restrict__ z, const unsigned char* __restrict__ mask, const double* __restrict__ p,
+                   double* __restrict__ pn, efb_pcg_peer P, long long it, unsigned long long ar_done, unsigned long long halo_done) {
+    __shared__ double red[kRedThreads];
+    __shared__ bool is_last;
+    PcgCtrl* own = (PcgCtrl*)P.base[P.rank];
+    double t[2];
+    gather_reduction<2>(P, own, ar_done + 2ull, t, red);
+    const double beta = t[0] / own->rz[it & 1];
+    const int nxt = (int)(it & 1) ^ 1;
+    const long long stride = (long long)gridDim.x * kRedThreads, first = (long long)blockIdx.x * kRedThreads + threadIdx.x;
+    // interface entries first: the neighbours wait for them
+    for (int s = 0; s < P.n_send; ++s) {
+        const int q = P.send_rank[s];
+        double* dst = (double*)((char*)P.base[q] + P.pbuf_off[q][nxt]) + P.send_dst[s];
+        const long long j0 = P.send_ptr[s], cnt = P.send_ptr[s + 1] - j0;
+        for (long long j = first; j < cnt; j += stride) {
+            const int i = P.send_idx[j0 + j];
+            dst[j] = (mask && !mask[i]) ? 0.0 : z[i] + beta * p[i];
+        }
+    }
+    for (long long i = first; i < n; i += stride) pn[i] = (mask && !mask[i]) ? 0.0 : z[i] + beta * p[i];
+    if (threadIdx.x == 0) {
+        if (P.n_send > 0) fence_sys();
+        else __threadfence();
+        is_last = atomicAdd(&own->ticket[2], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        own->rz[nxt] = t[0];
+        own->rr = t[1];
+        if (P.n_send > 0) {
+            fence_sys();
+            for (int s = 0; s < P.n_send; ++s)
+                st_release_sys(&((PcgCtrl*)P.base[P.send_rank[s]])->halo_flag[P.rank], halo_done + 1ull);
+        }
+        own->ticket[2] = 0;
+    }
+}
+
+using SpmvKernel = void (*)(long long, const void*, const void*, const double*, const double*, const unsigned char*, double*, double*,
+                            efb_pcg_peer, unsigned long long, unsigned long long);
+
+template <int KIND, int A>
+static SpmvKernel pcg_spmv_kernel(int lanes) {
+    switch (lanes) {
+        case 4: return k_pcg_spmv<KIND, A, 4>;
+        case 8: return k_pcg_spmv<KIND, A, 8>;
+        case 16: return k_pcg_spmv<KIND, A, 16>;
+        default: return k_pcg_spmv<KIND, A, 32>;
+    }
+}
+
+// one wave: every CTA of the three kernels is resident at once (grid-stride bodies, no tail wave), capped by the partials layout
+template <class K>
+static int resident_blocks_per_sm(K kernel) {
+    int b = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, kRedThreads, 0) != cudaSuccess || b < 1) b = 1;
+    return b;
+}
+
 }  // namespace efb
 
 using namespace efb;
@@ -328,6 +599,115 @@ extern "C" int efb_pcg_update_p(int64_t n, const double* rz_new, const double* r
                                 double* p, void* stream) {
     k_update_p<<<kRedBlocks, 256, 0, as_stream(stream)>>>(n, rz_new, rz_old, z, free_mask, p);
     return check_launch("efb_pcg_update_p");
+}
+
+extern "C" int efb_pcg_ctrl_bytes(void) { return kCtrlBytes; }
+
+extern "C" int efb_pcg_ctrl_layout(int32_t* out3) {
+    out3[0] = (int32_t)(offsetof(PcgCtrl, rz) / 8);
+    out3[1] = (int32_t)(offsetof(PcgCtrl, rr) / 8);
+    out3[2] = (int32_t)(offsetof(PcgCtrl, error) / 4);
+    return 0;
+}
+
+extern "C" int efb_pcg_iterate(const efb_pcg_system* sys, const efb_pcg_peer* peer, int n_iters, int64_t it0, void* stream) {
+    const efb_pcg_peer& P = *peer;
+    if (P.world < 1 || P.world > EFB_MAX_RANKS || P.rank < 0 || P.rank >= P.world || P.n_send < 0 || P.n_send > EFB_MAX_RANKS ||
+        P.n_recv < 0 || P.n_recv > EFB_MAX_RANKS) {
+        set_error("efb_pcg_iterate: bad communicator (world %d, rank %d, %d send / %d recv neighbours)", P.world, P.rank, P.n_send, P.n_recv);
+        return 1;
+    }
+    if (sys->nrows == 0 && P.world == 1) return 0;
+    cudaStream_t st = as_stream(stream);
+    SpmvArgs a{0, sys->indptr, sys->indices, sys->data, sys->free_mask, sys->Ap, sys->partials};
+    if (sys->kind == 1) {
+        if (sys->dof_n < 1 || sys->dof_n > 3 || sys->nrows % sys->dof_n) {
+            set_error("efb_pcg_iterate: node-block systems need dof_n in 1..3 dividing nrows (dof_n %d, nrows %lld)", sys->dof_n, (long long)sys->nrows);
+            return 1;
+        }
+        a.n = sys->nrows / sys->dof_n;
+    } else if (sys->kind == 0) {
+        if (sys->index_bytes != 4 && sys->index_bytes != 8) {
+            set_error("efb_pcg_iterate: index_bytes must be 4 or 8");
+            return 1;
+        }
+        a.n = sys->nrows;
+    } else {
+        set_error("efb_pcg_iterate: kind must be 0 (CSR) or 1 (node blocks)");
+        return 1;
+    }
+    SpmvKernel spmv_k;
+    if (sys->kind == 1)
+        spmv_k = sys->dof_n == 1 ? pcg_spmv_kernel<1, 1>(sys->lanes) : sys->dof_n == 2 ? pcg_spmv_kernel<1, 2>(sys->lanes) : pcg_spmv_kernel<1, 3>(sys->lanes);
+    else
+        spmv_k = sys->index_bytes == 4 ? pcg_spmv_kernel<0, 4>(sys->lanes) : pcg_spmv_kernel<0, 8>(sys->lanes);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int g_spmv = min(kRedBlocks, sms * resident_blocks_per_sm(spmv_k));
+    const int g_xr = min(kRedBlocks, sms * resident_blocks_per_sm(k_pcg_update_xr));
+    const int g_p = min(kRedBlocks, sms * resident_blocks_per_sm(k_pcg_update_p));
+    for (int k = 0; k < n_iters; ++k) {
+        const long long it = it0 + k;
+        const double* p = (const double*)((const char*)P.base[P.rank] + P.pbuf_off[P.rank][it & 1]);
+        double* pn = (double*)((char*)P.base[P.rank] + P.pbuf_off[P.rank][(it & 1) ^ 1]);
+        const unsigned long long ar_done = P.ar_seq + 2ull * (unsigned long long)k, halo_done = P.halo_seq + (unsigned long long)k;
+        spmv_k<<<g_spmv, kRedThreads, 0, st>>>(a.n, a.indptr, a.indices, a.data, p, a.mask, a.Ap, a.partials, P, ar_done, halo_done);
+        k_pcg_update_xr<<<g_xr, kRedThreads, 0, st>>>(sys->nrows, p, sys->x, sys->r, sys->z, sys->Ap, sys->inv_diag, sys->free_mask,
+                                                       sys->partials, P, it, ar_done);
+        k_pcg_update_p<<<g_p, kRedThreads, 0, st>>>(sys->nrows, sys->z, sys->free_mask, p, pn, P, it, ar_done, halo_done);
+    }
+    return check_launch("efb_pcg_iterate");
+}
+
+extern "C" int efb_peer_alloc(int64_t bytes, void** ptr) {
+    cudaError_t err = cudaMalloc(ptr, (size_t)bytes);
+    if (err == cudaSuccess) err = cudaMemset(*ptr, 0, (size_t)bytes);
+    if (err == cudaSuccess) err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) {
+        set_error("efb_peer_alloc(%lld): %s", (long long)bytes, cudaGetErrorString(err));
+        return 1;
+    }
+    return 0;
+}
+
+extern "C" int efb_peer_free(void* ptr) {
+    cudaError_t err = cudaFree(ptr);
+    if (err != cudaSuccess) {
+        set_error("efb_peer_free: %s", cudaGetErrorString(err));
+        return 1;
+    }
+    return 0;
+}
+
+extern "C" int efb_peer_export(void* ptr, void* handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t");
+    cudaError_t err = cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64, ptr);
+    if (err != cudaSuccess) {
+        set_error("cudaIpcGetMemHandle: %s", cudaGetErrorString(err));
+        return 1;
+    }
+    return 0;
+}
+
+extern "C" int efb_peer_open(const void* handle64, void** ptr) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    cudaError_t err = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (err != cudaSuccess) {
+        set_error("cudaIpcOpenMemHandle: %s (GPUs without peer access?)", cudaGetErrorString(err));
+        return 1;
+    }
+    return 0;
+}
+
+extern "C" int efb_peer_close(void* ptr) {
+    cudaError_t err = cudaIpcCloseMemHandle(ptr);
+    if (err != cudaSuccess) {
+        set_error("cudaIpcCloseMemHandle: %s", cudaGetErrorString(err));
+        return 1;
+    }
+    return 0;
 }
 
 extern "C" int efb_pack_f64(int64_t n, const int32_t* idx, const double* src, double* dst, void* stream) {

@@ -48,3 +48,16 @@ def to_host(t: torch.Tensor) -> np.ndarray:
 def ptr_array(tensors) -> ctypes.Array:
     """host array of device pointers (`const T* const*` arguments)"""
     return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+class _RawCuda:
+    """`__cuda_array_interface__` carrier for device memory that torch did not allocate (peer regions)"""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
+def view_f64(ptr: int, n: int) -> torch.Tensor:
+    """zero-copy float64 tensor over `n` doubles of raw device memory at `ptr` (the caller keeps the memory alive)"""
+    return torch.as_tensor(_RawCuda(ptr, n, "<f8"), device=device())

@@ -197,6 +197,14 @@ class RowComm:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
 
+    # -- peer-memory PCG workspace (efb_pcg_iterate) -------------------------------------------------------------
+    def pcg_workspace(self):
+        """Control block + the two search-direction buffers of this rank inside a cudaIpc-shared region, mapped on every
+        rank of the group, and the push plan of the halo exchange (built once per communicator, collective)."""
+        if getattr(self, "_ws", None) is None:
+            self._ws = PeerWorkspace(self)
+        return self._ws
+
     def all_reduce_sum(self, t: torch.Tensor) -> None:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
 
@@ -239,3 +247,123 @@ class ShardedGroup:
         pat = self.assembler.pattern(d, False, part.n_local * d, (self.group,))
         pat.replay([Fe])
         return pat.last_dense[:part.n_owned * d]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# peer-memory workspace of the fused PCG iterations
+# ---------------------------------------------------------------------------------------------------------
+def _pad256(nbytes: int) -> int:
+    return (int(nbytes) + 255) // 256 * 256
+
+
+class LocalWorkspace:
+    """Single-GPU workspace of `efb_pcg_iterate`: control block + two p buffers in ordinary device memory."""
+
+    def __init__(self, n: int):
+        import ctypes
+
+        lib = _lib.load()
+        self.n = int(n)
+        ctrl = lib.efb_pcg_ctrl_bytes()
+        lay = (ctypes.c_int32 * 3)()
+        lib.efb_pcg_ctrl_layout(lay)
+        self.rz_off, self.rr_off, self.err_off = int(lay[0]), int(lay[1]), int(lay[2])
+        self.ctrl_bytes = ctrl
+        self.pbuf_off = (ctrl, ctrl + _pad256(self.n * 8))
+        self.nbytes = ctrl + 2 * _pad256(self.n * 8)
+        self._alloc()
+        self.p = [self.f64[o // 8: o // 8 + self.n] for o in self.pbuf_off]
+        self.ctrl = self.f64[: ctrl // 8]
+        self.peer = _lib.EfbPcgPeer()
+        self._fill_peer()
+
+    def _alloc(self):
+        self.f64 = torch.zeros(self.nbytes // 8, dtype=torch.float64, device=dv.device())
+        self.base = self.f64.data_ptr()
+
+    def _fill_peer(self):
+        P = self.peer
+        P.world, P.rank, P.n_send, P.n_recv = 1, 0, 0, 0
+        P.base[0] = self.base
+        P.pbuf_off[0][0], P.pbuf_off[0][1] = self.pbuf_off
+        P.send_idx = None
+        P.ar_seq, P.halo_seq = 0, 0
+
+    def status(self):
+        """(r.r of the last finished iteration, error flag) — one small device-to-host copy"""
+        c = self.ctrl.cpu().numpy()
+        return float(c[self.rr_off]), int(c.view(np.uint32)[self.err_off])
+
+    def advance(self, n_iters: int):
+        self.peer.ar_seq += 2 * n_iters
+        self.peer.halo_seq += n_iters
+
+
+class PeerWorkspace(LocalWorkspace):
+    """Row-sharded workspace: the region is plain cudaMalloc memory exported with cudaIpc, every rank maps every other
+    rank's region, and the iteration kernels store reductions / interface entries straight into the neighbours' regions
+    (NVLink).  Construction is collective over the communicator's group."""
+
+    def __init__(self, comm: RowComm):
+        self.comm = comm
+        super().__init__(comm.part.n_local * comm.d)
+
+    def _alloc(self):
+        import ctypes
+
+        p = ctypes.c_void_p()
+        _lib.call("efb_peer_alloc", self.nbytes, ctypes.byref(p))
+        self.base = int(p.value)
+        self.f64 = dv.view_f64(self.base, self.nbytes // 8)
+
+    def _fill_peer(self):
+        import ctypes
+
+        comm, part, d = self.comm, self.comm.part, self.comm.d
+        dist = comm.dist
+        world, rank = part.world, part.rank
+        if world > _lib.MAX_RANKS:
+            raise _lib.EfbError(f"peer-memory PCG supports up to {_lib.MAX_RANKS} ranks of one box, got {world}")
+        handle = (ctypes.c_char * 64)()
+        _lib.call("efb_peer_export", ctypes.c_void_p(self.base), handle)
+        recv_lo = {int(q): int(lo) for q, lo, _ in comm.recv_segments}  # first entry of the segment received from q
+        mine = (bytes(handle.raw), self.pbuf_off, recv_lo)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine, group=comm.group)
+        P = self.peer
+        P.world, P.rank = world, rank
+        self._opened = []
+        for q, (h, off, _) in enumerate(gathered):
+            if q == rank:
+                P.base[q] = self.base
+            else:
+                ptr = ctypes.c_void_p()
+                hb = (ctypes.c_char * 64).from_buffer_copy(h)
+                _lib.call("efb_peer_open", hb, ctypes.byref(ptr))
+                self._opened.append(int(ptr.value))
+                P.base[q] = int(ptr.value)
+            P.pbuf_off[q][0], P.pbuf_off[q][1] = int(off[0]), int(off[1])
+        P.n_send = len(comm.peers_send)
+        for i, q in enumerate(comm.peers_send):
+            P.send_rank[i] = int(q)
+            P.send_ptr[i] = int(comm.send_ptr[i])
+            their = gathered[q][2]
+            assert rank in their, "a neighbour this rank sends to does not expect a segment from it"
+            P.send_dst[i] = int(their[rank])
+        P.send_ptr[P.n_send] = int(comm.send_ptr[-1])
+        P.n_recv = len(comm.recv_segments)
+        for i, (q, _, _) in enumerate(comm.recv_segments):
+            P.recv_rank[i] = int(q)
+        P.send_idx = comm.send_idx.data_ptr() if comm.send_idx.numel() else None
+        P.ar_seq, P.halo_seq = 0, 0
+        dist.barrier(group=comm.group)  # every region is mapped before anybody stores into it
+
+    def close(self):
+        import ctypes
+
+        for ptr in getattr(self, "_opened", []):
+            _lib.call("efb_peer_close", ctypes.c_void_p(ptr))
+        self._opened = []
+        if getattr(self, "base", None):
+            _lib.call("efb_peer_free", ctypes.c_void_p(self.base))
+            self.base = None

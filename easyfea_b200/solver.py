@@ -3,8 +3,9 @@
 `A[dofsUnknown,:][:,dofsUnknown]` on the host (:526-530); here Dirichlet dofs are masked instead (projected CG), all
 scalars stay on the device and every dot product is a fixed-order reduction, so a solve is reproducible run to run.
 
-Multi-GPU: rows are sharded in contiguous blocks; `p` is kept at global length on every rank and only its interface
-entries are exchanged per iteration (see `easyfea_b200.dist`).
+Multi-GPU: rows are sharded in contiguous blocks; `p` is kept over `[owned | halo]` on every rank and only its interface
+entries are exchanged per iteration — by stores into the neighbours' peer-mapped buffers from inside the iteration
+kernels (`efb_pcg_iterate`, `easyfea_b200.dist.PeerWorkspace`), not by collective calls.
 """
 from __future__ import annotations
 
@@ -41,13 +42,36 @@ def spmv(A: DeviceCsr, x: torch.Tensor, y: torch.Tensor = None, row_offset: int 
     return y
 
 
-def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: int = None, check_every: int = 25,
-        row_offset: int = 0, comm=None):
+def _system_struct(A: DeviceCsr, nrows, mask, inv_diag, x, r, z, Ap, partials) -> _lib.EfbPcgSystem:
+    S = _lib.EfbPcgSystem()
+    S.nrows = nrows
+    ng = getattr(A, "node_graph", None)
+    if ng is not None and ng[2] in (1, 2, 3) and nrows % ng[2] == 0:
+        adjptr, adj, d = ng
+        S.kind, S.dof_n, S.index_bytes = 1, d, 0
+        S.indptr, S.indices = adjptr.data_ptr(), adj.data_ptr()
+    else:
+        S.kind, S.dof_n, S.index_bytes = 0, 0, A.index_bytes
+        S.indptr, S.indices = A.indptr.data_ptr(), A.indices.data_ptr()
+    S.lanes = lanes_per_row(A.nnz, nrows)
+    S.data = A.data.data_ptr()
+    S.free_mask = mask.data_ptr() if mask is not None else None
+    S.inv_diag, S.x, S.r, S.z, S.Ap, S.partials = (t.data_ptr() for t in (inv_diag, x, r, z, Ap, partials))
+    return S
+
+
+def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: int = None, check_every: int = 25, comm=None,
+        fused: bool = True):
     """Solve A x = b on the free dofs (free_mask True / 1 = unknown; other entries of x keep the values of x0).
 
-    A holds the local row block [row_offset, row_offset + nrows) with GLOBAL column indices.  Stops when
-    ||r|| <= tol * ||b - A x_known|| (both restricted to free dofs).  Returns (x_local, info dict).
-    `comm` (easyfea_b200.dist.RowComm) supplies the halo exchange and scalar all-reduces for row-sharded runs.
+    A holds the owned rows in LOCAL numbering `[owned | halo]` columns.  Stops when ||r|| <= tol * ||b - A x_known||
+    (both restricted to free dofs).  Returns (x_owned, info dict).  `comm` (easyfea_b200.dist.RowComm) supplies the halo
+    exchange and scalar all-reduces for row-sharded runs.
+
+    `fused=True` (default): the iterations run as three kernels each, enqueued `check_every` at a time by
+    `efb_pcg_iterate`; reductions and the halo exchange go through peer memory inside those kernels.  `fused=False` keeps
+    one collective call per exchange (NCCL through torch.distributed) and one kernel per vector operation — the baseline
+    the fused path is measured against (bench.py) and checked against (tests).
     """
     dev = A.data.device
     nrows = A.indptr.numel() - 1
@@ -65,18 +89,26 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
     scal = torch.zeros(6, dtype=torch.float64, device=dev)  # [rz, pAp, rz_new, rr, -, -]
     s_ptr = lambda i: ctypes.c_void_p(scal.data_ptr() + 8 * i)  # noqa: E731
 
-    # vectors: p at global length (halo entries live outside the owned block), the rest local
+    # vectors: p over [owned | halo] (the halo entries belong to other ranks), the rest owned only
+    ws = None
+    if fused:
+        if comm is not None:
+            ws = comm.pcg_workspace()
+            assert ws.n == n_glob, "the communicator was planned for another vector length"
+        else:
+            from .dist import LocalWorkspace
+
+            ws = LocalWorkspace(n_glob)
     x_full = torch.zeros(n_glob, dtype=torch.float64, device=dev)
-    x = x_full[row_offset:row_offset + nrows]
+    x = x_full[:nrows]
     if x0 is not None:
         x.copy_(dv.to_device(x0).reshape(-1)[:nrows])  # a local [owned | halo] vector may be passed: the owned part counts
-    p_full = torch.zeros(n_glob, dtype=torch.float64, device=dev)
-    p = p_full[row_offset:row_offset + nrows]
+    p_full = ws.p[0] if ws is not None else torch.zeros(n_glob, dtype=torch.float64, device=dev)
+    p = p_full[:nrows]
     r, z, Ap = dv.empty((nrows,)), dv.empty((nrows,)), dv.empty((nrows,))
 
     diag = dv.empty((nrows,))
-    _lib.call("efb_csr_diagonal", nrows, int(row_offset), A.index_bytes, dv.ptr(A.indptr), dv.ptr(A.indices), dv.ptr(A.data),
-              dv.ptr(diag), st())
+    _lib.call("efb_csr_diagonal", nrows, 0, A.index_bytes, dv.ptr(A.indptr), dv.ptr(A.indices), dv.ptr(A.data), dv.ptr(diag), st())
     inv_diag = dv.empty((nrows,))
     _lib.call("efb_pcg_inv_diag", nrows, dv.ptr(diag), dv.ptr(mask), dv.ptr(inv_diag), st())
 
@@ -88,10 +120,10 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
     # reference norm: || b - A x_known || on the free dofs (x_known = x0 on constrained dofs, 0 elsewhere)
     if mask is not None:
         xk = torch.zeros_like(x_full)
-        xk[row_offset:row_offset + nrows] = x * (1 - mask.to(torch.float64))
+        xk[:nrows] = x * (1 - mask.to(torch.float64))
         if comm is not None:
             comm.halo_exchange(xk)
-        spmv(A, xk, Ap, row_offset)
+        spmv(A, xk, Ap)
         _lib.call("efb_pcg_init", nrows, dv.ptr(b), dv.ptr(Ap), dv.ptr(inv_diag), dv.ptr(mask), dv.ptr(r), dv.ptr(z), dv.ptr(p),
                   dv.ptr(partials), st())
         reduce_to(2, 2)
@@ -106,7 +138,7 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
     # initial residual with the actual start vector
     if comm is not None:
         comm.halo_exchange(x_full)
-    spmv(A, x_full, Ap, row_offset)
+    spmv(A, x_full, Ap)
     _lib.call("efb_pcg_init", nrows, dv.ptr(b), dv.ptr(Ap), dv.ptr(inv_diag), dv.ptr(mask), dv.ptr(r), dv.ptr(z), dv.ptr(p),
               dv.ptr(partials), st())
     reduce_to(2, 2)  # scal[2] = r.z, scal[3] = r.r
@@ -114,20 +146,40 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
     it = 0
     rr = float(scal[3].item())
     target = tol * tol * bnorm2
-    while rr > target and it < maxiter:
-        for _ in range(check_every):
-            if comm is not None:
-                comm.halo_exchange(p_full)
-            spmv(A, p_full, Ap, row_offset, mask, partials)
-            reduce_to(1, 1)  # pAp
-            _lib.call("efb_pcg_update_xr", nrows, s_ptr(0), s_ptr(1), dv.ptr(p), dv.ptr(Ap), dv.ptr(x), dv.ptr(r), dv.ptr(inv_diag),
-                      dv.ptr(mask), dv.ptr(z), dv.ptr(partials), st())
-            reduce_to(2, 2)  # rz_new, rr
-            _lib.call("efb_pcg_update_p", nrows, s_ptr(2), s_ptr(0), dv.ptr(z), dv.ptr(mask), dv.ptr(p), st())
-            scal[0:1].copy_(scal[2:3])
-            it += 1
-        rr = float(scal[3].item())
-        if rr != rr:
-            raise _lib.EfbError("PCG broke down (NaN residual): matrix not SPD on the free dofs?")
+    if ws is not None:
+        # p_0 complete on [owned | halo] in buffer 0, r.z of iteration 0 in the control block; then only kernels
+        if comm is not None:
+            comm.halo_exchange(p_full)
+        ws.ctrl[ws.rz_off:ws.rz_off + 1].copy_(scal[2:3])
+        S = _system_struct(A, nrows, mask, inv_diag, x, r, z, Ap, partials)
+        while rr > target and it < maxiter:
+            k = min(int(check_every), maxiter - it)
+            _lib.call("efb_pcg_iterate", ctypes.byref(S), ctypes.byref(ws.peer), k, it, st())
+            ws.advance(k)
+            it += k
+            rr, err = ws.status()
+            if err:
+                flags = ws.ctrl[:16].cpu().numpy().view("uint64").tolist()
+                raise _lib.EfbError(f"PCG: a wait on a neighbour rank timed out (peer process lost?) at iteration <= {it}: reduction "
+                                    f"flags {flags[:8]}, halo flags {flags[8:]}, expected sequence numbers {ws.peer.ar_seq} / "
+                                    f"{ws.peer.halo_seq}")
+            if rr != rr:
+                raise _lib.EfbError("PCG broke down (NaN residual): matrix not SPD on the free dofs?")
+    else:
+        while rr > target and it < maxiter:
+            for _ in range(min(int(check_every), maxiter - it)):
+                if comm is not None:
+                    comm.halo_exchange(p_full)
+                spmv(A, p_full, Ap, 0, mask, partials)
+                reduce_to(1, 1)  # pAp
+                _lib.call("efb_pcg_update_xr", nrows, s_ptr(0), s_ptr(1), dv.ptr(p), dv.ptr(Ap), dv.ptr(x), dv.ptr(r), dv.ptr(inv_diag),
+                          dv.ptr(mask), dv.ptr(z), dv.ptr(partials), st())
+                reduce_to(2, 2)  # rz_new, rr
+                _lib.call("efb_pcg_update_p", nrows, s_ptr(2), s_ptr(0), dv.ptr(z), dv.ptr(mask), dv.ptr(p), st())
+                scal[0:1].copy_(scal[2:3])
+                it += 1
+            rr = float(scal[3].item())
+            if rr != rr:
+                raise _lib.EfbError("PCG broke down (NaN residual): matrix not SPD on the free dofs?")
     rel = (rr / bnorm2) ** 0.5
-    return x.clone(), {"iterations": it, "rel_residual": rel, "converged": rel <= tol}
+    return x.clone(), {"iterations": it, "rel_residual": rel, "converged": rel <= tol, "fused": ws is not None}

@@ -101,6 +101,7 @@ class ElasticSolve:
         self.dim = int(system.group.dim)
         self.bc = Dirichlet(system.n_local * self.dim)
         self.u = torch.zeros(system.n_local * self.dim, dtype=torch.float64, device=dv.device())
+        self.pcg_fused = True  # False: one NCCL call per exchange (the baseline of solver.pcg)
 
     def assemble(self) -> DeviceCsr:
         scale = self.thickness if self.dim == 2 else 1.0
@@ -115,7 +116,7 @@ class ElasticSolve:
         _apply(self.u, dofs, vals)
         self.sys.refresh_halo(self.u, d)
         rhs = torch.zeros(nown, dtype=torch.float64, device=self.u.device) if b is None else dv.to_device(b)
-        x, info = pcg(K, rhs, x0=self.u, free_mask=mask, tol=tol, maxiter=maxiter, comm=self.sys.comm(d))
+        x, info = pcg(K, rhs, x0=self.u, free_mask=mask, tol=tol, maxiter=maxiter, comm=self.sys.comm(d), fused=self.pcg_fused)
         self.u[:nown] = x
         self.sys.refresh_halo(self.u, d)
         return self.u, info
@@ -136,6 +137,7 @@ class PhaseFieldStaggered:
         self.bc_u = Dirichlet(system.n_local * self.dim)
         self.bc_d = Dirichlet(system.n_local)
         self.pcg_tol, self.pcg_maxiter = pcg_tol, pcg_maxiter
+        self.pcg_fused = True
         self.info = {}
 
     def Bc_Init(self):
@@ -158,7 +160,8 @@ class PhaseFieldStaggered:
         mask, dofs, vals = self.bc_d.device_arrays(s.n_owned)
         _apply(self.d, dofs, vals)
         s.refresh_halo(self.d, 1)
-        x, info = pcg(K, F, x0=self.d, free_mask=mask, tol=self.pcg_tol, maxiter=self.pcg_maxiter, comm=s.comm(1))
+        x, info = pcg(K, F, x0=self.d, free_mask=mask, tol=self.pcg_tol, maxiter=self.pcg_maxiter, comm=s.comm(1),
+                      fused=self.pcg_fused)
         self.d[: s.n_owned] = x
         s.refresh_halo(self.d, 1)
         self.info["damage"] = info
@@ -174,7 +177,8 @@ class PhaseFieldStaggered:
         _apply(self.u, dofs, vals)
         s.refresh_halo(self.u, dim)
         rhs = torch.zeros(nown, dtype=torch.float64, device=self.u.device)
-        x, info = pcg(K, rhs, x0=self.u, free_mask=mask, tol=self.pcg_tol, maxiter=self.pcg_maxiter, comm=s.comm(dim))
+        x, info = pcg(K, rhs, x0=self.u, free_mask=mask, tol=self.pcg_tol, maxiter=self.pcg_maxiter, comm=s.comm(dim),
+                      fused=self.pcg_fused)
         self.u[:nown] = x
         s.refresh_halo(self.u, dim)
         self.info["elastic"] = info

@@ -195,6 +195,63 @@ int efb_pcg_update_xr(int64_t n, const double* rz, const double* pAp, const doub
 int efb_pcg_update_p(int64_t n, const double* rz_new, const double* rz_old, const double* z, const uint8_t* free_mask,
                      double* p, void* stream);
 
+/* ---- fused Jacobi-PCG iterations with peer-memory communication ----------------------
+ * Three kernels per iteration and no host round trip:  (1) Ap = A p with the p.Ap partials, (2) x, r, z update with the
+ * (r.z, r.r) partials, (3) p' = z + beta p written to the OTHER p buffer.  The last CTA of a kernel folds the per-CTA
+ * partials in fixed order and STORES the result into the control block of every rank (peer memory over NVLink);
+ * the next kernel's CTAs wait for the `world` contributions and add them in rank order, so every rank obtains the same
+ * bits without a collective call.  Kernel (3) also stores the interface entries of p' straight into the halo segments
+ * of the neighbours' p buffers and raises their halo flags; kernel (1) waits for its neighbours' flags.
+ * Replaces, for row-sharded runs, the per-iteration NCCL send/recv + 2 all-reduces (the reference: PETSc KSP over
+ * mpi4py, Simulations/Solvers.py:732-847).  world == 1 runs the same kernels on local memory. */
+#define EFB_MAX_RANKS 8
+typedef struct efb_pcg_system {
+    int64_t nrows;            /* owned dof rows */
+    int32_t kind;             /* 0: CSR (indptr/indices, index_bytes), 1: node blocks (adjptr/adj, dof_n) */
+    int32_t index_bytes;      /* 4 or 8 (kind 0) */
+    int32_t dof_n;            /* 1..3 (kind 1) */
+    int32_t lanes;            /* lanes per row / node: 4, 8, 16 or 32 */
+    const void* indptr;       /* kind 0: (nrows+1); kind 1: adjptr (n_nodes+1) int64 */
+    const void* indices;      /* kind 0: (nnz);     kind 1: adj int32 */
+    const double* data;
+    const uint8_t* free_mask; /* (nrows) or NULL */
+    const double* inv_diag;   /* (nrows), 0 on constrained rows */
+    double* x;                /* (nrows) */
+    double* r;
+    double* z;
+    double* Ap;
+    double* partials;         /* efb_pcg_partials_size() doubles */
+} efb_pcg_system;
+
+typedef struct efb_pcg_peer {
+    int32_t world, rank;
+    int32_t n_send, n_recv;                   /* neighbour counts of the halo exchange */
+    int32_t send_rank[EFB_MAX_RANKS];
+    int32_t recv_rank[EFB_MAX_RANKS];
+    int64_t send_ptr[EFB_MAX_RANKS + 1];      /* send_idx[send_ptr[i] : send_ptr[i+1]] goes to send_rank[i] */
+    int64_t send_dst[EFB_MAX_RANKS];          /* first entry of this rank's segment inside that neighbour's p buffers */
+    void* base[EFB_MAX_RANKS];                /* region of every rank as mapped HERE (own region at [rank]) */
+    int64_t pbuf_off[EFB_MAX_RANKS][2];       /* byte offsets of the two p buffers inside each region */
+    const int32_t* send_idx;                  /* owned local dof ids to push, concatenated per neighbour */
+    uint64_t ar_seq;                          /* reductions already published on this communicator */
+    uint64_t halo_seq;                        /* halo pushes already published */
+} efb_pcg_peer;
+
+/* a region starts with a control block of efb_pcg_ctrl_bytes() bytes (zero it once); offsets of the device scalars
+ * inside it (in doubles): out[0] = rz[2] ping-pong, out[1] = rr, out[2] = error flag (as uint32 index) */
+int efb_pcg_ctrl_bytes(void);
+int efb_pcg_ctrl_layout(int32_t* out3);
+/* enqueue n_iters iterations starting at iteration `it0` (p_it lives in p buffer it & 1, r.z of it in rz[it & 1]).
+ * The caller advances peer->ar_seq by 2*n_iters and halo_seq by n_iters afterwards. */
+int efb_pcg_iterate(const efb_pcg_system* sys, const efb_pcg_peer* peer, int n_iters, int64_t it0, void* stream);
+
+/* peer-mappable device memory (plain cudaMalloc so that cudaIpc can export it) */
+int efb_peer_alloc(int64_t bytes, void** ptr);                 /* zero-filled */
+int efb_peer_free(void* ptr);
+int efb_peer_export(void* ptr, void* handle64 /* 64 bytes out */);
+int efb_peer_open(const void* handle64, void** ptr);           /* maps a region exported by another process */
+int efb_peer_close(void* ptr);
+
 /* send-buffer packing of the PCG halo exchange (row-sharded runs): dst[i] = src[idx[i]] */
 int efb_pack_f64(int64_t n, const int32_t* idx, const double* src, double* dst, void* stream);
 

@@ -39,10 +39,20 @@ def _worker(rank, world, port, out):
         loc = np.arange(part.n_local)
         es.bc.add(loc[plane == 0], [0, 0, 0], [0, 1, 2], 3)
         es.bc.add(loc[plane == world * n[2]], [0.05], [2], 3)
-        u, info = es.solve(tol=1e-10)
-        assert info["converged"], info
+        u, info = es.solve(tol=1e-10)  # fused iterations: reductions + halo pushes through peer memory
+        assert info["converged"] and info["fused"], info
+        u_peer = u[: part.n_owned * 3].cpu().numpy()
+        u2, info2 = es.solve(tol=1e-10)  # second solve on the same communicator (sequence numbers carry on), warm start
+        assert info2["converged"], info2
+        es.u.zero_()
+        es.pcg_fused = False  # NCCL send/recv + all-reduce per iteration: same iterates up to summation order
+        u3, info3 = es.solve(tol=1e-10)
+        assert info3["converged"] and not info3["fused"], info3
+        u_nccl = u3[: part.n_owned * 3].cpu().numpy()
+        assert abs(info3["iterations"] - info["iterations"]) <= 25, (info, info3)
+        assert np.linalg.norm(u_peer - u_nccl) <= 1e-8 * max(np.linalg.norm(u_nccl), 1e-300), "peer-memory PCG differs from the NCCL loop"
         own = part.nodes[: part.n_owned]
-        out.put((rank, "ok", own, u[: part.n_owned * 3].cpu().numpy(), info["iterations"]))
+        out.put((rank, "ok", own, u_peer, info["iterations"]))
     except Exception as exc:
         import traceback
 
@@ -70,8 +80,8 @@ def test_sharded_elastic_solve_matches_single_gpu():
     res = [out.get(timeout=600) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
-    for r in res:
-        assert r[1] == "ok", f"rank {r[0]}: {r[2]}"
+    bad = [f"rank {r[0]}: {r[2]}" for r in res if r[1] != "ok"]
+    assert not bad, "\n".join(bad)
     # single-GPU solve of the same global mesh (rank-independent jitter per plane -> same coordinates)
     connect, elem_ids, owner_of, coords_of = meshgen.hexa8_slab((n[0], n[1], world * n[2]), 0, 1, jitter=0.15, seed=2)
     Nn = (n[0] + 1) * (n[1] + 1) * (world * n[2] + 1)

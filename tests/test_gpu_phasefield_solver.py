@@ -147,6 +147,35 @@ def test_pcg_elastic_cube(efb):
     xd = spla.spsolve(Ks[free][:, free].tocsc(), rhs)
     assert np.linalg.norm(x[free] - xd) / np.linalg.norm(xd) < 1e-6
     assert np.array_equal(x[known], x0[known])
+    # the fused iterations (3 kernels each, reductions folded by the last CTA) follow the kernel-per-operation loop up to
+    # the summation order of the dot products (one-wave grids), and are reproducible run to run
+    assert info["fused"]
+    x2, info2 = efb.solver.pcg(K, b, x0=x0, free_mask=~known, tol=1e-8, maxiter=5000, fused=False)
+    assert not info2["fused"] and abs(info2["iterations"] - info["iterations"]) <= 25
+    assert np.linalg.norm(x2.cpu().numpy() - x) / np.linalg.norm(x) < 1e-5
+    x2b, info2b = efb.solver.pcg(K, b, x0=x0, free_mask=~known, tol=1e-8, maxiter=5000)
+    assert info2b["iterations"] == info["iterations"] and np.array_equal(x2b.cpu().numpy(), x)
+    # generic CSR form of the fused SpMV (no node graph) and a system without a mask
+    from easyfea_b200.assembly import DeviceCsr
+
+    Kc = DeviceCsr(K.indptr, K.indices, K.data, K.shape)
+    x3, info3 = efb.solver.pcg(Kc, b, x0=x0, free_mask=~known, tol=1e-8, maxiter=5000, check_every=7)
+    assert info3["converged"] and np.linalg.norm(x3.cpu().numpy() - x) / np.linalg.norm(x) < 1e-5  # both stop at 1e-8 residual
+    import scipy.sparse as sp
+
+    Kreg = (Ks + 1e3 * sp.identity(Ndof, format="csr")).tocsr()
+    Kreg.sort_indices()
+    Kr = DeviceCsr(dv_t(Kreg.indptr), dv_t(Kreg.indices), dv_t(Kreg.data), Kreg.shape)
+    rhs_full = np.random.default_rng(3).standard_normal(Ndof)
+    x4, info4 = efb.solver.pcg(Kr, rhs_full, tol=1e-10, maxiter=5000)
+    assert info4["converged"]
+    assert np.linalg.norm(Kreg @ x4.cpu().numpy() - rhs_full) / np.linalg.norm(rhs_full) <= 1e-9
+
+
+def dv_t(a):
+    from easyfea_b200 import device as dv
+
+    return dv.to_device(a)
 
 
 @pytest.mark.parametrize("elemType,dof_n", [("HEXA8", 3), ("TETRA4", 3), ("TRI3", 2), ("TRI3", 1), ("QUAD9", 2), ("HEXA27", 1)])
