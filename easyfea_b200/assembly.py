@@ -81,7 +81,7 @@ class NodeGraph:
 class DeviceCsr:
     """CSR matrix resident on the device (`indptr`, `indices`, `data` torch tensors).
 
-    `node_graph = (adjptr, adj, dof_n)` is set for matrices assembled here: the dof rows of a node are one contiguous
+    `node_graph = (adjptr, adj, dof_n, max_deg)` is set for matrices assembled here: the dof rows of a node are one contiguous
     block whose column structure is the node adjacency, which the solver's SpMV reads instead of `indices`."""
 
     def __init__(self, indptr, indices, data, shape, node_graph=None):
@@ -171,9 +171,9 @@ class CsrPattern:
 
     @property
     def node_graph(self):
-        """(adjptr, adj, dof_n) of a matrix pattern whose rows are all node rows (no Lagrange rows), else None"""
+        """(adjptr, adj, dof_n, max_deg) of a matrix pattern whose rows are all node rows (no Lagrange rows), else None"""
         g = self.graph
-        return (g.adjptr, g.adj, self.dof_n) if self.isMatrix and self.Ndof == g.Nn * self.dof_n else None
+        return (g.adjptr, g.adj, self.dof_n, g.max_deg) if self.isMatrix and self.Ndof == g.Nn * self.dof_n else None
 
     def assemble(self, datas) -> DeviceCsr:
         return DeviceCsr(self.indptr, self.indices, self.replay(datas), self.shape, self.node_graph)

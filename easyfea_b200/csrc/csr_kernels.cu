@@ -1,6 +1,7 @@
 // C-ABI entry points of the CSR pattern build (A1) and the deterministic replay (A2).
 #include "common.cuh"
 #include "csr_kernels.cuh"
+#include "tma.cuh"
 
 #include <stdlib.h>
 #include <string.h>
@@ -456,32 +457,6 @@ static int launch_replay_ring(const double* data, long long Nn, const long long*
 // QUAD4/8, HEXA20): the ring is refilled by bulk asynchronous copies (cp.async.bulk, one for the K_e row and one for its
 // slot positions) issued by a single lane and completed on a per-slot mbarrier, so keeping R element rows in flight per
 // warp costs a handful of instructions per row instead of one cp.async per 16 bytes and lane.
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 template <int D, int NPE>
 struct ReplayTma {
     static constexpr int NDOF = D * NPE, NV = D * NDOF, VPL = (NV + 31) / 32;

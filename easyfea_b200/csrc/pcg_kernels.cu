@@ -5,6 +5,7 @@
 // (per-CTA partials in a fixed grid, then one CTA), hence deterministic.  Dirichlet dofs are handled by masking
 // (projected CG): the search direction is zero on constrained rows, so A_UU is never extracted.
 #include <stddef.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -71,37 +72,77 @@ __global__ void __launch_bounds__(kRedThreads)
 // contiguous D x (D*deg) block (csr_kernels.cuh), so the column structure is the NODE adjacency (adjptr/adj, one int32 per
 // D x D block instead of one index per coefficient: 9x less index traffic in 3D) and every gathered x value serves the D
 // rows of the block.  LPN lanes cooperate on one node; lane l takes columns l, l + LPN, ... of all D rows (coalesced).
-template <int D, int LPN>
-__device__ __forceinline__ double spmv_nodes(long long n_nodes, const long long* __restrict__ adjptr, const int* __restrict__ adj,
-                                             const double* __restrict__ data, const double* __restrict__ x, long long x_row_offset,
-                                             const unsigned char* __restrict__ row_mask, double* __restrict__ y, bool want_dot) {
+// Software-pipelined form: the adjacency pointers and the first PF column ids of a lane's NEXT node are loaded while the
+// current node is processed, so the only dependent load left on a node's critical path is the gather of x (the plain
+// form pays adjptr -> adj -> x, three DRAM latencies, per node and is latency-bound at ~55 % of HBM bandwidth).
+template <int D, int LPN, int PF>
+__device__ __forceinline__ double spmv_nodes_pipe(long long n_nodes, const long long* __restrict__ adjptr, const int* __restrict__ adj,
+                                                  const double* __restrict__ data, const double* __restrict__ x, long long x_row_offset,
+                                                  const unsigned char* __restrict__ row_mask, double* __restrict__ y, bool want_dot) {
     const int lane = threadIdx.x % LPN;
     constexpr int NPB = kRedThreads / LPN;  // nodes per CTA per pass
+    const long long stride = (long long)gridDim.x * NPB;
     double local = 0.0;
-    for (long long base = (long long)blockIdx.x * NPB; base < n_nodes; base += (long long)gridDim.x * NPB) {
-        const long long n = base + threadIdx.x / LPN;
-        const bool live = n < n_nodes;
+    long long n = (long long)blockIdx.x * NPB + threadIdx.x / LPN;
+    long long a0 = 0, a1 = 0;
+    if (n < n_nodes) {
+        a0 = adjptr[n];
+        a1 = adjptr[n + 1];
+    }
+    int col[PF];
+#pragma unroll
+    for (int k = 0; k < PF; ++k) {
+        const int l = lane + LPN * k;
+        col[k] = (l < D * (int)(a1 - a0)) ? adj[a0 + l / D] : 0;
+    }
+    // CTA-uniform trip count: every lane of a group runs the same number of shuffle steps
+    for (long long base = (long long)blockIdx.x * NPB; base < n_nodes; base += stride) {
+        const long long nn = n + stride;
+        long long na0 = 0, na1 = 0;
+        if (nn < n_nodes) {
+            na0 = adjptr[nn];
+            na1 = adjptr[nn + 1];
+        }
+        const int rowlen = D * (int)(a1 - a0);
+        const double* blk = data + (long long)D * D * a0;
+        double xv[PF];
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const int l = lane + LPN * k;
+            xv[k] = (l < rowlen) ? x[(long long)col[k] * D + (l % D)] : 0.0;
+        }
+        int ncol[PF];
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const int l = lane + LPN * k;
+            ncol[k] = (l < D * (int)(na1 - na0)) ? adj[na0 + l / D] : 0;
+        }
         double s[D];
 #pragma unroll
         for (int i = 0; i < D; ++i) s[i] = 0.0;
-        if (live) {
-            const long long a0 = adjptr[n];
-            const int rowlen = D * (int)(adjptr[n + 1] - a0);
-            const double* blk = data + (long long)D * D * a0;
-            const int* cols = adj + a0;
-#pragma unroll 3
-            for (int l = lane; l < rowlen; l += LPN) {
-                const int c = l / D, j = l - c * D;
-                const double xv = x[(long long)cols[c] * D + j];
 #pragma unroll
-                for (int i = 0; i < D; ++i) s[i] += blk[i * rowlen + l] * xv;
+        for (int k = 0; k < PF; ++k) {
+            const int l = lane + LPN * k;
+            if (l < rowlen) {
+#pragma unroll
+                for (int i = 0; i < D; ++i) s[i] += blk[i * rowlen + l] * xv[k];
+            }
+        }
+        if (rowlen > LPN * PF) {  // longer rows than the prefetch depth: the rest the plain way
+            const int* cols = adj + a0;
+#pragma unroll 2
+            for (int l = lane + LPN * PF; l < rowlen; l += LPN) {
+                const int c = l / D, j = l - c * D;
+                const double xr = x[(long long)cols[c] * D + j];
+#pragma unroll
+                for (int i = 0; i < D; ++i) s[i] += blk[i * rowlen + l] * xr;
             }
         }
 #pragma unroll
         for (int i = 0; i < D; ++i)
 #pragma unroll
             for (int off = LPN / 2; off > 0; off >>= 1) s[i] += __shfl_down_sync(0xffffffffu, s[i], off, LPN);
-        if (live && lane == 0) {
+        if (n < n_nodes && lane == 0) {
 #pragma unroll
             for (int i = 0; i < D; ++i) {
                 const long long r = n * D + i;
@@ -110,8 +151,26 @@ __device__ __forceinline__ double spmv_nodes(long long n_nodes, const long long*
                 if (want_dot) local += x[x_row_offset + r] * v;
             }
         }
+        n = nn;
+        a0 = na0;
+        a1 = na1;
+#pragma unroll
+        for (int k = 0; k < PF; ++k) col[k] = ncol[k];
     }
     return local;
+}
+
+// prefetched steps per lane (A/B on B200, profiles/README.md: 2 for short rows, 3 when a whole warp works on one node; 4 and 8
+// lose to register pressure)
+#ifndef EFB_SPMV_PF
+#define EFB_SPMV_PF(LPN) ((LPN) == 32 ? 3 : 2)
+#endif
+
+template <int D, int LPN>
+__device__ __forceinline__ double spmv_nodes(long long n_nodes, const long long* __restrict__ adjptr, const int* __restrict__ adj,
+                                             const double* __restrict__ data, const double* __restrict__ x, long long x_row_offset,
+                                             const unsigned char* __restrict__ row_mask, double* __restrict__ y, bool want_dot) {
+    return spmv_nodes_pipe<D, LPN, EFB_SPMV_PF(LPN)>(n_nodes, adjptr, adj, data, x, x_row_offset, row_mask, y, want_dot);
 }
 
 template <int D, int LPN>
@@ -124,13 +183,25 @@ __global__ void __launch_bounds__(kRedThreads)
     if (dot_partials) {
         const double tot = block_sum(local, red);
         if (threadIdx.x == 0) dot_partials[blockIdx.x] = tot;
+        if (blockIdx.x == 0)  // one-wave grid: efb_pcg_reduce folds the whole partials array, absent CTAs count as zero
+            for (int b = gridDim.x + threadIdx.x; b < kRedBlocks; b += kRedThreads) dot_partials[b] = 0.0;
     }
 }
+
 
 template <int D>
 static int launch_spmv_node(long long n_nodes, const long long* adjptr, const int* adj, const double* data, const double* x,
                             long long x_row_offset, const unsigned char* row_mask, double* y, double* partials, int lpn, cudaStream_t st) {
-#define EFB_SPMVN(L) k_spmv_node<D, L><<<kRedBlocks, kRedThreads, 0, st>>>(n_nodes, adjptr, adj, data, x, x_row_offset, row_mask, y, partials)
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+#define EFB_SPMVN(L)                                                                                                   \
+    {                                                                                                                  \
+        int per_sm = 1;                                                                                                \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spmv_node<D, L>, kRedThreads, 0);                     \
+        const int g = min(kRedBlocks, sms * max(per_sm, 1));                                                           \
+        k_spmv_node<D, L><<<g, kRedThreads, 0, st>>>(n_nodes, adjptr, adj, data, x, x_row_offset, row_mask, y, partials); \
+    }
     switch (lpn) {
         case 4: EFB_SPMVN(4); break;
         case 8: EFB_SPMVN(8); break;

@@ -32,7 +32,7 @@ def spmv(A: DeviceCsr, x: torch.Tensor, y: torch.Tensor = None, row_offset: int 
         y = dv.empty((nrows,))
     ng = getattr(A, "node_graph", None)
     if ng is not None and ng[2] in (1, 2, 3) and nrows % ng[2] == 0:
-        adjptr, adj, d = ng  # node-block product: the column structure is read from the node adjacency
+        adjptr, adj, d, max_deg = ng  # node-block product: the column structure is read from the node adjacency
         n_nodes = nrows // d
         _lib.call("efb_spmv_nodeblock", n_nodes, d, dv.ptr(adjptr), dv.ptr(adj), dv.ptr(A.data), dv.ptr(x), int(row_offset),
                   dv.ptr(mask), dv.ptr(y), dv.ptr(partials), lanes_per_row(A.nnz, nrows), dv.stream_ptr())
@@ -47,7 +47,7 @@ def _system_struct(A: DeviceCsr, nrows, mask, inv_diag, x, r, z, Ap, partials) -
     S.nrows = nrows
     ng = getattr(A, "node_graph", None)
     if ng is not None and ng[2] in (1, 2, 3) and nrows % ng[2] == 0:
-        adjptr, adj, d = ng
+        adjptr, adj, d, max_deg = ng
         S.kind, S.dof_n, S.index_bytes = 1, d, 0
         S.indptr, S.indices = adjptr.data_ptr(), adj.data_ptr()
     else:
