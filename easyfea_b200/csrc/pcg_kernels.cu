@@ -174,7 +174,7 @@ __device__ __forceinline__ double spmv_nodes(long long n_nodes, const long long*
 }
 
 template <int D, int LPN>
-__global__ void __launch_bounds__(kRedThreads)
+__global__ void __launch_bounds__(kRedThreads, 6)  // bound by loads in flight: 6 resident CTAs beat 5 with 8 more registers
     k_spmv_node(long long n_nodes, const long long* __restrict__ adjptr, const int* __restrict__ adj, const double* __restrict__ data,
                 const double* __restrict__ x, long long x_row_offset, const unsigned char* __restrict__ row_mask, double* __restrict__ y,
                 double* __restrict__ dot_partials) {
@@ -465,6 +465,9 @@ __device__ __forceinline__ bool publish_reduction(const efb_pcg_peer& P, PcgCtrl
     return true;
 }
 
+#ifndef EFB_PCG_SPMV_MINB
+#define EFB_PCG_SPMV_MINB 6  // the SpMV is bound by loads in flight: 6 resident CTAs (<= 40 registers) like the standalone kernel
+#endif
 struct SpmvArgs {  // host-side bundle only; the kernels take plain __restrict__ pointers (alias analysis, load batching)
     long long n;  // rows (CSR) or nodes (node blocks)
     const void* indptr;
@@ -477,7 +480,7 @@ struct SpmvArgs {  // host-side bundle only; the kernels take plain __restrict__
 
 // (1) Ap = A p_it with the p.Ap partials; waits for the neighbours' halo entries of p_it first
 template <int KIND, int A, int B>  // KIND 0: CSR, A = index bytes, B = lanes per row; KIND 1: node blocks, A = dof_n, B = lanes per node
-__global__ void __launch_bounds__(kRedThreads)
+__global__ void __launch_bounds__(kRedThreads, EFB_PCG_SPMV_MINB)
     k_pcg_spmv(long long n, const void* __restrict__ indptr, const void* __restrict__ indices, const double* __restrict__ data,
                const double* __restrict__ p, const unsigned char* __restrict__ mask, double* __restrict__ Ap,
                double* __restrict__ partials, efb_pcg_peer P, unsigned long long ar_done, unsigned long long halo_done) {
@@ -718,15 +721,38 @@ extern "C" int efb_pcg_iterate(const efb_pcg_system* sys, const efb_pcg_peer* pe
     const int g_spmv = min(kRedBlocks, sms * resident_blocks_per_sm(spmv_k));
     const int g_xr = min(kRedBlocks, sms * resident_blocks_per_sm(k_pcg_update_xr));
     const int g_p = min(kRedBlocks, sms * resident_blocks_per_sm(k_pcg_update_p));
+    // dev: EFB_PCG_TIMING=1 prints the mean duration of the three kernels of this call (CUDA events between the launches)
+    static const bool timing = [] { const char* e = getenv("EFB_PCG_TIMING"); return e && atoi(e) > 0; }();
+    cudaEvent_t* ev = nullptr;
+    if (timing) {
+        ev = new cudaEvent_t[3 * n_iters + 1];
+        for (int i = 0; i <= 3 * n_iters; ++i) cudaEventCreate(&ev[i]);
+        cudaEventRecord(ev[0], st);
+    }
     for (int k = 0; k < n_iters; ++k) {
         const long long it = it0 + k;
         const double* p = (const double*)((const char*)P.base[P.rank] + P.pbuf_off[P.rank][it & 1]);
         double* pn = (double*)((char*)P.base[P.rank] + P.pbuf_off[P.rank][(it & 1) ^ 1]);
         const unsigned long long ar_done = P.ar_seq + 2ull * (unsigned long long)k, halo_done = P.halo_seq + (unsigned long long)k;
         spmv_k<<<g_spmv, kRedThreads, 0, st>>>(a.n, a.indptr, a.indices, a.data, p, a.mask, a.Ap, a.partials, P, ar_done, halo_done);
+        if (timing) cudaEventRecord(ev[3 * k + 1], st);
         k_pcg_update_xr<<<g_xr, kRedThreads, 0, st>>>(sys->nrows, p, sys->x, sys->r, sys->z, sys->Ap, sys->inv_diag, sys->free_mask,
                                                        sys->partials, P, it, ar_done);
+        if (timing) cudaEventRecord(ev[3 * k + 2], st);
         k_pcg_update_p<<<g_p, kRedThreads, 0, st>>>(sys->nrows, sys->z, sys->free_mask, p, pn, P, it, ar_done, halo_done);
+        if (timing) cudaEventRecord(ev[3 * k + 3], st);
+    }
+    if (timing) {
+        cudaEventSynchronize(ev[3 * n_iters]);
+        float t[3] = {0, 0, 0}, ms;
+        for (int i = 0; i < 3 * n_iters; ++i) {
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            t[i % 3] += ms;
+        }
+        fprintf(stderr, "[efb_pcg_iterate rank %d] %d iterations, grids %d/%d/%d: spmv %.1f us, update_xr %.1f us, update_p %.1f us\n", P.rank,
+                n_iters, g_spmv, g_xr, g_p, 1e3 * t[0] / n_iters, 1e3 * t[1] / n_iters, 1e3 * t[2] / n_iters);
+        for (int i = 0; i <= 3 * n_iters; ++i) cudaEventDestroy(ev[i]);
+        delete[] ev;
     }
     return check_launch("efb_pcg_iterate");
 }
