@@ -90,6 +90,7 @@ SIGNATURES = {
     "efb_pcg_update_xr": [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "efb_pcg_update_p": [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "efb_pack_f64": [c_i64, c_vp, c_vp, c_vp, c_vp],
+    "efb_lincomb": [c_i64, ctypes.c_int, ctypes.POINTER(c_f64), _PP, c_vp, c_vp],
     "efb_pcg_ctrl_bytes": [],
     "efb_pcg_ctrl_layout": [_I32P],
     "efb_pcg_iterate": [ctypes.POINTER(EfbPcgSystem), ctypes.POINTER(EfbPcgPeer), ctypes.c_int, c_i64, c_vp],

@@ -595,6 +595,23 @@ static int resident_blocks_per_sm(K kernel) {
     return b;
 }
 
+// out = sum_k c[k] v[k], k < m <= 4 (the time-scheme combinations of CSR value arrays and of nodal vectors; `out` may be one
+// of the inputs).  _simu.py:1777-1853 (right-hand sides), :1890-1894 (A = coefK K + coefC C + coefM M), :1552-1657 (correctors)
+struct LinComb {
+    const double* v[4];
+    double c[4];
+    int m;
+};
+__global__ void k_lincomb(long long n, LinComb L, double* out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k < L.m) s += L.c[k] * L.v[k][i];
+        out[i] = s;
+    }
+}
+
 }  // namespace efb
 
 using namespace efb;
@@ -805,6 +822,24 @@ extern "C" int efb_peer_close(void* ptr) {
         return 1;
     }
     return 0;
+}
+
+extern "C" int efb_lincomb(int64_t n, int m, const double* coefs, const double* const* vecs_host, double* out, void* stream) {
+    if (m < 1 || m > 4) {
+        set_error("efb_lincomb: m must be 1..4, got %d", m);
+        return 1;
+    }
+    if (n == 0) return 0;
+    LinComb L;
+    L.m = m;
+    for (int k = 0; k < 4; ++k) {
+        L.v[k] = k < m ? vecs_host[k] : nullptr;
+        L.c[k] = k < m ? coefs[k] : 0.0;
+    }
+    long long nblk = (n + 255) / 256;
+    if (nblk > 148 * 16) nblk = 148 * 16;
+    k_lincomb<<<(unsigned)nblk, 256, 0, as_stream(stream)>>>(n, L, out);
+    return check_launch("efb_lincomb");
 }
 
 extern "C" int efb_pack_f64(int64_t n, const int32_t* idx, const double* src, double* dst, void* stream) {

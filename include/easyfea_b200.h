@@ -252,6 +252,12 @@ int efb_peer_export(void* ptr, void* handle64 /* 64 bytes out */);
 int efb_peer_open(const void* handle64, void** ptr);           /* maps a region exported by another process */
 int efb_peer_close(void* ptr);
 
+/* ---- time-scheme system build -------------------------------------------------
+ * out[i] = sum_{k<m} coefs[k] * vecs[k][i], m <= 4; coefs and the pointer table are HOST arrays, vecs[k] and out device
+ * arrays of n doubles (out may be one of the inputs).  Serves A = coefK K + coefC C + coefM M on the shared CSR pattern
+ * (_simu.py:1890-1894), the history terms of the right-hand side (:1777-1853) and the correctors (:1552-1657). */
+int efb_lincomb(int64_t n, int m, const double* coefs, const double* const* vecs_host, double* out, void* stream);
+
 /* send-buffer packing of the PCG halo exchange (row-sharded runs): dst[i] = src[idx[i]] */
 int efb_pack_f64(int64_t n, const int32_t* idx, const double* src, double* dst, void* stream);
 

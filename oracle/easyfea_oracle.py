@@ -630,3 +630,133 @@ class StaggeredOracle:
 
     def Save_Iter(self):
         self.psiP_old = self.psiP
+
+
+# =========================================================================================================
+# consumers: time-scheme system build        EasyFEA/Simulations/_simu.py:1399-1455, 1552-1657, 1758-1894
+# =========================================================================================================
+PARABOLIC = "parabolic"
+HYPERBOLIC = ("newmark", "hht", "midpoint", "hht_newmark", "euler_implicit", "euler_explicit")
+
+
+def time_scheme_coefs(algo, dt, beta=0.25, gamma=0.5, alpha=0.5):
+    """(coefK, coefC, coefM) of `A = coefK K + coefC C + coefM M`, `_Solver_Get_K_C_M_coefs_for_time_scheme` (_simu.py:1399-1455)."""
+    if algo == "newmark":
+        return 1.0, gamma / (beta * dt), 1 / (beta * dt**2)
+    if algo == "hht":
+        return 1 - alpha, (1 - alpha) * gamma / (beta * dt), (1 - alpha) / (beta * dt**2)
+    if algo == "midpoint":
+        return 0.5, 1 / dt, 2 / dt**2
+    if algo == "hht_newmark":
+        return 1 - alpha, gamma / (beta * dt), 1 / (beta * dt**2)
+    if algo == "parabolic":
+        return 1.0, 1 / (alpha * dt), 0.0
+    if algo == "euler_implicit":
+        return 1.0, 1 / dt, 1 / dt**2
+    if algo == "euler_explicit":
+        return 0.0, 0.0, 1.0
+    raise NotImplementedError(algo)
+
+
+def hht_newmark_params(alpha):
+    """beta, gamma imposed by `Solver_Set_Hyperbolic_Algorithm` for hht_newmark (_simu.py:1266-1276)"""
+    return 0.25 * (1 + alpha) ** 2, 0.5 + alpha
+
+
+class TransientOracle:
+    """One linear problem `K u + C v + M a = F` stepped by the reference's time schemes: right-hand side of
+    `_Solver_Apply_Neumann` (_simu.py:1777-1853), system matrix of `_Solver_Apply_Dirichlet` (:1890-1894), elimination solve of
+    `__Solver_1` (Solvers.py:502-553) and the corrector of `_Solver_Update_solutions` (_simu.py:1552-1657)."""
+
+    def __init__(self, K, C=None, M=None):
+        import scipy.sparse as sp
+
+        n = K.shape[0]
+        zero = sp.csr_matrix((n, n))
+        self.K, self.C, self.M = K.tocsr(), (zero if C is None else C.tocsr()), (zero if M is None else M.tocsr())
+        self.n = n
+        self.u, self.v, self.a = np.zeros(n), np.zeros(n), np.zeros(n)
+        self.algo = "elliptic"
+
+    def set_parabolic(self, dt, alpha=0.5):
+        self.algo, self.dt, self.alpha = "parabolic", dt, alpha
+
+    def set_hyperbolic(self, dt, algo="newmark", beta=0.25, gamma=0.5, alpha=0.5):
+        assert algo in HYPERBOLIC
+        if algo == "hht_newmark":
+            beta, gamma = hht_newmark_params(alpha)
+        self.algo, self.dt, self.beta, self.gamma, self.alpha = algo, dt, beta, gamma, alpha
+
+    def rhs(self, F):
+        """b of `_Solver_Apply_Neumann` for the current (u_n, v_n, a_n)"""
+        K, C, M, u, v, a, algo = self.K, self.C, self.M, self.u, self.v, self.a, self.algo
+        b = np.array(F, dtype=float)
+        if algo == "elliptic":
+            return b
+        dt = self.dt
+        if algo == "parabolic":
+            al = self.alpha
+            ut = u + (1 - al) * dt * v
+            return b + 1 / (al * dt) * (C @ ut)
+        be, ga, al = self.beta, self.gamma, self.alpha
+        if algo in ("newmark", "hht_newmark"):
+            ut = u + dt * v + dt**2 / 2 * (1 - 2 * be) * a
+            vt = v + dt * (1 - ga) * a
+            b = b + (ga / (be * dt) * C + 1 / (be * dt**2) * M) @ ut - C @ vt
+            if algo == "hht_newmark":
+                b = b - al * (K @ u)
+            return b
+        if algo == "midpoint":
+            return b + (2 / dt**2 * M + 1 / dt * C - 0.5 * K) @ u + 2 / dt * (M @ v)
+        if algo == "hht":
+            cM, cC = 1 / (be * dt**2), ga / (be * dt)
+            b = b - ((al - 1) * (cM * M + cC * C) + al * K) @ u
+            b = b - ((al - 1) / (be * dt) * M + ((al - 1) * (ga / be) + 1) * C) @ v
+            b = b - (((al - 1) / (2 * be) + 1) * M + dt * (al - 1) * (ga / (2 * be) - 1) * C) @ a
+            return b
+        if algo == "euler_implicit":
+            return b + (1 / dt**2 * M + 1 / dt * C) @ u + (1 / dt) * (M @ v)
+        if algo == "euler_explicit":
+            return b - K @ u - C @ v
+        raise NotImplementedError(algo)
+
+    def matrix(self):
+        if self.algo == "elliptic":
+            return self.K
+        cK, cC, cM = time_scheme_coefs(self.algo, self.dt, getattr(self, "beta", 0.25), getattr(self, "gamma", 0.5), self.alpha)
+        return (cK * self.K + cC * self.C + cM * self.M).tocsr()
+
+    def update(self, x):
+        """(u, v, a)_{n+1} from the solved unknown, `_Solver_Update_solutions`"""
+        u, v, a, algo = self.u, self.v, self.a, self.algo
+        if algo == "elliptic":
+            return x, v, a
+        dt = self.dt
+        if algo == "parabolic":
+            vt = u + (1 - self.alpha) * dt * v
+            return x, (x - vt) / (self.alpha * dt), a
+        be, ga = self.beta, self.gamma
+        if algo in ("newmark", "hht_newmark"):
+            ut = u + dt * v + dt**2 / 2 * (1 - 2 * be) * a
+            vt = v + dt * (1 - ga) * a
+            a1 = (x - ut) / (be * dt**2)
+            return x, vt + ga * dt * a1, a1
+        if algo == "midpoint":
+            v1 = 2 / dt * (x - u) - v
+            return x, v1, 2 / dt * (v1 - v) - a
+        if algo == "hht":
+            a1 = 1 / (be * dt) * ((x - u) / dt - v) + (1 - 1 / (2 * be)) * a
+            return x, dt * ((1 - ga) * a + ga * a1) + v, a1
+        if algo == "euler_implicit":
+            v1 = (x - u) / dt
+            return x, v1, (v1 - v) / dt
+        if algo == "euler_explicit":
+            return u + dt * v, v + dt * x, x
+        raise NotImplementedError(algo)
+
+    def Solve(self, F, dofs_known, x_known):
+        """one step: Dirichlet values are those of the solved unknown (zero accelerations for euler_explicit, _simu.py:1903-1905)"""
+        x_known = np.zeros(len(dofs_known)) if self.algo == "euler_explicit" else np.asarray(x_known, dtype=float)
+        x = solve_dirichlet(self.matrix(), self.rhs(F), np.asarray(dofs_known), x_known)
+        self.u, self.v, self.a = self.update(x)
+        return self.u
