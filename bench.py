@@ -317,6 +317,11 @@ def run_ours(args):
             extras["phase_field"] = phase_field_leg(args, rank, world, dist)
         except Exception as exc:
             extras["phase_field"] = {"error": repr(exc)[:300]}
+    if not args.no_transient:
+        try:
+            extras["transient"] = transient_leg(args, rank, world, dist)
+        except Exception as exc:
+            extras["transient"] = {"error": repr(exc)[:300]}
     line["extras"] = extras
 
     if rank == 0:
@@ -459,6 +464,81 @@ def phase_field_leg(args, rank, world, dist):
             "last_damage_increment": float(conv.item()), "max_damage": float(dmax.item())}
 
 
+def transient_leg(args, rank, world, dist):
+    """BASELINE config 5: HEXA27 mesh, K + M assembly (elastodynamics: 81x81 element matrices at 27 Gauss points) and Newmark
+    steps, then thermal K + C assembly and parabolic steps — seconds per assembly and per time step, element-partitioned."""
+    import torch
+
+    from easyfea_b200 import dist as efd
+    from easyfea_b200 import mesh, meshgen, staggered, transient
+
+    n = args.tr_n
+    lattice, connect = meshgen.structured_mesh("HEXA27", n)
+    coords, _ = meshgen.structured_mesh("HEXA27", n, jitter=0.1, seed=3)
+    Nn = coords.shape[0]
+    if world > 1:
+        part = efd.Partition.from_global(connect, Nn, world, rank)
+        g = mesh.ElemGroup("HEXA27", part.connect, coords[part.nodes], all_nodes_used=True)
+        sysm = staggered.LocalSystem(g, part, lambda p, d: efd.RowComm(p, d))
+        nodes = part.nodes
+    else:
+        g = mesh.ElemGroup("HEXA27", connect, coords, all_nodes_used=True)
+        sysm = staggered.LocalSystem(g)
+        nodes = np.arange(Nn)
+    x = lattice[nodes, 0]
+    loc = np.arange(nodes.size)
+    lo, hi = loc[x < 1e-12], loc[x > 1 - 1e-12]
+
+    def timed(fn, reps):
+        fn()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    out = {"workload": f"BASELINE config 5: HEXA27 {n}^3 = {n**3} elements, {Nn} nodes, over {world} GPU(s)"}
+    box = {}
+
+    def build_dyn():
+        box["dyn"] = transient.TransientSolve.elastodynamic(sysm, _material_C(), 7.8e-3, coefM=0.1, coefK=1e-5)
+
+    out["elastodynamic_assembly_ms"] = timed(build_dyn, 2)  # K_e, M_e (27 Gauss points), two CSR replays, Rayleigh C
+    dyn = box["dyn"]
+    dyn.Solver_Set_Hyperbolic_Algorithm(dt=1e-3)  # Newmark average acceleration
+    dyn.pcg_tol = 1e-8
+    dyn.bc.add(lo, [0.0, 0.0, 0.0], [0, 1, 2], 3)
+    dyn.bc.add(hi, [1e-3], [0], 3)
+    out["newmark_step_ms"] = timed(lambda: dyn.Solve(), args.tr_steps)
+    out["newmark_pcg_iters"] = dyn.info["iterations"]
+    out["newmark_pcg_converged"] = bool(dyn.info["converged"])
+    del dyn, box["dyn"]
+
+    def build_th():
+        box["th"] = transient.TransientSolve.thermal(sysm, 1.0, 1.0)
+
+    out["thermal_assembly_ms"] = timed(build_th, 2)
+    th = box["th"]
+    th.Solver_Set_Parabolic_Algorithm(dt=0.1, alpha=0.5)
+    th.pcg_tol = 1e-8
+    th.bc.add(lo, [0.0], [0], 1)
+    th.bc.add(hi, [40.0], [0], 1)
+    out["parabolic_step_ms"] = timed(lambda: th.Solve(), args.tr_steps)
+    out["parabolic_pcg_iters"] = th.info["iterations"]
+    out["parabolic_pcg_converged"] = bool(th.info["converged"])
+    return out
+
+
 def e2e_leg(args, g, part, C, pat, Ke, data, world):
     """Same step through host buffers: pinned (connect int32, coords) -> device, K_e + replay, owned CSR data -> pinned host."""
     import torch
@@ -511,6 +591,9 @@ def main():
     ap.add_argument("--pf-n", type=int, default=1000, help="TRI3 cells per side (1000 -> 2.0 M elements, config 3)")
     ap.add_argument("--pf-iters", type=int, default=2)
     ap.add_argument("--pf-maxiter", type=int, default=20000)
+    ap.add_argument("--no-transient", action="store_true", help="skip the HEXA27 transient extra (config 5)")
+    ap.add_argument("--tr-n", type=int, default=40, help="HEXA27 cells per side (40 -> 64 000 elements, 531 441 nodes)")
+    ap.add_argument("--tr-steps", type=int, default=3)
     ap.add_argument("--pf-unfused", action="store_true", help="phase-field solves with the NCCL/kernel-per-operation PCG loop")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -23,12 +23,12 @@ for w in $what; do
       tail -c 3000 gpurun_out/${tag}_bench.json; tail -5 gpurun_out/${tag}_bench.err ;;
     launches)
       timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-        --log-file gpurun_out/${tag}_launches.csv python bench.py --n 128 --steps 3 --warmup 3 --no-cpu --e2e-steps 1 --no-pf --no-solve \
+        --log-file gpurun_out/${tag}_launches.csv python bench.py --n 128 --steps 3 --warmup 3 --no-cpu --e2e-steps 1 --no-pf --no-solve --no-transient \
         > gpurun_out/${tag}_launches.log 2>&1
       tail -2 gpurun_out/${tag}_launches.log ;;
     full)
       timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'k_elastic|k_replay|k_fused' -s 6 -c 2 \
-        -f -o gpurun_out/${tag}_full python bench.py --n 128 --steps 2 --warmup 3 --no-cpu --e2e-steps 1 --no-pf --no-solve \
+        -f -o gpurun_out/${tag}_full python bench.py --n 128 --steps 2 --warmup 3 --no-cpu --e2e-steps 1 --no-pf --no-solve --no-transient \
         > gpurun_out/${tag}_full.log 2>&1
       tail -2 gpurun_out/${tag}_full.log ;;
   esac

@@ -31,7 +31,7 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-n
 rows = list(csv.reader(io.StringIO(src)))
 if len(rows) > 2:
     hdr = rows[1]; idx = {h: i for i, h in enumerate(hdr)}
-    data = [r for r in rows[2:] if len(r) == len(hdr)]
+    data = [r for r in rows[2:] if len(r) == len(hdr) and r[idx['# Samples']].isdigit()]  # several captured launches repeat the header
     tot = sum(int(r[idx['# Samples']]) for r in data) or 1
     op = collections.Counter(); exe = collections.Counter()
     for r in data:
