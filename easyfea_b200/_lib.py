@@ -94,6 +94,7 @@ SIGNATURES = {
     "efb_pcg_ctrl_bytes": [],
     "efb_pcg_ctrl_layout": [_I32P],
     "efb_pcg_iterate": [ctypes.POINTER(EfbPcgSystem), ctypes.POINTER(EfbPcgPeer), ctypes.c_int, c_i64, c_vp],
+    "efb_pcg_solve_persistent": [ctypes.POINTER(EfbPcgSystem), ctypes.POINTER(EfbPcgPeer), c_i64, c_i64, c_f64, c_vp],
     "efb_peer_alloc": [c_i64, _PP],
     "efb_peer_free": [c_vp],
     "efb_peer_export": [c_vp, c_vp],

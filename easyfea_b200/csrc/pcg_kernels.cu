@@ -353,6 +353,8 @@ struct PcgCtrl {
     double rz[2];                                 // local: r.z of iteration it in rz[it & 1]
     double pAp;
     double rr;                                    // local: r.r after the last finished iteration
+    unsigned long long gbar;                      // local: grid-barrier arrivals of the persistent kernel (zeroed before each launch)
+    unsigned long long iters_done;                // local: iterations the last persistent launch ran
 };
 constexpr int kCtrlBytes = 1024;
 static_assert(sizeof(PcgCtrl) <= kCtrlBytes, "control block");
@@ -587,6 +589,200 @@ static SpmvKernel pcg_spmv_kernel(int lanes) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent form: ONE kernel runs the iterations until convergence.  The three steps are separated by grid barriers
+// (monotonic arrival counter in the control block; the grid is one resident wave, launched cooperatively), after a barrier
+// EVERY CTA folds the per-CTA partials itself in the same fixed order, so no CTA waits for a designated reducer, and
+// every CTA of every rank sees the same r.r and leaves the loop in the same iteration: no host round trip, no kernel
+// launch and no launch-boundary drain per iteration (3 x ~13 us in the three-kernel form, which dominates small systems
+// and strong-scaled shards).  Multi-GPU: CTA 0 stores the rank's sums into the peers' control blocks and raises their
+// flags; the interface entries of p' go straight into the neighbours' buffers, as in the three-kernel form.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// all CTAs arrive, all CTAs leave; `target` = arrivals expected so far (monotonic).  False when the wait was abandoned.
+__device__ __forceinline__ bool grid_barrier(PcgCtrl* own, unsigned long long target) {
+    __shared__ int ok;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&own->gbar, 1ull);
+        int good = 1;
+        const long long t0 = clock64();
+        while (ld_acquire_gpu(&own->gbar) < target) {
+            if (*(volatile unsigned int*)&own->error || clock64() - t0 > kSpinTimeoutCycles) {
+                atomicExch(&own->error, 1u);
+                good = 0;
+                break;
+            }
+        }
+        ok = good;
+    }
+    __syncthreads();
+    return ok != 0;
+}
+
+// after a grid barrier: every CTA folds the G per-CTA partials of M quantities in fixed order; with several ranks CTA 0
+// publishes the rank's sums (reduction number `seq`) and every CTA adds the ranks' sums in rank order
+template <int M>
+__device__ __forceinline__ void fold_partials(const efb_pcg_peer& P, PcgCtrl* own, const double* __restrict__ partials, int G,
+                                              unsigned long long seq, double (&out)[M], double* red) {
+    double mine[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        double s = 0.0;
+        for (int b = threadIdx.x; b < G; b += kRedThreads) s += __ldcg(&partials[m * kRedBlocks + b]);
+        const double tot = block_sum(s, red);  // red[0] read by every thread inside block_sum
+        mine[m] = tot;
+    }
+    if (P.world == 1) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) out[m] = mine[m];
+        return;
+    }
+    const int buf = (int)((seq - 1) & 1);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int q = 0; q < P.world; ++q) {
+            if (q == P.rank) continue;
+            PcgCtrl* c = (PcgCtrl*)P.base[q];
+#pragma unroll
+            for (int m = 0; m < M; ++m) *(volatile double*)&c->ar_val[buf][P.rank][m] = mine[m];
+        }
+        fence_sys();
+        for (int q = 0; q < P.world; ++q)
+            if (q != P.rank) st_release_sys(&((PcgCtrl*)P.base[q])->ar_flag[P.rank], seq);
+    }
+    if (threadIdx.x < EFB_MAX_RANKS) {
+        const int q = threadIdx.x;
+        if (q < P.world) {
+            if (q == P.rank) {
+#pragma unroll
+                for (int m = 0; m < M; ++m) red[q * M + m] = mine[m];
+            } else {
+                spin_until(&own->ar_flag[q], seq, own);
+#pragma unroll
+                for (int m = 0; m < M; ++m) red[q * M + m] = *(volatile double*)&own->ar_val[buf][q][m];
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        double acc = 0.0;
+        for (int q = 0; q < P.world; ++q) acc += red[q * M + m];
+        out[m] = acc;
+    }
+    __syncthreads();
+}
+
+template <int D, int LPN>
+__global__ void __launch_bounds__(kRedThreads, EFB_PCG_SPMV_MINB)
+    k_pcg_persistent(long long n_nodes, const long long* __restrict__ adjptr, const int* __restrict__ adj, const double* __restrict__ data,
+                     const unsigned char* __restrict__ mask, const double* __restrict__ inv_diag, double* __restrict__ x,
+                     double* __restrict__ r, double* __restrict__ z, double* __restrict__ Ap, double* __restrict__ partials,
+                     efb_pcg_peer P, long long it0, long long max_iters, double target_rr) {
+    __shared__ double red[kRedThreads];
+    PcgCtrl* own = (PcgCtrl*)P.base[P.rank];
+    const int G = (int)gridDim.x;
+    const long long n = n_nodes * D;
+    const long long first = (long long)blockIdx.x * kRedThreads + threadIdx.x, stride = (long long)G * kRedThreads;
+    double* pa = partials;                   // p.Ap partials
+    double* pb = partials + kRedBlocks;      // (r.z, r.r) partials: a CTA may still fold `pa` while a faster one writes these
+    double rz_old = own->rz[it0 & 1], rr = own->rr;
+    unsigned long long nbar = 0;
+    long long k = 0;
+    bool alive = true;
+    for (; k < max_iters && alive; ++k) {
+        const long long it = it0 + k;
+        const double* p = (const double*)((const char*)P.base[P.rank] + P.pbuf_off[P.rank][it & 1]);
+        double* pn = (double*)((char*)P.base[P.rank] + P.pbuf_off[P.rank][(it & 1) ^ 1]);
+        // (1) Ap = A p, p.Ap
+        if (P.n_recv > 0) {
+            if (threadIdx.x == 0)
+                for (int i = 0; i < P.n_recv; ++i) spin_until(&own->halo_flag[P.recv_rank[i]], P.halo_seq + (unsigned long long)k, own);
+            __syncthreads();
+        }
+        const double local = spmv_nodes<D, LPN>(n_nodes, adjptr, adj, data, p, 0, mask, Ap, true);
+        const double tot = block_sum(local, red);
+        if (threadIdx.x == 0) pa[blockIdx.x] = tot;
+        nbar += G;
+        alive = grid_barrier(own, nbar);
+        double pAp[1];
+        fold_partials<1>(P, own, pa, G, P.ar_seq + 2ull * (unsigned long long)k + 1ull, pAp, red);
+        // (2) x, r, z and (r.z, r.r)
+        const double alpha = rz_old / pAp[0];
+        double s_rz = 0.0, s_rr = 0.0;
+        for (long long i = first; i < n; i += stride) {
+            if (mask && !mask[i]) continue;
+            x[i] += alpha * p[i];
+            const double ri = r[i] - alpha * Ap[i];
+            r[i] = ri;
+            const double zi = ri * inv_diag[i];
+            z[i] = zi;
+            s_rz += ri * zi;
+            s_rr += ri * ri;
+        }
+        const double t0 = block_sum(s_rz, red), t1 = block_sum(s_rr, red);
+        if (threadIdx.x == 0) {
+            pb[blockIdx.x] = t0;
+            pb[kRedBlocks + blockIdx.x] = t1;
+        }
+        nbar += G;
+        alive = grid_barrier(own, nbar) && alive;
+        double t[2];
+        fold_partials<2>(P, own, pb, G, P.ar_seq + 2ull * (unsigned long long)k + 2ull, t, red);
+        // (3) p' = z + beta p into the other buffer, interface entries also into the neighbours' halo segments
+        const double beta = t[0] / rz_old;
+        const int nxt = (int)(it & 1) ^ 1;
+        for (int s = 0; s < P.n_send; ++s) {
+            const int q = P.send_rank[s];
+            double* dst = (double*)((char*)P.base[q] + P.pbuf_off[q][nxt]) + P.send_dst[s];
+            const long long j0 = P.send_ptr[s], cnt = P.send_ptr[s + 1] - j0;
+            for (long long j = first; j < cnt; j += stride) {
+                const int i = P.send_idx[j0 + j];
+                dst[j] = (mask && !mask[i]) ? 0.0 : z[i] + beta * p[i];
+            }
+        }
+        for (long long i = first; i < n; i += stride) pn[i] = (mask && !mask[i]) ? 0.0 : z[i] + beta * p[i];
+        if (P.n_send > 0) fence_sys();  // this thread's stores into the neighbours are visible before it arrives
+        nbar += G;
+        alive = grid_barrier(own, nbar) && alive;
+        if (P.n_send > 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+            fence_sys();
+            for (int s = 0; s < P.n_send; ++s)
+                st_release_sys(&((PcgCtrl*)P.base[P.send_rank[s]])->halo_flag[P.rank], P.halo_seq + (unsigned long long)k + 1ull);
+        }
+        rz_old = t[0];
+        rr = t[1];
+        if (!(rr > target_rr)) {  // converged, or NaN: every CTA of every rank sees the same bits and leaves together
+            ++k;
+            break;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        own->rz[(it0 + k) & 1] = rz_old;
+        own->rr = rr;
+        own->iters_done = (unsigned long long)k;
+    }
+}
+
+using PersistentKernel = void (*)(long long, const long long*, const int*, const double*, const unsigned char*, const double*, double*,
+                                  double*, double*, double*, double*, efb_pcg_peer, long long, long long, double);
+template <int D>
+static PersistentKernel pcg_persistent_kernel(int lanes) {
+    switch (lanes) {
+        case 4: return k_pcg_persistent<D, 4>;
+        case 8: return k_pcg_persistent<D, 8>;
+        case 16: return k_pcg_persistent<D, 16>;
+        default: return k_pcg_persistent<D, 32>;
+    }
+}
+
 // one wave: every CTA of the three kernels is resident at once (grid-stride bodies, no tail wave), capped by the partials layout
 template <class K>
 static int resident_blocks_per_sm(K kernel) {
@@ -616,7 +812,7 @@ __global__ void k_lincomb(long long n, LinComb L, double* out) {
 
 using namespace efb;
 
-extern "C" int efb_pcg_partials_size(void) { return 2 * kRedBlocks; }
+extern "C" int efb_pcg_partials_size(void) { return 3 * kRedBlocks; }
 
 extern "C" int efb_spmv_csr(int64_t nrows, int index_bytes, const void* indptr, const void* indices, const double* data,
                             const double* x, int64_t x_row_offset, const uint8_t* row_mask, double* y, double* dot_partials,
@@ -694,10 +890,11 @@ extern "C" int efb_pcg_update_p(int64_t n, const double* rz_new, const double* r
 
 extern "C" int efb_pcg_ctrl_bytes(void) { return kCtrlBytes; }
 
-extern "C" int efb_pcg_ctrl_layout(int32_t* out3) {
+extern "C" int efb_pcg_ctrl_layout(int32_t* out3) {  // 4 entries
     out3[0] = (int32_t)(offsetof(PcgCtrl, rz) / 8);
     out3[1] = (int32_t)(offsetof(PcgCtrl, rr) / 8);
     out3[2] = (int32_t)(offsetof(PcgCtrl, error) / 4);
+    out3[3] = (int32_t)(offsetof(PcgCtrl, iters_done) / 8);
     return 0;
 }
 
@@ -772,6 +969,53 @@ extern "C" int efb_pcg_iterate(const efb_pcg_system* sys, const efb_pcg_peer* pe
         delete[] ev;
     }
     return check_launch("efb_pcg_iterate");
+}
+
+extern "C" int efb_pcg_solve_persistent(const efb_pcg_system* sys, const efb_pcg_peer* peer, int64_t it0, int64_t max_iters,
+                                        double target_rr, void* stream) {
+    const efb_pcg_peer& P = *peer;
+    if (P.world < 1 || P.world > EFB_MAX_RANKS || P.rank < 0 || P.rank >= P.world) {
+        set_error("efb_pcg_solve_persistent: bad communicator (world %d, rank %d)", P.world, P.rank);
+        return 1;
+    }
+    if (sys->kind != 1 || sys->dof_n < 1 || sys->dof_n > 3 || sys->nrows % sys->dof_n) {
+        set_error("efb_pcg_solve_persistent: node-block systems only (kind 1, dof_n 1..3 dividing nrows)");
+        return 1;
+    }
+    cudaStream_t st = as_stream(stream);
+    PersistentKernel kern = sys->dof_n == 1 ? pcg_persistent_kernel<1>(sys->lanes)
+                            : sys->dof_n == 2 ? pcg_persistent_kernel<2>(sys->lanes) : pcg_persistent_kernel<3>(sys->lanes);
+    int dev = 0, sms = 148, coop = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (!coop) {
+        set_error("efb_pcg_solve_persistent: the device does not support cooperative launches");
+        return 1;
+    }
+    const int G = min(kRedBlocks, sms * resident_blocks_per_sm(kern));
+    PcgCtrl* own = (PcgCtrl*)P.base[P.rank];
+    cudaError_t err = cudaMemsetAsync(&own->gbar, 0, 2 * sizeof(unsigned long long), st);  // gbar, iters_done
+    if (err != cudaSuccess) {
+        set_error("efb_pcg_solve_persistent: %s", cudaGetErrorString(err));
+        return 1;
+    }
+    long long n_nodes = sys->nrows / sys->dof_n, it0_ = it0, max_ = max_iters;
+    const long long* adjptr = (const long long*)sys->indptr;
+    const int* adj = (const int*)sys->indices;
+    const double* data = sys->data;
+    const unsigned char* mask = sys->free_mask;
+    const double* inv_diag = sys->inv_diag;
+    double *x = sys->x, *r = sys->r, *z = sys->z, *Ap = sys->Ap, *partials = sys->partials;
+    efb_pcg_peer Pv = P;
+    void* args[] = {&n_nodes, &adjptr, &adj, &data, &mask, &inv_diag, &x, &r, &z, &Ap, &partials, &Pv, &it0_, &max_, &target_rr};
+    err = cudaLaunchCooperativeKernel((const void*)kern, dim3(G), dim3(kRedThreads), args, 0, st);
+    if (err != cudaSuccess) {
+        set_error("efb_pcg_solve_persistent: cooperative launch of %d CTAs failed: %s", G, cudaGetErrorString(err));
+        cudaGetLastError();
+        return 1;
+    }
+    return 0;
 }
 
 extern "C" int efb_peer_alloc(int64_t bytes, void** ptr) {

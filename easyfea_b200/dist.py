@@ -265,9 +265,9 @@ class LocalWorkspace:
         lib = _lib.load()
         self.n = int(n)
         ctrl = lib.efb_pcg_ctrl_bytes()
-        lay = (ctypes.c_int32 * 3)()
+        lay = (ctypes.c_int32 * 4)()
         lib.efb_pcg_ctrl_layout(lay)
-        self.rz_off, self.rr_off, self.err_off = int(lay[0]), int(lay[1]), int(lay[2])
+        self.rz_off, self.rr_off, self.err_off, self.iters_off = int(lay[0]), int(lay[1]), int(lay[2]), int(lay[3])
         self.ctrl_bytes = ctrl
         self.pbuf_off = (ctrl, ctrl + _pad256(self.n * 8))
         self.nbytes = ctrl + 2 * _pad256(self.n * 8)
@@ -290,9 +290,9 @@ class LocalWorkspace:
         P.ar_seq, P.halo_seq = 0, 0
 
     def status(self):
-        """(r.r of the last finished iteration, error flag) — one small device-to-host copy"""
+        """(r.r of the last finished iteration, error flag, iterations of the last persistent launch) — one small copy"""
         c = self.ctrl.cpu().numpy()
-        return float(c[self.rr_off]), int(c.view(np.uint32)[self.err_off])
+        return float(c[self.rr_off]), int(c.view(np.uint32)[self.err_off]), int(c.view(np.uint64)[self.iters_off])
 
     def advance(self, n_iters: int):
         self.peer.ar_seq += 2 * n_iters

@@ -61,15 +61,19 @@ def _system_struct(A: DeviceCsr, nrows, mask, inv_diag, x, r, z, Ap, partials) -
 
 
 def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: int = None, check_every: int = 25, comm=None,
-        fused: bool = True):
+        fused: bool = True, persistent: bool = False):
     """Solve A x = b on the free dofs (free_mask True / 1 = unknown; other entries of x keep the values of x0).
 
     A holds the owned rows in LOCAL numbering `[owned | halo]` columns.  Stops when ||r|| <= tol * ||b - A x_known||
     (both restricted to free dofs).  Returns (x_owned, info dict).  `comm` (easyfea_b200.dist.RowComm) supplies the halo
     exchange and scalar all-reduces for row-sharded runs.
 
-    `fused=True` (default): the iterations run as three kernels each, enqueued `check_every` at a time by
-    `efb_pcg_iterate`; reductions and the halo exchange go through peer memory inside those kernels.  `fused=False` keeps
+    `fused=True` (default): the iterations run on the device, reductions and the halo exchange go through peer memory
+    inside the kernels: three kernels per iteration, enqueued `check_every` at a time (`efb_pcg_iterate`).  With
+    `persistent=True` (matrices assembled by this library) ONE cooperative kernel iterates until convergence instead
+    (`efb_pcg_solve_persistent`: grid barriers between the steps, every rank leaves in the same iteration, no host round
+    trip at all); measured equal on small systems and ~8 % slower on large ones (profiles/README.md), hence opt-in.
+    `fused=False` keeps
     one collective call per exchange (NCCL through torch.distributed) and one kernel per vector operation — the baseline
     the fused path is measured against (bench.py) and checked against (tests).
     """
@@ -151,13 +155,21 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
         if comm is not None:
             comm.halo_exchange(p_full)
         ws.ctrl[ws.rz_off:ws.rz_off + 1].copy_(scal[2:3])
+        ws.ctrl[ws.rr_off:ws.rr_off + 1].copy_(scal[3:4])
         S = _system_struct(A, nrows, mask, inv_diag, x, r, z, Ap, partials)
+        use_persistent = bool(persistent) and S.kind == 1
         while rr > target and it < maxiter:
-            k = min(int(check_every), maxiter - it)
-            _lib.call("efb_pcg_iterate", ctypes.byref(S), ctypes.byref(ws.peer), k, it, st())
+            if use_persistent:
+                _lib.call("efb_pcg_solve_persistent", ctypes.byref(S), ctypes.byref(ws.peer), it, maxiter - it, float(target), st())
+                rr, err, k = ws.status()
+                if k == 0 and not err:
+                    raise _lib.EfbError("PCG: the persistent kernel made no progress")
+            else:
+                k = min(int(check_every), maxiter - it)
+                _lib.call("efb_pcg_iterate", ctypes.byref(S), ctypes.byref(ws.peer), k, it, st())
+                rr, err, _ = ws.status()
             ws.advance(k)
             it += k
-            rr, err = ws.status()
             if err:
                 flags = ws.ctrl[:16].cpu().numpy().view("uint64").tolist()
                 raise _lib.EfbError(f"PCG: a wait on a neighbour rank timed out (peer process lost?) at iteration <= {it}: reduction "
@@ -182,4 +194,5 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
             if rr != rr:
                 raise _lib.EfbError("PCG broke down (NaN residual): matrix not SPD on the free dofs?")
     rel = (rr / bnorm2) ** 0.5
-    return x.clone(), {"iterations": it, "rel_residual": rel, "converged": rel <= tol, "fused": ws is not None}
+    return x.clone(), {"iterations": it, "rel_residual": rel, "converged": rel <= tol, "fused": ws is not None,
+                       "persistent": ws is not None and use_persistent}

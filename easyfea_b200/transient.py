@@ -104,7 +104,7 @@ class TransientSolve:
         self.bc = Dirichlet(n)
         self.K = self.C = self.M = None
         self.algo = "elliptic"
-        self.pcg_tol, self.pcg_maxiter, self.pcg_fused = 1e-10, None, True
+        self.pcg_tol, self.pcg_maxiter, self.pcg_fused, self.pcg_persistent = 1e-10, None, True, False
         self.info = {}
 
     # -- systems ---------------------------------------------------------------------------------------------------
@@ -212,7 +212,8 @@ class TransientSolve:
         x0 = self.a.clone() if explicit else self.u.clone()  # the unknown of euler_explicit is a^n, zero on constrained dofs
         _apply(x0, dofs, torch.zeros_like(vals) if explicit else vals)
         s.refresh_halo(x0, d)
-        x, info = pcg(A, b, x0=x0, free_mask=mask, tol=self.pcg_tol, maxiter=self.pcg_maxiter, comm=s.comm(d), fused=self.pcg_fused)
+        x, info = pcg(A, b, x0=x0, free_mask=mask, tol=self.pcg_tol, maxiter=self.pcg_maxiter, comm=s.comm(d), fused=self.pcg_fused,
+                      persistent=self.pcg_persistent)
         self.info = info
         x0[:n_own] = x
         s.refresh_halo(x0, d)

@@ -238,12 +238,20 @@ typedef struct efb_pcg_peer {
 } efb_pcg_peer;
 
 /* a region starts with a control block of efb_pcg_ctrl_bytes() bytes (zero it once); offsets of the device scalars
- * inside it (in doubles): out[0] = rz[2] ping-pong, out[1] = rr, out[2] = error flag (as uint32 index) */
+ * inside it: out[0] = rz[2] ping-pong and out[1] = rr (in doubles), out[2] = error flag (uint32 index),
+ * out[3] = iterations run by the last persistent launch (uint64 index) */
 int efb_pcg_ctrl_bytes(void);
-int efb_pcg_ctrl_layout(int32_t* out3);
+int efb_pcg_ctrl_layout(int32_t* out4);
 /* enqueue n_iters iterations starting at iteration `it0` (p_it lives in p buffer it & 1, r.z of it in rz[it & 1]).
  * The caller advances peer->ar_seq by 2*n_iters and halo_seq by n_iters afterwards. */
 int efb_pcg_iterate(const efb_pcg_system* sys, const efb_pcg_peer* peer, int n_iters, int64_t it0, void* stream);
+/* Persistent form for node-block systems (kind 1): ONE cooperative kernel runs iterations it0, it0+1, ... until
+ * r.r <= target_rr or max_iters are done; the three steps are separated by grid barriers, every CTA folds the partials
+ * itself, and every CTA of every rank leaves in the same iteration (same bits everywhere) — no host round trip and no
+ * launch per iteration.  sys->partials holds efb_pcg_partials_size() doubles.  Afterwards the control block holds the
+ * iteration count (layout out[3]) and r.r; the caller advances ar_seq by 2*iterations and halo_seq by iterations. */
+int efb_pcg_solve_persistent(const efb_pcg_system* sys, const efb_pcg_peer* peer, int64_t it0, int64_t max_iters,
+                             double target_rr, void* stream);
 
 /* peer-mappable device memory (plain cudaMalloc so that cudaIpc can export it) */
 int efb_peer_alloc(int64_t bytes, void** ptr);                 /* zero-filled */

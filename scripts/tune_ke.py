@@ -63,6 +63,16 @@ def main():
         t = timeit(lambda: pat.replay([Ke], out=data), reps)
         out["replay_ms"] = t
         out["replay_GBps"] = (Ne * ndof * ndof * 8 + Ne * dg.nPe**2 * 4 + pat.nnz * 8) / t / 1e6
+    if os.environ.get("TUNE_MASS", "0") == "1":
+        Me = dv.empty((Ne, ndof, ndof))
+        out["Me_vec_ms"] = timeit(lambda: operators.mass_Me_dev(g, 2.0, dim, "mass", 1.0, out=Me), reps)
+        del Me
+        Ms = dv.empty((Ne, dg.nPe, dg.nPe))
+        out["Me_scalar_ms"] = timeit(lambda: operators.mass_Me_dev(g, 2.0, 1, "mass", 1.0, out=Ms), reps)
+        out["Kdiff_scalar_ms"] = timeit(lambda: operators.diffusion_Ke_dev(g, None, 1.5, "rigi", 1.0, out=Ms), reps)
+        pat1 = assembly.Assembler().pattern(1, True, coords.shape[0], (g,))
+        d1 = dv.empty((pat1.nnz,))
+        out["replay_scalar_ms"] = timeit(lambda: pat1.replay([Ms], out=d1), reps)
     if os.environ.get("TUNE_SPMV", "0") == "1":
         from easyfea_b200 import solver
         from easyfea_b200.assembly import DeviceCsr

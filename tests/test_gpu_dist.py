@@ -40,10 +40,16 @@ def _worker(rank, world, port, out):
         es.bc.add(loc[plane == 0], [0, 0, 0], [0, 1, 2], 3)
         es.bc.add(loc[plane == world * n[2]], [0.05], [2], 3)
         u, info = es.solve(tol=1e-10)  # fused iterations: reductions + halo pushes through peer memory
-        assert info["converged"] and info["fused"], info
+        assert info["converged"] and info["fused"] and not info["persistent"], info
         u_peer = u[: part.n_owned * 3].cpu().numpy()
         u2, info2 = es.solve(tol=1e-10)  # second solve on the same communicator (sequence numbers carry on), warm start
         assert info2["converged"], info2
+        es.u.zero_()
+        es.pcg_persistent = True  # one cooperative kernel per solve, same peer-memory exchanges
+        u4, info4 = es.solve(tol=1e-10)
+        es.pcg_persistent = False
+        assert info4["converged"] and info4["fused"] and info4["persistent"], info4
+        assert np.linalg.norm(u4[: part.n_owned * 3].cpu().numpy() - u_peer) <= 1e-8 * np.linalg.norm(u_peer)
         es.u.zero_()
         es.pcg_fused = False  # NCCL send/recv + all-reduce per iteration: same iterates up to summation order
         u3, info3 = es.solve(tol=1e-10)

@@ -155,6 +155,14 @@ def test_pcg_elastic_cube(efb):
     assert np.linalg.norm(x2.cpu().numpy() - x) / np.linalg.norm(x) < 1e-5
     x2b, info2b = efb.solver.pcg(K, b, x0=x0, free_mask=~known, tol=1e-8, maxiter=5000)
     assert info2b["iterations"] == info["iterations"] and np.array_equal(x2b.cpu().numpy(), x)
+    # opt-in: ONE persistent cooperative kernel per solve; same iterates as the three-kernel form up to summation order
+    assert not info["persistent"]
+    x2c, info2c = efb.solver.pcg(K, b, x0=x0, free_mask=~known, tol=1e-8, maxiter=5000, persistent=True)
+    assert info2c["fused"] and info2c["persistent"] and abs(info2c["iterations"] - info["iterations"]) <= 25
+    assert np.linalg.norm(x2c.cpu().numpy() - x) / np.linalg.norm(x) < 1e-5
+    # maxiter is honoured exactly by the persistent kernel
+    _, info2d = efb.solver.pcg(K, b, x0=x0, free_mask=~known, tol=1e-30, maxiter=17, persistent=True)
+    assert info2d["iterations"] == 17 and not info2d["converged"]
     # generic CSR form of the fused SpMV (no node graph) and a system without a mask
     from easyfea_b200.assembly import DeviceCsr
 
@@ -203,7 +211,7 @@ def test_spmv_nodeblock_matches_scipy(efb, elemType, dof_n):
     partials = dv.empty((_lib.load().efb_pcg_partials_size(),))
     y = efb.solver.spmv(A, xd, mask=md, partials=partials)
     assert rel_err(y.cpu().numpy(), ref) < 1e-13
-    nblk = partials.numel() // 2
+    nblk = partials.numel() // 3  # efb_pcg_partials_size() = 3 x the number of reduction CTAs
     assert abs(float(partials[:nblk].sum()) - float(x @ ref)) <= 1e-10 * np.abs(x * ref).sum()
     y_csr = efb.solver.spmv(DeviceCsr(A.indptr, A.indices, A.data, A.shape), xd, mask=md)
     assert rel_err(y.cpu().numpy(), y_csr.cpu().numpy()) < 1e-13
