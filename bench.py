@@ -409,37 +409,42 @@ def pcg_leg(args, g, part, pat, data, world, dist):
 
 
 def phase_field_leg(args, rank, world, dist):
-    """BASELINE config 3: 2D shear test, TRI3 2*n^2 elements, Miehe split, AT2 — seconds per staggered iteration
-    (damage assembly + solve, displacement assembly + solve) with the mesh partitioned element-wise over the ranks."""
+    """BASELINE config 3 (default): 2D shear test, TRI3 2*n^2 elements, Miehe split, AT2; `--pf-config 4`: 3D notched specimen,
+    TETRA4 6*n^3 elements (Kuhn split of n^3 cubes), He split, AT2 — seconds per staggered iteration (damage assembly + solve,
+    displacement assembly + solve) with the mesh partitioned element-wise over the ranks."""
     import torch
 
     from easyfea_b200 import dist as efd
     from easyfea_b200 import mesh, meshgen, phasefield, staggered
 
-    n = args.pf_n
+    cfg4 = args.pf_config == 4
+    et, dim, split = ("TETRA4", 3, "He") if cfg4 else ("TRI3", 2, "Miehe")
+    n = args.pf_n if args.pf_n else (119 if cfg4 else 1000)
     L, l0 = 1e-3, 1e-5 * max(1.0, 1000.0 / n)  # l0 = 2 h like examples/PhaseField/Shear.py (clC = l0/2 there)
-    lattice, connect = meshgen.structured_mesh("TRI3", n, lengths=(L, L))
-    coords, _ = meshgen.structured_mesh("TRI3", n, lengths=(L, L), jitter=0.15, seed=1)
-    Nn = coords.shape[0]
+    lengths = (L,) * dim
+    lattice, connect = meshgen.structured_mesh(et, n, lengths=lengths)
+    coords, _ = meshgen.structured_mesh(et, n, lengths=lengths, jitter=0.15, seed=1)
+    Nn, Ne = coords.shape[0], connect.shape[0]
     if world > 1:
         part = efd.Partition.from_global(connect, Nn, world, rank)
-        g = mesh.ElemGroup("TRI3", part.connect, coords[part.nodes], all_nodes_used=True)
+        g = mesh.ElemGroup(et, part.connect, coords[part.nodes], all_nodes_used=True)
         sysm = staggered.LocalSystem(g, part, lambda p, d: efd.RowComm(p, d))
         nodes = part.nodes
     else:
-        g = mesh.ElemGroup("TRI3", connect, coords, all_nodes_used=True)
+        g = mesh.ElemGroup(et, connect, coords, all_nodes_used=True)
         sysm = staggered.LocalSystem(g)
         nodes = np.arange(Nn)
-    pfm = phasefield.PhaseFieldModel(phasefield.IsotropicMaterial(2, 210e9, 0.3, planeStress=False, thickness=1.0), "Miehe",
+    del connect
+    pfm = phasefield.PhaseFieldModel(phasefield.IsotropicMaterial(dim, 210e9, 0.3, planeStress=False, thickness=1.0), split,
                                      "AT2", 2.7e3, l0)
     simu = staggered.PhaseFieldStaggered(sysm, pfm, pcg_tol=1e-8, pcg_maxiter=args.pf_maxiter)
     simu.pcg_fused = not args.pf_unfused
-    x, y = lattice[nodes, 0], lattice[nodes, 1]
-    tol = 1e-12
+    ix, iy = np.rint(lattice[nodes, 0] / L * n).astype(np.int64), np.rint(lattice[nodes, 1] / L * n).astype(np.int64)
     loc = np.arange(nodes.size)
-    simu.add_dirichlet(loc[(np.abs(y - L / 2) < tol) & (x <= L / 2 + tol)], [1], [0], problemType="damage")
-    simu.add_dirichlet(loc[np.abs(y - L) < tol], [8e-6, 4e-6], [0, 1])
-    simu.add_dirichlet(loc[np.abs(y) < tol], [0, 0], [0, 1])
+    comps = list(range(dim))
+    simu.add_dirichlet(loc[(iy == n // 2) & (ix <= n // 2)], [1], [0], problemType="damage")  # crack / notch as d = 1
+    simu.add_dirichlet(loc[iy == n], [8e-6, 4e-6, 0.0][:dim], comps)
+    simu.add_dirichlet(loc[iy == 0], [0.0] * dim, comps)
     simu.iterate()  # warm-up iteration (pattern build, first solves from zero fields)
     if dist is not None:
         dist.barrier()
@@ -456,9 +461,10 @@ def phase_field_leg(args, rank, world, dist):
         t = torch.tensor([ms], dtype=torch.float64, device=conv.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    return {"workload": f"BASELINE config 3: TRI3 shear test 2*{n}^2 = {2 * n * n} elements, Miehe, AT2, strong-scaled over "
-                        f"{world} GPU(s)", "s_per_iter": ms / its / 1e3, "iterations_timed": its,
-            "pcg_iters_damage": simu.info["damage"]["iterations"], "pcg_iters_elastic": simu.info["elastic"]["iterations"],
+    return {"workload": f"BASELINE config {4 if cfg4 else 3}: {et} {'notched specimen' if cfg4 else 'shear test'}, {Ne} elements, "
+                        f"{Nn} nodes, {split}, AT2, strong-scaled over {world} GPU(s)", "s_per_iter": ms / its / 1e3,
+            "iterations_timed": its, "pcg_iters_damage": simu.info["damage"]["iterations"],
+            "pcg_iters_elastic": simu.info["elastic"]["iterations"],
             "pcg_converged": bool(simu.info["damage"]["converged"] and simu.info["elastic"]["converged"]),
             "pcg_fused": bool(simu.pcg_fused),
             "last_damage_increment": float(conv.item()), "max_damage": float(dmax.item())}
@@ -588,7 +594,8 @@ def main():
     ap.add_argument("--no-solve", action="store_true", help="skip the Jacobi-PCG extra")
     ap.add_argument("--pcg-iters", type=int, default=50)
     ap.add_argument("--no-pf", action="store_true", help="skip the phase-field staggered-iteration extra")
-    ap.add_argument("--pf-n", type=int, default=1000, help="TRI3 cells per side (1000 -> 2.0 M elements, config 3)")
+    ap.add_argument("--pf-config", type=int, default=3, choices=[3, 4], help="phase-field extra: config 3 (TRI3, Miehe) or 4 (TETRA4, He)")
+    ap.add_argument("--pf-n", type=int, default=0, help="cells per side (default: 1000 -> 2.0 M TRI3; config 4: 119 -> 10.1 M TETRA4)")
     ap.add_argument("--pf-iters", type=int, default=2)
     ap.add_argument("--pf-maxiter", type=int, default=20000)
     ap.add_argument("--no-transient", action="store_true", help="skip the HEXA27 transient extra (config 5)")
