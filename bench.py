@@ -517,6 +517,7 @@ def transient_leg(args, rank, world, dist):
     box = {}
 
     def build_dyn():
+        box.pop("dyn", None)  # free the previous system first: K, C, M of this mesh are 3 x 3 GB
         box["dyn"] = transient.TransientSolve.elastodynamic(sysm, _material_C(), 7.8e-3, coefM=0.1, coefK=1e-5)
 
     out["elastodynamic_assembly_ms"] = timed(build_dyn, 2)  # K_e, M_e (27 Gauss points), two CSR replays, Rayleigh C
@@ -531,6 +532,7 @@ def transient_leg(args, rank, world, dist):
     del dyn, box["dyn"]
 
     def build_th():
+        box.pop("th", None)
         box["th"] = transient.TransientSolve.thermal(sysm, 1.0, 1.0)
 
     out["thermal_assembly_ms"] = timed(build_th, 2)

@@ -19,10 +19,29 @@ from .assembly import DeviceCsr
 
 
 def lanes_per_row(nnz: int, nrows: int) -> int:
+    """lanes cooperating on one row of the generic CSR product"""
     avg = nnz / max(nrows, 1)
     for lanes in (4, 8, 16):
         if avg <= 2 * lanes:
             return lanes
+    return 32
+
+
+def lanes_per_node(nnz: int, nrows: int) -> int:
+    """lanes cooperating on one node of the node-block product.  Measured on B200 (profiles/README.md, lanes A/B): few lanes
+    per node keep more independent nodes in flight per warp and let the two prefetched steps cover most of a short row —
+    TETRA4 d=3 (45 entries per row) 2.9 TB/s with 32 lanes, 4.7 TB/s with 8; HEXA8 d=1 (27) 2.8 -> 4.6 TB/s with 4."""
+    import os
+
+    if os.environ.get("EFB_SPMV_LANES"):  # dev/tuning knob
+        return int(os.environ["EFB_SPMV_LANES"])
+    avg = nnz / max(nrows, 1)
+    if avg <= 32:
+        return 4
+    if avg <= 128:
+        return 8
+    if avg <= 384:
+        return 16
     return 32
 
 
@@ -35,7 +54,7 @@ def spmv(A: DeviceCsr, x: torch.Tensor, y: torch.Tensor = None, row_offset: int 
         adjptr, adj, d, max_deg = ng  # node-block product: the column structure is read from the node adjacency
         n_nodes = nrows // d
         _lib.call("efb_spmv_nodeblock", n_nodes, d, dv.ptr(adjptr), dv.ptr(adj), dv.ptr(A.data), dv.ptr(x), int(row_offset),
-                  dv.ptr(mask), dv.ptr(y), dv.ptr(partials), lanes_per_row(A.nnz, nrows), dv.stream_ptr())
+                  dv.ptr(mask), dv.ptr(y), dv.ptr(partials), lanes_per_node(A.nnz, nrows), dv.stream_ptr())
         return y
     _lib.call("efb_spmv_csr", nrows, A.index_bytes, dv.ptr(A.indptr), dv.ptr(A.indices), dv.ptr(A.data), dv.ptr(x), int(row_offset),
               dv.ptr(mask), dv.ptr(y), dv.ptr(partials), lanes_per_row(A.nnz, nrows), dv.stream_ptr())
@@ -50,10 +69,11 @@ def _system_struct(A: DeviceCsr, nrows, mask, inv_diag, x, r, z, Ap, partials) -
         adjptr, adj, d, max_deg = ng
         S.kind, S.dof_n, S.index_bytes = 1, d, 0
         S.indptr, S.indices = adjptr.data_ptr(), adj.data_ptr()
+        S.lanes = lanes_per_node(A.nnz, nrows)
     else:
         S.kind, S.dof_n, S.index_bytes = 0, 0, A.index_bytes
         S.indptr, S.indices = A.indptr.data_ptr(), A.indices.data_ptr()
-    S.lanes = lanes_per_row(A.nnz, nrows)
+        S.lanes = lanes_per_row(A.nnz, nrows)
     S.data = A.data.data_ptr()
     S.free_mask = mask.data_ptr() if mask is not None else None
     S.inv_diag, S.x, S.r, S.z, S.Ap, S.partials = (t.data_ptr() for t in (inv_diag, x, r, z, Ap, partials))
