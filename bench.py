@@ -146,6 +146,43 @@ class CpuSample:
         return time.perf_counter() - t0
 
 
+def _cpu_worker(n_sample, warm, passes, barrier, out):
+    """one host process of the CPU arm: its own sample mesh, `passes` timed steps after a common barrier"""
+    try:
+        smp = CpuSample(n_sample)
+        for _ in range(warm):
+            smp.step()
+        barrier.wait(timeout=600)
+        t0 = time.perf_counter()
+        for _ in range(passes):
+            smp.step()
+        out.put((time.perf_counter() - t0, smp.units, smp.pattern_s))
+    except Exception as exc:  # pragma: no cover
+        out.put((float("nan"), 0, repr(exc)))
+
+
+def cpu_arm(n_sample: int, warm: int, passes: int, procs: int = 0):
+    """The reference's CPU path on ALL host cores: `procs` processes (default: one per core), each integrating and assembling
+    its own n_sample^3-element chunk — what an MPI-partitioned EasyFEA run does for this path (docs/howto/use_mpi.md); NumPy's
+    einsum/bincount are single-threaded.  Returns (GP/s over all processes, seconds per step, processes, pattern seconds)."""
+    import multiprocessing as mp
+
+    procs = procs or (os.cpu_count() or 1)
+    ctx = mp.get_context("spawn")  # the parent may hold a CUDA context
+    barrier, out = ctx.Barrier(procs), ctx.Queue()
+    ps = [ctx.Process(target=_cpu_worker, args=(n_sample, warm, passes, barrier, out)) for _ in range(procs)]
+    for p in ps:
+        p.start()
+    res = [out.get(timeout=1200) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+    bad = [r for r in res if not r[1]]
+    if bad:
+        raise RuntimeError(f"CPU arm worker failed: {bad[0][2]}")
+    wall = max(r[0] for r in res)
+    return sum(r[1] for r in res) * passes / wall, wall / passes, procs, float(np.mean([r[2] for r in res]))
+
+
 def blas_threads() -> int:
     try:
         from threadpoolctl import threadpool_info
@@ -161,20 +198,17 @@ def run_reference(args):
         return
     t_all0 = time.perf_counter()
     n_sample = args.cpu_sample
-    smp = CpuSample(n_sample)
-    for _ in range(args.warmup):
-        smp.step()
-    secs = [smp.step() for _ in range(args.steps)]
-    dt = float(np.mean(secs))
-    value = smp.units / dt
-    sample = f"HEXA8 {n_sample}^3 = {n_sample**3} elements x 8 Gauss points per step (same jittered-cube family)"
+    value, dt, procs, pattern_s = cpu_arm(n_sample, max(args.warmup, 1), args.steps, args.cpu_procs)
+    units_step = procs * n_sample**3 * 8
+    sample = (f"{procs} host processes x HEXA8 {n_sample}^3 = {n_sample**3} elements x 8 Gauss points per step "
+              f"(same jittered-cube family; one process per core, like an MPI-partitioned run of the reference)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "GP/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"BASELINE config 2: HEXA8 elastic cube, K_e (8 GP) + CSR replay, CPU sample of {n_sample}^3 "
-                                   f"elements per step, E={E_MOD}, v={NU}"},
-            "cpu_baseline": {"value": value, "unit": "GP/s", "cores": blas_threads(), "kind": "port", "sample": sample,
-                             "host_cores": os.cpu_count(), "pattern_build_s": smp.pattern_s},
+            "config": {"workload": f"BASELINE config 2: HEXA8 elastic cube, K_e (8 GP) + CSR replay, CPU sample of {procs} x "
+                                   f"{n_sample}^3 elements per step, E={E_MOD}, v={NU}"},
+            "cpu_baseline": {"value": value, "unit": "GP/s", "cores": procs, "kind": "port", "sample": sample,
+                             "host_cores": os.cpu_count(), "pattern_build_s": pattern_s, "units_per_step": units_step},
             "e2e": {"value": value, "unit": "GP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t_all0}
     print(json.dumps(line), flush=True)
@@ -328,13 +362,12 @@ def run_ours(args):
         # ---- e2e through the host-buffer boundary (pinned in, pinned out) ----
         line["e2e"] = e2e_leg(args, g, part, C, pat, Ke, data, world)
         if world == 1 and not args.no_cpu:
-            smp = CpuSample(args.cpu_sample)
-            smp.step()
-            secs = [smp.step() for _ in range(3)]
-            line["cpu_baseline"] = {"value": smp.units / float(np.mean(secs)), "unit": "GP/s", "cores": blas_threads(),
-                                    "kind": "port", "host_cores": os.cpu_count(), "pattern_build_s": smp.pattern_s,
-                                    "sample": f"HEXA8 {args.cpu_sample}^3 = {args.cpu_sample**3} elements, cold geometry + K_e "
-                                              f"einsum + bincount replay, mean of 3 passes of {np.mean(secs):.2f} s"}
+            v, dt, procs, pattern_s = cpu_arm(args.cpu_sample, 1, 3, args.cpu_procs)
+            line["cpu_baseline"] = {"value": v, "unit": "GP/s", "cores": procs, "kind": "port", "host_cores": os.cpu_count(),
+                                    "pattern_build_s": pattern_s,
+                                    "sample": f"{procs} host processes x HEXA8 {args.cpu_sample}^3 = {args.cpu_sample**3} elements, cold "
+                                              f"geometry + K_e einsum + bincount replay, 3 passes of {dt:.2f} s each (one process "
+                                              f"per core, like an MPI-partitioned run of the reference)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -591,6 +624,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", "--cells", dest="n", type=int, default=200, help="cells per side of the owned HEXA8 cube (200 -> 8.0 M elements)")
     ap.add_argument("--cpu-sample", type=int, default=32, help="cells per side of the CPU sample (32 -> 32 768 elements)")
+    ap.add_argument("--cpu-procs", type=int, default=0, help="host processes of the CPU arm (0 = one per core)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-solve", action="store_true", help="skip the Jacobi-PCG extra")
