@@ -20,14 +20,21 @@ static GroupView view_of(const efb_group* g) {
     return v;
 }
 
-// elements per CTA: ~256 threads, and at most ~72 KB of shared memory so that 3 CTAs fit an SM
+// elements per CTA: ~256 threads, and at most ~72 KB of shared memory so that 3 CTAs fit an SM; high-order elements
+// (HEXA27: 34 KB of per-element geometry) would be left with one or two elements = a warp or two per CTA, so the budget
+// grows to 2 and then 1 CTA per SM until the CTA has at least 4 warps
 template <int DIM, int NPE>
-static int elems_per_block(int TPE, int nPg, int extra) {
-    int epb = 256 / TPE;
-    if (epb < 1) epb = 1;
-    if (epb > 16) epb = 16;
-    while (epb > 1 && SmemMap<DIM, NPE>(nPg, epb, extra).total() * sizeof(double) > 72 * 1024) --epb;
-    return epb;
+static int elems_per_block(int TPE, int nPg, int extra, bool grad = true) {
+    int best = 1;
+    for (const size_t budget : {72 * 1024, 110 * 1024, 220 * 1024}) {
+        int epb = 256 / TPE;
+        if (epb < 1) epb = 1;
+        if (epb > 16) epb = 16;
+        while (epb > 1 && SmemMap<DIM, NPE>(nPg, epb, extra, grad).total() * sizeof(double) > budget) --epb;
+        best = epb;
+        if (epb * TPE >= 128) break;
+    }
+    return best;
 }
 
 static int validate(const efb_group* g) {
@@ -481,8 +488,8 @@ __global__ void __launch_bounds__(256) k_scalar(GroupView g, ScalarOp op, int EP
 
 template <int DIM, int NPE>
 static int launch_scalar(const efb_group* g, const ScalarOp& op, cudaStream_t st, const char* what) {
-    const int TPE = NPE, EPB = elems_per_block<DIM, NPE>(TPE, g->nPg, NPE * NPE + NPE);
-    const SmemMap<DIM, NPE> sm(g->nPg, EPB, NPE * NPE + NPE);
+    const int TPE = NPE, EPB = elems_per_block<DIM, NPE>(TPE, g->nPg, NPE * NPE + NPE, op.has_k);
+    const SmemMap<DIM, NPE> sm(g->nPg, EPB, NPE * NPE + NPE, op.has_k);
     const size_t bytes = sizeof(double) * sm.total();
     if (ensure_smem(k_scalar<DIM, NPE>, bytes)) return 1;
     const long long nblk = (g->Ne + EPB - 1) / EPB;

@@ -30,7 +30,8 @@ struct SmemMap {
     // 16-byte loads
     static constexpr int GS = (DIM == 3) ? 4 : 2;
     int nPg, EPB, extra;  // extra = op-specific doubles per element
-    EFB_HD SmemMap(int nPg_, int EPB_, int extra_) : nPg(nPg_), EPB(EPB_), extra(extra_) {}
+    bool grad;            // false: no gN table (operators that need no physical gradients, e.g. the mass matrix)
+    EFB_HD SmemMap(int nPg_, int EPB_, int extra_, bool grad_ = true) : nPg(nPg_), EPB(EPB_), extra(extra_), grad(grad_) {}
     // tables
     EFB_HD int off_dN() const { return 0; }
     EFB_HD int off_N() const { return nPg * DIM * NPE; }
@@ -43,7 +44,7 @@ struct SmemMap {
     EFB_HD int o_det() const { return o_Fi() + nPg * DIM * DIM; }
     EFB_HD int o_wJ() const { return o_det() + nPg; }
     EFB_HD int o_gN() const { return (o_wJ() + nPg + 1) & ~1; }  // 16-byte aligned
-    EFB_HD int o_extra() const { return o_gN() + nPg * NPE * GS; }
+    EFB_HD int o_extra() const { return o_gN() + (grad ? nPg * NPE * GS : 0); }
     // even stride (keeps 16-byte alignment) that is not a multiple of 16 doubles, so the same field of the elements
     // sharing a warp falls in different banks
     EFB_HD int per_elem() const {
@@ -890,7 +891,7 @@ struct ScalarOp {
 template <int DIM, int NPE>
 EFB_D void scalar_block(const GroupView& g, const ScalarOp& op, int EPB, long long blockId, int nthreads, double* smem) {
     const int nPg = g.nPg;
-    const SmemMap<DIM, NPE> sm(nPg, EPB, NPE * NPE + NPE);
+    const SmemMap<DIM, NPE> sm(nPg, EPB, NPE * NPE + NPE, op.has_k);
     const long long e0 = blockId * EPB;
     const double* Nt = smem + sm.off_N();
     geometry_phases<DIM, NPE>(g, sm, e0, NPE, nthreads, smem, op.has_k);
