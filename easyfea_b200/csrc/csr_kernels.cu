@@ -467,6 +467,9 @@ struct ReplayTma {
     static constexpr int R = R0 < 3 ? 3 : (R0 > 24 ? 24 : R0);     // slots per warp (~5 KB: 8 HEXA8 rows; a deeper ring costs occupancy and is slower, profiles/README.md)
 };
 
+#ifndef EFB_REPLAY_ELECT
+#define EFB_REPLAY_ELECT elect_one()  // (lane == 0) is the form that makes ptxas uniformise every bulk-copy operand
+#endif
 #ifndef EFB_REPLAY_MINB
 #define EFB_REPLAY_MINB 4
 #endif
@@ -513,7 +516,7 @@ __global__ void __launch_bounds__(256, EFB_REPLAY_MINB)
     auto issue = [&]() {
         if (si < s_hi) {  // warp-uniform
             const long long q = __shfl_sync(FULL, qa, (int)(si - qbase));
-            if (lane == 0) {
+            if (EFB_REPLAY_ELECT) {
                 double* slot = ring + islot * SLOT;
                 mbar_expect_tx(bars + islot, RT::TX);
                 bulk_load(slot, data + q * (long long)NV, NV * 8, bars + islot);

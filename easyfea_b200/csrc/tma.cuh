@@ -31,6 +31,20 @@ __device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, unsigned
                  : "memory");
 }
 
+// one lane of a converged warp; ptxas then knows the bulk-copy operands are warp-uniform and emits UBLKCP without the
+// vote-and-loop uniformisation it wraps around copies issued from `if (lane == 0)` code
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 }  // namespace efb
