@@ -256,6 +256,23 @@ def _pad256(nbytes: int) -> int:
     return (int(nbytes) + 255) // 256 * 256
 
 
+def peer_push_plan(comm: "RowComm", recv_lo_of_rank):
+    """Who stores what where in the peer-memory halo exchange: for every neighbour this rank sends to, the range of
+    `comm.send_idx` it gets and the first entry of this rank's segment inside THAT rank's `[owned | halo]` vector
+    (`recv_lo_of_rank[q]` = {source rank: first entry of its segment on rank q}, gathered from all ranks).
+    Returns (send_rank, send_ptr, send_dst, recv_rank) as Python lists."""
+    rank = comm.part.rank
+    send_rank = [int(q) for q in comm.peers_send]
+    send_ptr = [int(v) for v in comm.send_ptr]
+    send_dst = []
+    for q in send_rank:
+        their = recv_lo_of_rank[q]
+        assert rank in their, "a neighbour this rank sends to does not expect a segment from it"
+        send_dst.append(int(their[rank]))
+    recv_rank = [int(q) for q, _, _ in comm.recv_segments]
+    return send_rank, send_ptr, send_dst, recv_rank
+
+
 class LocalWorkspace:
     """Single-GPU workspace of `efb_pcg_iterate`: control block + two p buffers in ordinary device memory."""
 
@@ -343,17 +360,14 @@ class PeerWorkspace(LocalWorkspace):
                 self._opened.append(int(ptr.value))
                 P.base[q] = int(ptr.value)
             P.pbuf_off[q][0], P.pbuf_off[q][1] = int(off[0]), int(off[1])
-        P.n_send = len(comm.peers_send)
-        for i, q in enumerate(comm.peers_send):
-            P.send_rank[i] = int(q)
-            P.send_ptr[i] = int(comm.send_ptr[i])
-            their = gathered[q][2]
-            assert rank in their, "a neighbour this rank sends to does not expect a segment from it"
-            P.send_dst[i] = int(their[rank])
-        P.send_ptr[P.n_send] = int(comm.send_ptr[-1])
-        P.n_recv = len(comm.recv_segments)
-        for i, (q, _, _) in enumerate(comm.recv_segments):
-            P.recv_rank[i] = int(q)
+        send_rank, send_ptr, send_dst, recv_rank = peer_push_plan(comm, [g[2] for g in gathered])
+        P.n_send, P.n_recv = len(send_rank), len(recv_rank)
+        for i, q in enumerate(send_rank):
+            P.send_rank[i], P.send_dst[i] = q, send_dst[i]
+        for i, v in enumerate(send_ptr):
+            P.send_ptr[i] = v
+        for i, q in enumerate(recv_rank):
+            P.recv_rank[i] = q
         P.send_idx = comm.send_idx.data_ptr() if comm.send_idx.numel() else None
         P.ar_seq, P.halo_seq = 0, 0
         dist.barrier(group=comm.group)  # every region is mapped before anybody stores into it

@@ -125,6 +125,25 @@ def _worker(rank, world, port, elemType, n, out):
         x[: part.n_owned * dim] = torch.from_numpy(f[: part.n_owned * dim])
         comm.halo_exchange(x)
         assert np.array_equal(x.numpy(), f)
+        # 1b. the same exchange as the peer-memory kernels do it: every rank STORES its interface entries at the planned
+        #     offsets of the neighbours' vectors (emulated here by shipping (destination, offset, values) over gloo)
+        recv_lo = {int(q): int(lo) for q, lo, _ in comm.recv_segments}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, recv_lo)
+        send_rank, send_ptr, send_dst, recv_rank = efd.peer_push_plan(comm, gathered)
+        assert recv_rank == [int(q) for q in part.halo_ranks]
+        idx = comm.send_idx.long().numpy()
+        stores = [(q, send_dst[i], f[idx[send_ptr[i]:send_ptr[i + 1]]]) for i, q in enumerate(send_rank)]
+        all_stores = [None] * world
+        dist.all_gather_object(all_stores, stores)
+        y = f.copy()
+        y[part.n_owned * dim:] = np.nan
+        for src, msgs in enumerate(all_stores):
+            for q, off, vals in msgs:
+                if q == rank:
+                    assert src != rank and np.all(np.isnan(y[off:off + vals.size])), "segments overlap"
+                    y[off:off + vals.size] = vals
+        assert np.array_equal(y, f), "peer stores do not reproduce the halo exchange"
         # 2. distributed matvec == rows of the global matvec
         A = local_block(part, Ke, dim)
         y = A @ x.numpy()
