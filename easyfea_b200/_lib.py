@@ -90,6 +90,10 @@ SIGNATURES = {
     "efb_pcg_update_xr": [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "efb_pcg_update_p": [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "efb_pack_f64": [c_i64, c_vp, c_vp, c_vp, c_vp],
+    "efb_hooke": [c_i64, ctypes.c_int, ctypes.c_int, c_vp, c_vp, ctypes.c_int, c_vp, c_vp],
+    "efb_field_result": [c_i64, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int, c_f64, c_vp, c_vp],
+    "efb_energy_e": [c_i64, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp, c_f64, c_vp, c_vp],
+    "efb_node_values": [c_i64, c_vp, c_vp, ctypes.c_int, c_vp, ctypes.c_int, c_vp, c_vp],
     "efb_lincomb": [c_i64, ctypes.c_int, ctypes.POINTER(c_f64), _PP, c_vp, c_vp],
     "efb_pcg_ctrl_bytes": [],
     "efb_pcg_ctrl_layout": [_I32P],

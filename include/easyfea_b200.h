@@ -266,6 +266,22 @@ int efb_peer_close(void* ptr);
  * (_simu.py:1890-1894), the history terms of the right-hand side (:1777-1853) and the correctors (:1552-1657). */
 int efb_lincomb(int64_t n, int m, const double* coefs, const double* const* vecs_host, double* out, void* stream);
 
+/* ---- post-processing fields ----------------------------------------------------
+ * sigma (Ne,nPg,ns) = C eps, `Calc_Sigma_e_pg` (Models/Elastic/_laws.py:159-185); C_mode 0: (ns,ns), 1: (Ne,ns,ns),
+ * 2: (Ne,nPg,ns,ns) */
+int efb_hooke(int64_t Ne, int nPg, int ns, const double* eps, const double* C, int C_mode, double* sigma, void* stream);
+/* per-element result of a Kelvin-Mandel strain/stress field, `Result_strain_or_stress_field_e` (Models/_utils.py:302-430):
+ * shear components / coef, then the mean over the Gauss points of component `what` (>= 0), of the von Mises value (-1),
+ * or of every component (-2: out is (Ne, ns)) */
+int efb_field_result(int64_t Ne, int nPg, int dim, const double* field, int what, double coef, double* out, void* stream);
+/* Wdef_e (Ne) = scale * sum_p wJ * 1/2 sigma.eps, `_Calc_Psi_Elas` (Simulations/_elastic.py:323-396) */
+int efb_energy_e(int64_t Ne, int nPg, int ns, const double* eps, const double* sigma, const double* wJ, double scale,
+                 double* out, void* stream);
+/* out (Nn, ncols) = element values averaged over the elements around each node, `Mesh.Get_Node_Values`
+ * (FEM/_mesh.py:822-873); rowptr/qlist of the assembly pattern (efb_csr_fill_node_rows), one group of nPe-node elements */
+int efb_node_values(int64_t Nn, const int64_t* rowptr, const int64_t* qlist, int nPe, const double* values_e, int ncols,
+                    double* out, void* stream);
+
 /* send-buffer packing of the PCG halo exchange (row-sharded runs): dst[i] = src[idx[i]] */
 int efb_pack_f64(int64_t n, const int32_t* idx, const double* src, double* dst, void* stream);
 

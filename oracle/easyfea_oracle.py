@@ -760,3 +760,62 @@ class TransientOracle:
         x = solve_dirichlet(self.matrix(), self.rhs(F), np.asarray(dofs_known), x_known)
         self.u, self.v, self.a = self.update(x)
         return self.u
+
+
+# =========================================================================================================
+# post-processing fields
+#                 EasyFEA/Models/_utils.py:302-430, Models/Elastic/_laws.py:159-215, Simulations/_elastic.py:323-396, FEM/_mesh.py:822-873
+# =========================================================================================================
+def hooke(eps, C):
+    """sigma = C eps at every Gauss point (`Calc_Sigma_e_pg`, _laws.py:159-185); C (ns,ns), (Ne,ns,ns) or (Ne,nPg,ns,ns)"""
+    C = np.asarray(C)
+    if C.ndim == 2:
+        return np.einsum("ij,epj->epi", C, eps)
+    if C.ndim == 3:
+        return np.einsum("eij,epj->epi", C, eps)
+    return np.einsum("epij,epj->epi", C, eps)
+
+
+def field_result_e(field_e_pg, result, coef=SQRT2):
+    """`Result_strain_or_stress_field_e` for one group (_utils.py:302-430): shear components / coef, then component, von Mises
+    or the whole field, averaged over the Gauss points.  `result` like "Sxx", "Eyz", "Svm", "Stress", "Strain"."""
+    f = np.array(field_e_pg, dtype=float)
+    ns = f.shape[2]
+    dim = 2 if ns == 3 else 3
+    f[:, :, dim:] *= 1 / coef
+    if dim == 2:
+        xx, yy, xy = (f[:, :, i] for i in range(3))
+        comp = {"xx": xx, "yy": yy, "xy": xy}
+        vm = np.sqrt(xx**2 + yy**2 - xx * yy + 3 * xy**2)
+    else:
+        xx, yy, zz, yz, xz, xy = (f[:, :, i] for i in range(6))
+        comp = {"xx": xx, "yy": yy, "zz": zz, "yz": yz, "xz": xz, "xy": xy}
+        vm = np.sqrt(0.5 * ((xx - yy) ** 2 + (yy - zz) ** 2 + (zz - xx) ** 2 + 6 * (xy**2 + yz**2 + xz**2)))
+    if result in ("Strain", "Stress"):
+        return f.mean(1)
+    if "vm" in result:
+        return vm.mean(1)
+    for key, val in comp.items():
+        if key in result:
+            return val.mean(1)
+    raise ValueError(result)
+
+
+def psi_elas_e(eps, C, wJ, thickness=1.0):
+    """Wdef_e = int 1/2 sigma:eps (`_Calc_Psi_Elas`, _elastic.py:323-396, raw element stresses)"""
+    psi = 0.5 * np.einsum("epi,epi->ep", hooke(eps, C), eps)
+    return (thickness * wJ * psi).sum(1)
+
+
+def node_values(connect, Nn, result_e):
+    """`Mesh.Get_Node_Values` (_mesh.py:822-873): average of the values of the elements around each node"""
+    import scipy.sparse as sp
+
+    Ne, nPe = connect.shape
+    r = np.asarray(result_e, dtype=float)
+    is1d = r.ndim == 1
+    r = r.reshape(Ne, -1)
+    M = sp.csr_matrix((np.ones(Ne * nPe), (connect.ravel(), np.repeat(np.arange(Ne), nPe))), shape=(Nn, Ne))
+    cnt = np.asarray(M.sum(axis=1)).reshape(-1, 1)
+    out = (M @ r) * 1 / np.where(cnt == 0, 1, cnt)
+    return out.ravel() if is1d else out
