@@ -140,6 +140,7 @@ class PhaseFieldStaggered:
         self.bc_d = Dirichlet(system.n_local)
         self.pcg_tol, self.pcg_maxiter = pcg_tol, pcg_maxiter
         self.pcg_fused, self.pcg_persistent = True, False
+        self._updatedDamage = self._updatedDisplacement = False
         self.info = {}
 
     def Bc_Init(self):
@@ -152,13 +153,59 @@ class PhaseFieldStaggered:
         else:
             self.bc_u.add(nodes, values, components, self.dim)
 
+    # -- matrices with the reference's "assemble only when the other field changed" flags ----------------------------
+    # `PhaseField.Get_K_C_M_F` (Simulations/_phasefield.py:248-269): Kd is rebuilt when the displacement changed since its
+    # last assembly, Ku when the damage changed; neither `Bc_Init` nor `Save_Iter` resets the flags.
+    def _get_Kd(self):
+        """`__Construct_Damage_Matrix` (:540-571) -> (Kd, Fd), assembled from the current displacement and the history"""
+        if not self._updatedDamage:
+            s = self.sys
+            Ke, Fe, self.psiP = self.pfm.damage_system_dev(s.group, self.u, self.psiP_old)
+            self._Kd, self._Fd = s.matrix(Ke, 1), s.vector(Fe, 1).clone()  # the pattern reuses its dense vector buffer
+            self._updatedDamage = True
+        return self._Kd, self._Fd
+
+    def _get_Ku(self):
+        """`__Construct_Elastic_Matrix` (:444-482): the split uses the CURRENT displacement, g the current damage"""
+        if not self._updatedDisplacement:
+            Ke = self.pfm.elastic_Ke_dev(self.sys.group, self.u, self.d)
+            self._Ku = self.sys.matrix(Ke, self.dim)
+            self._updatedDisplacement = True
+        return self._Ku
+
+    def Need_Update(self, value=True):
+        self._updatedDamage = self._updatedDisplacement = not value
+
+    def _energy(self, A: DeviceCsr, x_local: torch.Tensor, dof_n: int) -> torch.Tensor:
+        """`_Simu.Calc_Energy` (Simulations/_simu.py:177-210): 1/2 x[owned] . (A[owned] @ x), summed over the ranks (1-element
+        device tensor); the dot product rides in the SpMV (fixed-order partials)."""
+        from . import _lib
+        from .solver import spmv
+
+        nrows = A.indptr.numel() - 1
+        partials = dv.empty((_lib.load().efb_pcg_partials_size(),))
+        y = dv.empty((nrows,))
+        spmv(A, x_local, y, 0, None, partials)
+        e = torch.zeros(1, dtype=torch.float64, device=y.device)
+        _lib.call("efb_pcg_reduce", dv.ptr(partials), 1, dv.ptr(e), dv.stream_ptr())
+        c = self.sys.comm(dof_n)
+        if c is not None:
+            c.all_reduce_sum(e)
+        return 0.5 * e
+
+    def Calc_Psi_Crack(self) -> float:
+        """`_Calc_Psi_Crack` (:802-823): 1/2 d^T Kd d with the current damage matrix"""
+        return float(self._energy(self._get_Kd()[0], self.d, 1).item())
+
+    def Calc_Psi_Elas(self) -> float:
+        """`_Calc_Psi_Elas` (:779-800): 1/2 u^T Ku u"""
+        return float(self._energy(self._get_Ku(), self.u, self.dim).item())
+
     # -- the two sub-problems ----------------------------------------------------------------------------------
     def solve_damage(self):
-        """`__Solve_damage` (:573-578) with `__Construct_Damage_Matrix` (:540-571)."""
+        """`__Solve_damage` (:573-578)"""
         s = self.sys
-        Ke, Fe, self.psiP = self.pfm.damage_system_dev(s.group, self.u, self.psiP_old)
-        K = s.matrix(Ke, 1)
-        F = s.vector(Fe, 1)
+        K, F = self._get_Kd()
         mask, dofs, vals = self.bc_d.device_arrays(s.n_owned)
         _apply(self.d, dofs, vals)
         s.refresh_halo(self.d, 1)
@@ -166,14 +213,14 @@ class PhaseFieldStaggered:
                       fused=self.pcg_fused, persistent=self.pcg_persistent)
         self.d[: s.n_owned] = x
         s.refresh_halo(self.d, 1)
+        self._updatedDisplacement = False  # new damage -> new displacement matrices (:367-368)
         self.info["damage"] = info
         return self.d
 
     def solve_elastic(self):
-        """`__Solve_elastic` with `__Construct_Elastic_Matrix` (:444-482): the split uses the CURRENT displacement."""
+        """`__Solve_elastic`"""
         s, dim = self.sys, self.dim
-        Ke = self.pfm.elastic_Ke_dev(s.group, self.u, self.d)
-        K = s.matrix(Ke, dim)
+        K = self._get_Ku()
         nown = s.n_owned * dim
         mask, dofs, vals = self.bc_u.device_arrays(nown)
         _apply(self.u, dofs, vals)
@@ -183,34 +230,67 @@ class PhaseFieldStaggered:
                       fused=self.pcg_fused, persistent=self.pcg_persistent)
         self.u[:nown] = x
         s.refresh_halo(self.u, dim)
+        self._updatedDamage = False  # new displacement -> new damage matrices (:372-373)
         self.info["elastic"] = info
         return self.u
+
+    def _reduce(self, t: torch.Tensor, op: str) -> torch.Tensor:
+        c = self.sys.comm(1)
+        if c is not None:
+            (c.all_reduce_max if op == "max" else c.all_reduce_sum)(t)
+        return t
 
     def iterate(self):
         """one staggered iteration; returns max |d_new - d_old| over the owned nodes (device scalar, all-reduced)"""
         d_n = self.d[: self.sys.n_owned].clone()
         self.solve_damage()
         self.solve_elastic()
-        conv = (self.d[: self.sys.n_owned] - d_n).abs().max().reshape(1)
-        dmax = self.d[: self.sys.n_owned].max().reshape(1)
-        c = self.sys.comm(1)
-        if c is not None:
-            c.all_reduce_max(conv)
-            c.all_reduce_max(dmax)
+        conv = self._reduce((self.d[: self.sys.n_owned] - d_n).abs().max().reshape(1), "max")
+        dmax = self._reduce(self.d[: self.sys.n_owned].max().reshape(1), "max")
         return conv, dmax
 
     def Solve(self, tolConv=1.0, maxIter=500, convOption=0):
-        """(u, d, converged) — convergence on max |d_np1 - d_n| (convOption 0 of the reference, :372-373, 392-397)."""
+        """(u, d, converged) — `Simulations.PhaseField.Solve` (:300-432).  convOption 0: max |d_np1 - d_n|; 1: relative change
+        of the crack energy; 2: of the total energy (Ambati 2015; no external work: this driver carries no Neumann loads);
+        3: summed relative increments of u and d (Pech 2022)."""
         assert 0 < tolConv <= 1, "tolConv must be between 0 and 1."
         assert maxIter > 1, "Must be > 1."
-        if convOption != 0:
-            raise NotImplementedError("only convOption=0 (damage increment) runs on the device")
-        Niter, converged = 0, False
+        assert convOption in (0, 1, 2, 3)
+        nd, nu = self.sys.n_owned, self.sys.n_owned * self.dim
+        Niter, converged, convIter = 0, False, 0.0
         while not converged and Niter < maxIter:
             Niter += 1
-            conv, dmax = self.iterate()
-            convIter = float(conv.item())
-            converged = tolConv == 1 or float(dmax.item()) == 0 or convIter <= tolConv
+            d_n, u_n = self.d[:nd].clone(), self.u[:nu].clone()
+            if convOption == 1:
+                E_n = self.Calc_Psi_Crack()
+            elif convOption == 2:
+                E_n = self.Calc_Psi_Crack() + self.Calc_Psi_Elas()
+            self.solve_damage()
+            self.solve_elastic()
+            d1, u1 = self.d[:nd], self.u[:nu]
+            if convOption == 0:
+                convIter = float(self._reduce((d1 - d_n).abs().max().reshape(1), "max").item())
+            elif convOption in (1, 2):
+                E1 = self.Calc_Psi_Crack()
+                if convOption == 2:
+                    E1 += self.Calc_Psi_Elas()
+                convIter = abs(E_n - E1) if E1 == 0 else abs((E_n - E1) / E1)
+            else:
+                def rel_sum(new, old):
+                    diff = (new - old).abs()
+                    nz = new != 0
+                    diff = torch.where(nz, diff * (1 / new.abs().clamp_min(1e-300)), diff)
+                    return float(self._reduce(diff.sum().reshape(1), "sum").item())
+
+                convU, convD = rel_sum(u1, u_n), rel_sum(d1, d_n)
+                convIter = max(convD, convU)
+            dmax = float(self._reduce(d1.max().reshape(1), "max").item())
+            if tolConv == 1 or dmax == 0:
+                converged = True
+            elif convOption == 3:
+                converged = convD <= tolConv and convU <= tolConv * 0.999
+            else:
+                converged = convIter <= tolConv
         self.Niter, self.convIter = Niter, convIter
         return self.u, self.d, converged
 

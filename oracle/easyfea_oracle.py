@@ -605,27 +605,89 @@ class StaggeredOracle:
         inv, indices, indptr, nnz = m
         return self.sp.csr_matrix((assemble_replay([Xe], inv, nnz), indices, indptr), shape=(n, n))
 
-    def iterate(self):
-        dim = self.dim
-        u_e = locate_sol_e(self.u, self.connect, dim)
-        Ke, Fe, self.psiP = pf_damage_system(self.geo_m, self.N_m, self.mat, self.split, self.regu, self.Gc, self.l0, u_e,
-                                             self.psiP_old)
-        Kd = self._csr(Ke * self.thickness, self.map_d, self.Nn)
-        Fd = np.bincount(self.connect.ravel(), weights=(Fe[..., 0] * self.thickness).ravel(), minlength=self.Nn)
-        d_n = self.d
+    # -- matrices with the reference's "assemble only when the other field changed" flags --------------------------------
+    # `Get_K_C_M_F` (Simulations/_phasefield.py:248-269): Kd is rebuilt when the displacement changed since its last
+    # assembly (`__updatedDamage` False), Ku when the damage changed (`__updatedDisplacement` False).
+    def _get_Kd(self):
+        if not getattr(self, "_updatedDamage", False):
+            u_e = locate_sol_e(self.u, self.connect, self.dim)
+            Ke, Fe, self.psiP = pf_damage_system(self.geo_m, self.N_m, self.mat, self.split, self.regu, self.Gc, self.l0, u_e,
+                                                 self.psiP_old)
+            self._Kd = self._csr(Ke * self.thickness, self.map_d, self.Nn)
+            self._Fd = np.bincount(self.connect.ravel(), weights=(Fe[..., 0] * self.thickness).ravel(), minlength=self.Nn)
+            self._updatedDamage = True
+        return self._Kd, self._Fd
+
+    def _get_Ku(self):
+        if not getattr(self, "_updatedDisplacement", False):
+            u_e = locate_sol_e(self.u, self.connect, self.dim)
+            Ke = pf_elastic_Ke(self.geo_r, self.N_r, self.mat, self.split, u_e, self.d[self.connect]) * self.thickness
+            self._Ku = self._csr(Ke, self.map_u, self.Nn * self.dim)
+            self._updatedDisplacement = True
+        return self._Ku
+
+    def Psi_Crack(self):
+        """`_Calc_Psi_Crack` (:802-823): 1/2 d^T Kd d with the CURRENT damage matrix"""
+        Kd, _ = self._get_Kd()
+        return 0.0 if np.linalg.norm(self.d) == 0 else float(0.5 * self.d @ (Kd @ self.d))
+
+    def Psi_Elas(self):
+        """`_Calc_Psi_Elas` (:779-800): 1/2 u^T Ku u"""
+        Ku = self._get_Ku()
+        return 0.0 if np.linalg.norm(self.u) == 0 else float(0.5 * self.u @ (Ku @ self.u))
+
+    def solve_damage(self):
+        Kd, Fd = self._get_Kd()
         self.d = solve_dirichlet(Kd, Fd, np.concatenate(self.bc_d[0]), np.concatenate(self.bc_d[1]))
-        Ke = pf_elastic_Ke(self.geo_r, self.N_r, self.mat, self.split, u_e, self.d[self.connect]) * self.thickness
-        Ku = self._csr(Ke, self.map_u, self.Nn * dim)
-        self.u = solve_dirichlet(Ku, np.zeros(self.Nn * dim), np.concatenate(self.bc_u[0]), np.concatenate(self.bc_u[1]))
+        self._updatedDisplacement = False  # new damage -> new displacement matrices (:367-368)
+        return self.d
+
+    def solve_elastic(self):
+        Ku = self._get_Ku()
+        self.u = solve_dirichlet(Ku, np.zeros(self.Nn * self.dim), np.concatenate(self.bc_u[0]), np.concatenate(self.bc_u[1]))
+        self._updatedDamage = False  # new displacement -> new damage matrices (:372-373)
+        return self.u
+
+    def iterate(self):
+        d_n = self.d
+        self.solve_damage()
+        self.solve_elastic()
         return np.max(np.abs(self.d - d_n))
 
-    def Solve(self, tolConv=1.0, maxIter=500):
+    def Solve(self, tolConv=1.0, maxIter=500, convOption=0):
+        """`Simulations.PhaseField.Solve` (:300-432): convOption 0 max|d_np1 - d_n|, 1 crack energy, 2 total energy (no
+        external work: this driver has no Neumann loads), 3 summed relative increments of u and d (Pech 2022)."""
         Niter, converged = 0, False
         while not converged and Niter < maxIter:
             Niter += 1
-            conv = self.iterate()
-            converged = tolConv == 1 or self.d.max() == 0 or conv <= tolConv
-        self.Niter = Niter
+            d_n, u_n = self.d, self.u
+            if convOption == 1:
+                E_n = self.Psi_Crack()
+            elif convOption == 2:
+                E_n = self.Psi_Crack() + self.Psi_Elas()
+            d1 = self.solve_damage()
+            u1 = self.solve_elastic()
+            if convOption == 0:
+                conv = np.max(np.abs(d1 - d_n))
+            elif convOption in (1, 2):
+                E1 = self.Psi_Crack()
+                if convOption == 2:
+                    E1 += self.Psi_Elas()
+                conv = abs(E_n - E1) if E1 == 0 else abs((E_n - E1) / E1)
+            else:
+                diffU = np.abs(u1 - u_n)
+                diffU[u1 != 0] *= 1 / np.abs(u1[u1 != 0])
+                diffD = np.abs(d1 - d_n)
+                diffD[d1 != 0] *= 1 / np.abs(d1[d1 != 0])
+                convU, convD = np.sum(diffU), np.sum(diffD)
+                conv = max(convD, convU)
+            if tolConv == 1 or self.d.max() == 0:
+                converged = True
+            elif convOption == 3:
+                converged = bool(convD <= tolConv and convU <= tolConv * 0.999)
+            else:
+                converged = bool(conv <= tolConv)
+        self.Niter, self.convIter = Niter, conv
         return self.u, self.d, converged
 
     def Save_Iter(self):

@@ -69,5 +69,40 @@ def main():
         np.savez_compressed(os.path.join(OUT, f"staggered_{name}.npz"), **d)
 
 
+def conv_options():
+    """the energy / relative-increment convergence tests of `Simulations.PhaseField.Solve` (convOption 1, 2, 3,
+    Simulations/_phasefield.py:354-397) on the TRI3 Miehe and TETRA4 He cases, two load steps each"""
+    for name in ("TRI3_Miehe", "TETRA4_He"):
+        et, n, split, regu, loads = CASES[name]
+        dim = 2 if et in ("TRI3", "QUAD9") else 3
+        lengths = (L, L) if dim == 2 else (L, L, L * n[2] / n[0])
+        lattice, connect = meshgen.structured_mesh(et, n, lengths=lengths)
+        coords, _ = meshgen.structured_mesh(et, n, lengths=lengths, jitter=0.15, seed=5)
+        crack, top, bot, left, right = bc_sets(lattice, dim, n)
+        for opt, tol in ((1, 1e-2), (2, 1e-3), (3, 5e-2)):
+            g = GroupElemFactory.Create(ElemType(et), connect, coords)
+            mesh = Mesh({ElemType(et): g})
+            mat = Models.Elastic.Isotropic(dim, E=E, v=v, planeStress=False, thickness=1.0)
+            simu = Simulations.PhaseField(mesh, Models.PhaseField(mat, split, regu, Gc, l0))
+            d = {"coords": coords, "connect": connect, "crack": crack, "top": top, "bot": bot, "loads": np.array(loads[:2]),
+                 "params": np.array([L, l0, E, v, Gc]), "tolConv": np.array(tol), "convOption": np.array(opt)}
+            for k, dep in enumerate(loads[:2]):
+                simu.Bc_Init()
+                simu.add_dirichlet(crack, [1], ["d"], problemType="damage")
+                simu.add_dirichlet(top, [dep, 0.5 * dep] + [0] * (dim - 2), simu.Get_unknowns()[:dim])
+                simu.add_dirichlet(bot, [0] * dim, simu.Get_unknowns())
+                u, dmg, conv = simu.Solve(tol, 60, convOption=opt)
+                d[f"u_{k}"], d[f"d_{k}"] = np.array(u), np.array(dmg)
+                d[f"Niter_{k}"], d[f"convIter_{k}"] = simu._PhaseField__Niter, simu._PhaseField__convIter
+                d[f"psiP_{k}"] = np.asarray(simu._PhaseField__psiP_e_pg)
+                d[f"Psi_Crack_{k}"], d[f"Psi_Elas_{k}"] = simu._Calc_Psi_Crack(), simu._Calc_Psi_Elas()
+                simu.Save_Iter()
+                print(name, "convOption", opt, "step", k, "Niter", d[f"Niter_{k}"], "convIter", d[f"convIter_{k}"], "conv", conv)
+            np.savez_compressed(os.path.join(OUT, f"staggered_conv{opt}_{name}.npz"), **d)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "conv":
+        conv_options()
+    else:
+        main()

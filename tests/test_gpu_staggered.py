@@ -43,6 +43,37 @@ def test_staggered_loop_matches_reference(name, elemType, split):
         simu.Save_Iter()
 
 
+@pytest.mark.parametrize("opt", [1, 2, 3])
+@pytest.mark.parametrize("name,elemType,split", [("TRI3_Miehe", "TRI3", "Miehe"), ("TETRA4_He", "TETRA4", "He")])
+def test_staggered_convergence_options_match_reference(name, elemType, split, opt):
+    """convOption 1/2/3 of `Simulations.PhaseField.Solve` on the device: iteration counts, convergence measure, fields and the
+    two energies against fixtures minted from the live reference (the energy forms re-assemble Kd after the displacement
+    solve, which the update flags reproduce)."""
+    from easyfea_b200 import _lib, mesh, phasefield, staggered
+
+    _lib.require_cuda()
+    d = dict(np.load(os.path.join(GOLD, f"staggered_conv{opt}_{name}.npz")))
+    L, l0, E, v, Gc = d["params"]
+    g = mesh.ElemGroup(elemType, d["connect"], d["coords"])
+    dim = g.dim
+    pfm = phasefield.PhaseFieldModel(phasefield.IsotropicMaterial(dim, E, v, planeStress=False, thickness=1.0), split, "AT2", Gc, l0)
+    simu = staggered.PhaseFieldStaggered(staggered.LocalSystem(g), pfm, pcg_tol=1e-12)
+    for k, dep in enumerate(d["loads"]):
+        simu.Bc_Init()
+        simu.add_dirichlet(d["crack"], [1], [0], problemType="damage")
+        simu.add_dirichlet(d["top"], [dep, 0.5 * dep] + [0] * (dim - 2), list(range(dim)))
+        simu.add_dirichlet(d["bot"], [0] * dim, list(range(dim)))
+        u, dmg, conv = simu.Solve(float(d["tolConv"]), 60, convOption=opt)
+        assert conv and simu.Niter == int(d[f"Niter_{k}"]), (k, simu.Niter, int(d[f"Niter_{k}"]))
+        assert abs(simu.convIter - float(d[f"convIter_{k}"])) <= 1e-3 * abs(float(d[f"convIter_{k}"]))
+        assert rel_err(dmg.cpu().numpy(), d[f"d_{k}"]) < FIELD_TOL
+        assert rel_err(u.cpu().numpy(), d[f"u_{k}"]) < FIELD_TOL
+        assert rel_err(simu.psiP.cpu().numpy(), d[f"psiP_{k}"]) < FIELD_TOL
+        assert abs(simu.Calc_Psi_Crack() - float(d[f"Psi_Crack_{k}"])) <= 1e-6 * abs(float(d[f"Psi_Crack_{k}"]))
+        assert abs(simu.Calc_Psi_Elas() - float(d[f"Psi_Elas_{k}"])) <= 1e-6 * abs(float(d[f"Psi_Elas_{k}"]))
+        simu.Save_Iter()
+
+
 def test_elastic_solve_residual_and_direct_solution():
     """Config 2 at test size: assemble + Jacobi-PCG through `ElasticSolve`; residual <= 1e-8, matches a direct solve."""
     import scipy.sparse.linalg as spla
