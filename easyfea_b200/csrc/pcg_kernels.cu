@@ -360,32 +360,15 @@ constexpr int kCtrlBytes = 1024;
 static_assert(sizeof(PcgCtrl) <= kCtrlBytes, "control block");
 constexpr long long kSpinTimeoutCycles = 6000000000LL;  // ~3 s at 1.9 GHz: a lost peer must not hang the GPU
 
-#ifndef EFB_PCG_VARIANT
-#define EFB_PCG_VARIANT 0  // dev timing variants (scripts/build_variant.sh): 1 no CTA fence, 2 gpu scope, 3 no publish
-#endif
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
     unsigned long long v;
-#if EFB_PCG_VARIANT == 2
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-#else
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-#endif
     return v;
 }
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-#if EFB_PCG_VARIANT == 2
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-#else
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-#endif
 }
-__device__ __forceinline__ void fence_sys() {
-#if EFB_PCG_VARIANT == 2
-    __threadfence();
-#else
-    __threadfence_system();
-#endif
-}
+__device__ __forceinline__ void fence_sys() { __threadfence_system(); }
 
 // one thread: wait until *flag >= want (flags are monotonic); false when the wait was abandoned
 __device__ bool spin_until(const unsigned long long* flag, unsigned long long want, PcgCtrl* own) {
@@ -433,15 +416,10 @@ __device__ __forceinline__ bool publish_reduction(const efb_pcg_peer& P, PcgCtrl
                                                   const double (&mine)[M], int ticket_id, unsigned long long seq, double* red,
                                                   double (&total)[M]) {
     __shared__ bool is_last;
-#if EFB_PCG_VARIANT == 3
-    return false;
-#endif
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int m = 0; m < M; ++m) partials[m * kRedBlocks + blockIdx.x] = mine[m];
-#if EFB_PCG_VARIANT != 1
         __threadfence();
-#endif
         is_last = atomicAdd(&own->ticket[ticket_id], 1u) == gridDim.x - 1;
     }
     __syncthreads();
