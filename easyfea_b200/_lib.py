@@ -38,7 +38,7 @@ class EfbPcgSystem(ctypes.Structure):
 
     _fields_ = [("nrows", c_i64), ("kind", c_i32), ("index_bytes", c_i32), ("dof_n", c_i32), ("lanes", c_i32), ("indptr", c_vp),
                 ("indices", c_vp), ("data", c_vp), ("free_mask", c_vp), ("inv_diag", c_vp), ("x", c_vp), ("r", c_vp), ("z", c_vp),
-                ("Ap", c_vp), ("partials", c_vp)]
+                ("Ap", c_vp), ("partials", c_vp), ("s", c_vp)]
 
 
 class EfbPcgPeer(ctypes.Structure):
@@ -98,6 +98,7 @@ SIGNATURES = {
     "efb_pcg_ctrl_bytes": [],
     "efb_pcg_ctrl_layout": [_I32P],
     "efb_pcg_iterate": [ctypes.POINTER(EfbPcgSystem), ctypes.POINTER(EfbPcgPeer), ctypes.c_int, c_i64, c_vp],
+    "efb_pcg_iterate_cg2": [ctypes.POINTER(EfbPcgSystem), ctypes.POINTER(EfbPcgPeer), ctypes.c_int, c_i64, c_vp],
     "efb_pcg_solve_persistent": [ctypes.POINTER(EfbPcgSystem), ctypes.POINTER(EfbPcgPeer), c_i64, c_i64, c_f64, c_vp],
     "efb_peer_alloc": [c_i64, _PP],
     "efb_peer_free": [c_vp],

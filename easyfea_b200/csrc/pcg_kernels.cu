@@ -346,7 +346,7 @@ static int launch_spmv(long long nrows, const void* indptr, const void* indices,
 struct PcgCtrl {
     unsigned long long ar_flag[EFB_MAX_RANKS];    // [src] = number of reductions rank `src` has published here
     unsigned long long halo_flag[EFB_MAX_RANKS];  // [src] = number of halo pushes rank `src` has completed into this region
-    double ar_val[2][EFB_MAX_RANKS][2];           // [seq & 1][src][quantity]
+    double ar_val[2][EFB_MAX_RANKS][4];           // [seq & 1][src][quantity]
     unsigned int ticket[4];                       // local: last-CTA detection, one counter per kernel
     unsigned int error;                           // local: 1 = a wait timed out (peer lost); drains every later wait
     unsigned int pad_[3];
@@ -355,6 +355,8 @@ struct PcgCtrl {
     double rr;                                    // local: r.r after the last finished iteration
     unsigned long long gbar;                      // local: grid-barrier arrivals of the persistent kernel (zeroed before each launch)
     unsigned long long iters_done;                // local: iterations the last persistent launch ran
+    double cg2_gam[2], cg2_alp[2];                // local, single-reduction form: r.z and alpha of iteration it-1 in [it & 1]
+    double cg2_init[3];                           // local, single-reduction form: (r.z, z.Az, r.r) of the start vector
 };
 constexpr int kCtrlBytes = 1024;
 static_assert(sizeof(PcgCtrl) <= kCtrlBytes, "control block");
@@ -761,6 +763,162 @@ static PersistentKernel pcg_persistent_kernel(int lanes) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Single-reduction form (Chronopoulos & Gear 1989): the same Krylov iterates with ONE all-reduce per iteration.
+//   p = z + beta p ; s = w + beta s (= A p) ; x += alpha p ; r -= alpha s ; z = M^-1 r ; w = A z ;
+//   gamma' = r.z, delta = z.w (one fused reduction) ; beta = gamma'/gamma ; alpha = gamma' / (delta - beta gamma'/alpha)
+// Two kernels per iteration (vector update, SpMV) and two cross-GPU sync points (the reduction, the halo of z) instead
+// of three and three: strong-scaled shards are bound by those sync points.  The halo travels with z.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRedThreads)
+    k_cg2_update(long long n, const double* __restrict__ zc, double* __restrict__ zn, const double* __restrict__ w, double* __restrict__ p,
+                 double* __restrict__ s, double* __restrict__ x, double* __restrict__ r, const double* __restrict__ inv_diag,
+                 const unsigned char* __restrict__ mask, double* __restrict__ partials, efb_pcg_peer P, long long it,
+                 unsigned long long ar_done) {
+    __shared__ double red[kRedThreads];
+    PcgCtrl* own = (PcgCtrl*)P.base[P.rank];
+    double v[3];  // gamma = r.z, delta = z.Az, r.r of the current iterate
+    if (it == 0) {
+        v[0] = own->cg2_init[0];
+        v[1] = own->cg2_init[1];
+        v[2] = own->cg2_init[2];
+    } else {
+        gather_reduction<3>(P, own, ar_done, v, red);
+    }
+    double beta = 0.0, alpha = v[0] / v[1];
+    if (it > 0) {
+        beta = v[0] / own->cg2_gam[it & 1];
+        alpha = v[0] / (v[1] - beta * v[0] / own->cg2_alp[it & 1]);
+    }
+    double s_rz = 0.0, s_rr = 0.0;
+    for (long long i = (long long)blockIdx.x * kRedThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kRedThreads) {
+        if (mask && !mask[i]) {
+            zn[i] = 0.0;
+            continue;
+        }
+        const double pi = zc[i] + beta * p[i];
+        const double si = w[i] + beta * s[i];
+        p[i] = pi;
+        s[i] = si;
+        x[i] += alpha * pi;
+        const double ri = r[i] - alpha * si;
+        r[i] = ri;
+        const double zi = ri * inv_diag[i];
+        zn[i] = zi;
+        s_rz += ri * zi;
+        s_rr += ri * ri;
+    }
+    const double t0 = block_sum(s_rz, red), t1 = block_sum(s_rr, red);
+    if (threadIdx.x == 0) {
+        partials[kRedBlocks + blockIdx.x] = t0;      // folded by the SpMV kernel's last CTA together with its z.Az partials
+        partials[2 * kRedBlocks + blockIdx.x] = t1;
+        if (blockIdx.x == 0) {
+            own->cg2_gam[(it + 1) & 1] = v[0];
+            own->cg2_alp[(it + 1) & 1] = alpha;
+            own->rr = v[2];
+        }
+    }
+}
+
+// interface entries of the new z into the neighbours' halo segments; the last CTA raises their flags
+__global__ void __launch_bounds__(kRedThreads) k_cg2_push(const double* __restrict__ zn, efb_pcg_peer P, int nxt, unsigned long long halo_done) {
+    __shared__ bool is_last;
+    PcgCtrl* own = (PcgCtrl*)P.base[P.rank];
+    const long long stride = (long long)gridDim.x * kRedThreads, first = (long long)blockIdx.x * kRedThreads + threadIdx.x;
+    for (int sidx = 0; sidx < P.n_send; ++sidx) {
+        const int q = P.send_rank[sidx];
+        double* dst = (double*)((char*)P.base[q] + P.pbuf_off[q][nxt]) + P.send_dst[sidx];
+        const long long j0 = P.send_ptr[sidx], cnt = P.send_ptr[sidx + 1] - j0;
+        for (long long j = first; j < cnt; j += stride) dst[j] = zn[P.send_idx[j0 + j]];
+    }
+    fence_sys();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(&own->ticket[2], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        fence_sys();
+        for (int sidx = 0; sidx < P.n_send; ++sidx) st_release_sys(&((PcgCtrl*)P.base[P.send_rank[sidx]])->halo_flag[P.rank], halo_done + 1ull);
+        own->ticket[2] = 0;
+    }
+}
+
+// w = A z (waits for the neighbours' halo entries of z), then ONE reduction of (r.z, z.Az, r.r): the z.Az partials of this
+// kernel and the (r.z, r.r) partials the update kernel left behind (g_update CTAs)
+template <int KIND, int A, int B>
+__global__ void __launch_bounds__(kRedThreads, EFB_PCG_SPMV_MINB)
+    k_cg2_spmv(long long n, const void* __restrict__ indptr, const void* __restrict__ indices, const double* __restrict__ data,
+               const double* __restrict__ z, const unsigned char* __restrict__ mask, double* __restrict__ w, double* __restrict__ partials,
+               int g_update, efb_pcg_peer P, unsigned long long ar_done, unsigned long long halo_done) {
+    __shared__ double red[kRedThreads];
+    __shared__ bool is_last;
+    PcgCtrl* own = (PcgCtrl*)P.base[P.rank];
+    if (P.n_recv > 0) {
+        if (threadIdx.x == 0)
+            for (int i = 0; i < P.n_recv; ++i) spin_until(&own->halo_flag[P.recv_rank[i]], halo_done, own);
+        __syncthreads();
+    }
+    double local;
+    if constexpr (KIND == 0) {
+        if constexpr (A == 4)
+            local = spmv_rows<int, B>(n, (const int*)indptr, (const int*)indices, data, z, 0, mask, w, true);
+        else
+            local = spmv_rows<long long, B>(n, (const long long*)indptr, (const long long*)indices, data, z, 0, mask, w, true);
+    } else {
+        local = spmv_nodes<A, B>(n, (const long long*)indptr, (const int*)indices, data, z, 0, mask, w, true);
+    }
+    const double mine = block_sum(local, red);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = mine;
+        __threadfence();
+        is_last = atomicAdd(&own->ticket[0], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double tot[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        const int cnt = m == 1 ? (int)gridDim.x : g_update;               // m: 0 r.z, 1 z.Az, 2 r.r
+        const double* src = partials + (m == 1 ? 0 : (m == 0 ? 1 : 2)) * kRedBlocks;
+        double acc = 0.0;
+        for (int b = threadIdx.x; b < cnt; b += kRedThreads) acc += __ldcg(&src[b]);
+        tot[m] = block_sum(acc, red);
+    }
+    if (threadIdx.x == 0) {
+        const unsigned long long seq = ar_done + 1ull;
+        const int buf = (int)((seq - 1) & 1);
+        for (int q = 0; q < P.world; ++q) {
+            PcgCtrl* c = (PcgCtrl*)P.base[q];
+#pragma unroll
+            for (int m = 0; m < 3; ++m) *(volatile double*)&c->ar_val[buf][P.rank][m] = tot[m];
+        }
+        fence_sys();
+        for (int q = 0; q < P.world; ++q) st_release_sys(&((PcgCtrl*)P.base[q])->ar_flag[P.rank], seq);
+        own->ticket[0] = 0;
+    }
+}
+
+// end of a call: r.r of the last iterate into the control block (the host reads it between calls)
+__global__ void __launch_bounds__(kRedThreads) k_cg2_finish(efb_pcg_peer P, unsigned long long seq) {
+    __shared__ double red[kRedThreads];
+    PcgCtrl* own = (PcgCtrl*)P.base[P.rank];
+    double v[3];
+    gather_reduction<3>(P, own, seq, v, red);
+    if (threadIdx.x == 0) own->rr = v[2];
+}
+
+using Cg2SpmvKernel = void (*)(long long, const void*, const void*, const double*, const double*, const unsigned char*, double*, double*, int,
+                               efb_pcg_peer, unsigned long long, unsigned long long);
+template <int KIND, int A>
+static Cg2SpmvKernel cg2_spmv_kernel(int lanes) {
+    switch (lanes) {
+        case 4: return k_cg2_spmv<KIND, A, 4>;
+        case 8: return k_cg2_spmv<KIND, A, 8>;
+        case 16: return k_cg2_spmv<KIND, A, 16>;
+        default: return k_cg2_spmv<KIND, A, 32>;
+    }
+}
+
 // one wave: every CTA of the three kernels is resident at once (grid-stride bodies, no tail wave), capped by the partials layout
 template <class K>
 static int resident_blocks_per_sm(K kernel) {
@@ -868,11 +1026,12 @@ extern "C" int efb_pcg_update_p(int64_t n, const double* rz_new, const double* r
 
 extern "C" int efb_pcg_ctrl_bytes(void) { return kCtrlBytes; }
 
-extern "C" int efb_pcg_ctrl_layout(int32_t* out3) {  // 4 entries
+extern "C" int efb_pcg_ctrl_layout(int32_t* out3) {  // 5 entries
     out3[0] = (int32_t)(offsetof(PcgCtrl, rz) / 8);
     out3[1] = (int32_t)(offsetof(PcgCtrl, rr) / 8);
     out3[2] = (int32_t)(offsetof(PcgCtrl, error) / 4);
     out3[3] = (int32_t)(offsetof(PcgCtrl, iters_done) / 8);
+    out3[4] = (int32_t)(offsetof(PcgCtrl, cg2_init) / 8);
     return 0;
 }
 
@@ -947,6 +1106,61 @@ extern "C" int efb_pcg_iterate(const efb_pcg_system* sys, const efb_pcg_peer* pe
         delete[] ev;
     }
     return check_launch("efb_pcg_iterate");
+}
+
+extern "C" int efb_pcg_iterate_cg2(const efb_pcg_system* sys, const efb_pcg_peer* peer, int n_iters, int64_t it0, void* stream) {
+    const efb_pcg_peer& P = *peer;
+    if (P.world < 1 || P.world > EFB_MAX_RANKS || P.rank < 0 || P.rank >= P.world || P.n_send < 0 || P.n_send > EFB_MAX_RANKS ||
+        P.n_recv < 0 || P.n_recv > EFB_MAX_RANKS) {
+        set_error("efb_pcg_iterate_cg2: bad communicator (world %d, rank %d)", P.world, P.rank);
+        return 1;
+    }
+    if (!sys->s) {
+        set_error("efb_pcg_iterate_cg2: the system needs the extra vector s");
+        return 1;
+    }
+    if (n_iters <= 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    long long n_spmv;
+    Cg2SpmvKernel spmv_k;
+    if (sys->kind == 1) {
+        if (sys->dof_n < 1 || sys->dof_n > 3 || sys->nrows % sys->dof_n) {
+            set_error("efb_pcg_iterate_cg2: node-block systems need dof_n in 1..3 dividing nrows");
+            return 1;
+        }
+        n_spmv = sys->nrows / sys->dof_n;
+        spmv_k = sys->dof_n == 1 ? cg2_spmv_kernel<1, 1>(sys->lanes) : sys->dof_n == 2 ? cg2_spmv_kernel<1, 2>(sys->lanes) : cg2_spmv_kernel<1, 3>(sys->lanes);
+    } else if (sys->kind == 0 && (sys->index_bytes == 4 || sys->index_bytes == 8)) {
+        n_spmv = sys->nrows;
+        spmv_k = sys->index_bytes == 4 ? cg2_spmv_kernel<0, 4>(sys->lanes) : cg2_spmv_kernel<0, 8>(sys->lanes);
+    } else {
+        set_error("efb_pcg_iterate_cg2: kind must be 0 (CSR, index_bytes 4 or 8) or 1 (node blocks)");
+        return 1;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int g_spmv = min(kRedBlocks, sms * resident_blocks_per_sm(spmv_k));
+    const int g_upd = min(kRedBlocks, sms * resident_blocks_per_sm(k_cg2_update));
+    long long n_push = P.n_send > 0 ? P.send_ptr[P.n_send] : 0;
+    int g_push = (int)((n_push + kRedThreads - 1) / kRedThreads);
+    if (g_push > sms) g_push = sms;
+    if (g_push < 1) g_push = 1;
+    for (int k = 0; k < n_iters; ++k) {
+        const long long it = it0 + k;
+        const int cur = (int)(it & 1), nxt = cur ^ 1;
+        const double* zc = (const double*)((const char*)P.base[P.rank] + P.pbuf_off[P.rank][cur]);
+        double* zn = (double*)((char*)P.base[P.rank] + P.pbuf_off[P.rank][nxt]);
+        const unsigned long long ar_done = P.ar_seq + (unsigned long long)k, halo_done = P.halo_seq + (unsigned long long)k;
+        // p lives in sys->z (z itself lives in the two peer buffers), w in sys->Ap
+        k_cg2_update<<<g_upd, kRedThreads, 0, st>>>(sys->nrows, zc, zn, sys->Ap, sys->z, sys->s, sys->x, sys->r, sys->inv_diag, sys->free_mask,
+                                                    sys->partials, P, it, ar_done);
+        if (P.n_send > 0) k_cg2_push<<<g_push, kRedThreads, 0, st>>>(zn, P, nxt, halo_done);
+        spmv_k<<<g_spmv, kRedThreads, 0, st>>>(n_spmv, sys->indptr, sys->indices, sys->data, zn, sys->free_mask, sys->Ap, sys->partials, g_upd, P,
+                                               ar_done, halo_done + 1ull);
+    }
+    k_cg2_finish<<<1, kRedThreads, 0, st>>>(P, P.ar_seq + (unsigned long long)n_iters);
+    return check_launch("efb_pcg_iterate_cg2");
 }
 
 extern "C" int efb_pcg_solve_persistent(const efb_pcg_system* sys, const efb_pcg_peer* peer, int64_t it0, int64_t max_iters,

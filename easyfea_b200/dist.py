@@ -282,9 +282,10 @@ class LocalWorkspace:
         lib = _lib.load()
         self.n = int(n)
         ctrl = lib.efb_pcg_ctrl_bytes()
-        lay = (ctypes.c_int32 * 4)()
+        lay = (ctypes.c_int32 * 5)()
         lib.efb_pcg_ctrl_layout(lay)
         self.rz_off, self.rr_off, self.err_off, self.iters_off = int(lay[0]), int(lay[1]), int(lay[2]), int(lay[3])
+        self.cg2_init_off = int(lay[4])
         self.ctrl_bytes = ctrl
         self.pbuf_off = (ctrl, ctrl + _pad256(self.n * 8))
         self.nbytes = ctrl + 2 * _pad256(self.n * 8)
@@ -311,8 +312,8 @@ class LocalWorkspace:
         c = self.ctrl.cpu().numpy()
         return float(c[self.rr_off]), int(c.view(np.uint32)[self.err_off]), int(c.view(np.uint64)[self.iters_off])
 
-    def advance(self, n_iters: int):
-        self.peer.ar_seq += 2 * n_iters
+    def advance(self, n_iters: int, reductions_per_iter: int = 2):
+        self.peer.ar_seq += reductions_per_iter * n_iters
         self.peer.halo_seq += n_iters
 
 

@@ -18,6 +18,9 @@ from . import device as dv
 from .assembly import DeviceCsr
 
 
+SINGLE_REDUCTION_MAX_ROWS = 2_000_000  # per-rank rows below which a sharded solve defaults to the single-reduction form
+
+
 def lanes_per_row(nnz: int, nrows: int) -> int:
     """lanes cooperating on one row of the generic CSR product"""
     avg = nnz / max(nrows, 1)
@@ -81,7 +84,7 @@ def _system_struct(A: DeviceCsr, nrows, mask, inv_diag, x, r, z, Ap, partials) -
 
 
 def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: int = None, check_every: int = 25, comm=None,
-        fused: bool = True, persistent: bool = False):
+        fused: bool = True, persistent: bool = False, single_reduction: bool = None):
     """Solve A x = b on the free dofs (free_mask True / 1 = unknown; other entries of x keep the values of x0).
 
     A holds the owned rows in LOCAL numbering `[owned | halo]` columns.  Stops when ||r|| <= tol * ||b - A x_known||
@@ -93,6 +96,10 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
     `persistent=True` (matrices assembled by this library) ONE cooperative kernel iterates until convergence instead
     (`efb_pcg_solve_persistent`: grid barriers between the steps, every rank leaves in the same iteration, no host round
     trip at all); measured equal on small systems and ~8 % slower on large ones (profiles/README.md), hence opt-in.
+    `single_reduction=True`: the Chronopoulos-Gear form of the same iteration (`efb_pcg_iterate_cg2`) — one all-reduce, two
+    kernels and two cross-GPU sync points per iteration instead of two, three and three; one more vector pass.  Default
+    (None): used for row-sharded solves whose shard is small enough to be bound by the sync points (<= 2 M dofs per rank:
+    8 % faster at 0.2 M dofs on 2 GPUs, 1 % slower at 3 M; same iteration counts on the phase-field systems).
     `fused=False` keeps
     one collective call per exchange (NCCL through torch.distributed) and one kernel per vector operation — the baseline
     the fused path is measured against (bench.py) and checked against (tests).
@@ -100,6 +107,9 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
     dev = A.data.device
     nrows = A.indptr.numel() - 1
     n_glob = A.shape[1]
+    if single_reduction is None:
+        single_reduction = bool(fused) and comm is not None and nrows <= SINGLE_REDUCTION_MAX_ROWS
+    single_reduction = bool(single_reduction) and bool(fused)
     st = dv.stream_ptr
     b = dv.to_device(b)
     assert b.numel() == nrows
@@ -177,8 +187,29 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
         ws.ctrl[ws.rz_off:ws.rz_off + 1].copy_(scal[2:3])
         ws.ctrl[ws.rr_off:ws.rr_off + 1].copy_(scal[3:4])
         S = _system_struct(A, nrows, mask, inv_diag, x, r, z, Ap, partials)
-        use_persistent = bool(persistent) and S.kind == 1
+        use_persistent = bool(persistent) and S.kind == 1 and not single_reduction
+        if single_reduction:
+            # z_0 already sits in buffer 0 (the classic start has p_0 = z_0) with its halo; w_0 = A z_0 with z_0.w_0, p = s = 0
+            spmv(A, p_full, Ap, 0, mask, partials)
+            reduce_to(1, 1)  # scal[1] = z.Az
+            ws.ctrl[ws.cg2_init_off:ws.cg2_init_off + 1].copy_(scal[2:3])
+            ws.ctrl[ws.cg2_init_off + 1:ws.cg2_init_off + 2].copy_(scal[1:2])
+            ws.ctrl[ws.cg2_init_off + 2:ws.cg2_init_off + 3].copy_(scal[3:4])
+            z.zero_()  # the `z` vector of the system holds p in this form
+            s_vec = torch.zeros(nrows, dtype=torch.float64, device=dev)
+            S.s = s_vec.data_ptr()
         while rr > target and it < maxiter:
+            if single_reduction:
+                k = min(int(check_every), maxiter - it)
+                _lib.call("efb_pcg_iterate_cg2", ctypes.byref(S), ctypes.byref(ws.peer), k, it, st())
+                rr, err, _ = ws.status()
+                ws.advance(k, 1)
+                it += k
+                if err:
+                    raise _lib.EfbError("PCG: a wait on a neighbour rank timed out (peer process lost?)")
+                if rr != rr:
+                    raise _lib.EfbError("PCG broke down (NaN residual): matrix not SPD on the free dofs?")
+                continue
             if use_persistent:
                 _lib.call("efb_pcg_solve_persistent", ctypes.byref(S), ctypes.byref(ws.peer), it, maxiter - it, float(target), st())
                 rr, err, k = ws.status()
@@ -215,4 +246,4 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
                 raise _lib.EfbError("PCG broke down (NaN residual): matrix not SPD on the free dofs?")
     rel = (rr / bnorm2) ** 0.5
     return x.clone(), {"iterations": it, "rel_residual": rel, "converged": rel <= tol, "fused": ws is not None,
-                       "persistent": ws is not None and use_persistent}
+                       "persistent": ws is not None and use_persistent, "single_reduction": ws is not None and bool(single_reduction)}

@@ -103,6 +103,7 @@ class ElasticSolve:
         self.u = torch.zeros(system.n_local * self.dim, dtype=torch.float64, device=dv.device())
         self.pcg_fused = True  # False: one NCCL call per exchange (the baseline of solver.pcg)
         self.pcg_persistent = False  # True: one cooperative kernel per solve instead of three kernels per iteration
+        self.pcg_single_reduction = None  # Chronopoulos-Gear form (one all-reduce per iteration); None: solver.pcg decides
 
     def assemble(self) -> DeviceCsr:
         scale = self.thickness if self.dim == 2 else 1.0
@@ -118,7 +119,7 @@ class ElasticSolve:
         self.sys.refresh_halo(self.u, d)
         rhs = torch.zeros(nown, dtype=torch.float64, device=self.u.device) if b is None else dv.to_device(b)
         x, info = pcg(K, rhs, x0=self.u, free_mask=mask, tol=tol, maxiter=maxiter, comm=self.sys.comm(d), fused=self.pcg_fused,
-                      persistent=self.pcg_persistent)
+                      persistent=self.pcg_persistent, single_reduction=self.pcg_single_reduction)
         self.u[:nown] = x
         self.sys.refresh_halo(self.u, d)
         return self.u, info
@@ -139,7 +140,7 @@ class PhaseFieldStaggered:
         self.bc_u = Dirichlet(system.n_local * self.dim)
         self.bc_d = Dirichlet(system.n_local)
         self.pcg_tol, self.pcg_maxiter = pcg_tol, pcg_maxiter
-        self.pcg_fused, self.pcg_persistent = True, False
+        self.pcg_fused, self.pcg_persistent, self.pcg_single_reduction = True, False, None
         self._updatedDamage = self._updatedDisplacement = False
         self.info = {}
 
@@ -210,7 +211,7 @@ class PhaseFieldStaggered:
         _apply(self.d, dofs, vals)
         s.refresh_halo(self.d, 1)
         x, info = pcg(K, F, x0=self.d, free_mask=mask, tol=self.pcg_tol, maxiter=self.pcg_maxiter, comm=s.comm(1),
-                      fused=self.pcg_fused, persistent=self.pcg_persistent)
+                      fused=self.pcg_fused, persistent=self.pcg_persistent, single_reduction=self.pcg_single_reduction)
         self.d[: s.n_owned] = x
         s.refresh_halo(self.d, 1)
         self._updatedDisplacement = False  # new damage -> new displacement matrices (:367-368)
@@ -227,7 +228,7 @@ class PhaseFieldStaggered:
         s.refresh_halo(self.u, dim)
         rhs = torch.zeros(nown, dtype=torch.float64, device=self.u.device)
         x, info = pcg(K, rhs, x0=self.u, free_mask=mask, tol=self.pcg_tol, maxiter=self.pcg_maxiter, comm=s.comm(dim),
-                      fused=self.pcg_fused, persistent=self.pcg_persistent)
+                      fused=self.pcg_fused, persistent=self.pcg_persistent, single_reduction=self.pcg_single_reduction)
         self.u[:nown] = x
         s.refresh_halo(self.u, dim)
         self._updatedDamage = False  # new displacement -> new damage matrices (:372-373)

@@ -105,6 +105,7 @@ class TransientSolve:
         self.K = self.C = self.M = None
         self.algo = "elliptic"
         self.pcg_tol, self.pcg_maxiter, self.pcg_fused, self.pcg_persistent = 1e-10, None, True, False
+        self.pcg_single_reduction = None
         self.info = {}
 
     # -- systems ---------------------------------------------------------------------------------------------------
@@ -213,7 +214,7 @@ class TransientSolve:
         _apply(x0, dofs, torch.zeros_like(vals) if explicit else vals)
         s.refresh_halo(x0, d)
         x, info = pcg(A, b, x0=x0, free_mask=mask, tol=self.pcg_tol, maxiter=self.pcg_maxiter, comm=s.comm(d), fused=self.pcg_fused,
-                      persistent=self.pcg_persistent)
+                      persistent=self.pcg_persistent, single_reduction=self.pcg_single_reduction)
         self.info = info
         x0[:n_own] = x
         s.refresh_halo(x0, d)

@@ -221,6 +221,7 @@ typedef struct efb_pcg_system {
     double* z;
     double* Ap;
     double* partials;         /* efb_pcg_partials_size() doubles */
+    double* s;                /* (nrows) extra vector of the single-reduction form (efb_pcg_iterate_cg2), else NULL */
 } efb_pcg_system;
 
 typedef struct efb_pcg_peer {
@@ -239,12 +240,20 @@ typedef struct efb_pcg_peer {
 
 /* a region starts with a control block of efb_pcg_ctrl_bytes() bytes (zero it once); offsets of the device scalars
  * inside it: out[0] = rz[2] ping-pong and out[1] = rr (in doubles), out[2] = error flag (uint32 index),
- * out[3] = iterations run by the last persistent launch (uint64 index) */
+ * out[3] = iterations run by the last persistent launch (uint64 index), out[4] = (r.z, z.Az, r.r) of the start vector for
+ * the single-reduction form (in doubles) */
 int efb_pcg_ctrl_bytes(void);
-int efb_pcg_ctrl_layout(int32_t* out4);
+int efb_pcg_ctrl_layout(int32_t* out5);
 /* enqueue n_iters iterations starting at iteration `it0` (p_it lives in p buffer it & 1, r.z of it in rz[it & 1]).
  * The caller advances peer->ar_seq by 2*n_iters and halo_seq by n_iters afterwards. */
 int efb_pcg_iterate(const efb_pcg_system* sys, const efb_pcg_peer* peer, int n_iters, int64_t it0, void* stream);
+/* Single-reduction form (Chronopoulos-Gear): the same iterates with ONE all-reduce per iteration — two kernels (vector
+ * update, SpMV) and two cross-GPU sync points per iteration instead of three and three.  z lives in the two peer buffers
+ * (its halo is what travels), p in sys->z, w = A z in sys->Ap, s = A p in sys->s.  Before iteration 0 the caller puts z_0
+ * (owned + halo) in buffer 0, w_0 = A z_0 in sys->Ap, zeros in p and s, and (r.z, z.Az, r.r) in the control block
+ * (layout out[4]).  The caller advances ar_seq and halo_seq by n_iters afterwards; r.r of the last iterate is in the
+ * control block when the call's work is done. */
+int efb_pcg_iterate_cg2(const efb_pcg_system* sys, const efb_pcg_peer* peer, int n_iters, int64_t it0, void* stream);
 /* Persistent form for node-block systems (kind 1): ONE cooperative kernel runs iterations it0, it0+1, ... until
  * r.r <= target_rr or max_iters are done; the three steps are separated by grid barriers, every CTA folds the partials
  * itself, and every CTA of every rank leaves in the same iteration (same bits everywhere) — no host round trip and no

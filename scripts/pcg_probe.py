@@ -30,12 +30,12 @@ for c in range(dim):
 free[hi * dim] = 0
 x0[hi * dim] = 0.01
 b = torch.zeros(Nn * dim, dtype=torch.float64, device="cuda")
-for fused, persistent in ((True, True), (True, False), (False, False)):
+for fused, persistent, sr in ((True, False, True), (True, False, False), (False, False, False)):
     for rep in range(2):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        x, info = solver.pcg(K, b, x0=x0, free_mask=free, tol=1e-30, maxiter=iters, check_every=iters, fused=fused, persistent=persistent)
+        x, info = solver.pcg(K, b, x0=x0, free_mask=free, tol=1e-30, maxiter=iters, check_every=iters, fused=fused, persistent=persistent, single_reduction=sr)
         e1.record()
         torch.cuda.synchronize()
-        print(f"{elem} n={n} fused={fused} persistent={persistent} rep={rep}: {e0.elapsed_time(e1) / iters:.4f} ms/iter, rel {info['rel_residual']:.6e}", flush=True)
+        print(f"{elem} n={n} fused={fused} single_reduction={sr} rep={rep}: {e0.elapsed_time(e1) / iters:.4f} ms/iter, rel {info['rel_residual']:.6e}", flush=True)

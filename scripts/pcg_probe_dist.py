@@ -42,17 +42,17 @@ x0[top * 3 + 2] = 0.01
 free[top[top < part.n_owned] * 3 + 2] = 0
 b = torch.zeros(nrows, dtype=torch.float64, device="cuda")
 for rep in range(2):
-    for fused, persistent in ((True, True), (True, False), (False, False)):
-        solver.pcg(K, b, x0=x0, free_mask=free, tol=1e-30, maxiter=3, check_every=3, comm=comm, fused=fused, persistent=persistent)
+    for fused, persistent, sr in ((True, False, True), (True, False, False), (False, False, False)):
+        solver.pcg(K, b, x0=x0, free_mask=free, tol=1e-30, maxiter=3, check_every=3, comm=comm, fused=fused, persistent=persistent, single_reduction=sr)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        x, info = solver.pcg(K, b, x0=x0, free_mask=free, tol=1e-30, maxiter=iters, check_every=iters, comm=comm, fused=fused, persistent=persistent)
+        x, info = solver.pcg(K, b, x0=x0, free_mask=free, tol=1e-30, maxiter=iters, check_every=iters, comm=comm, fused=fused, persistent=persistent, single_reduction=sr)
         e1.record()
         torch.cuda.synchronize()
-        print(f"rank {rank}/{world} n={n} fused={fused} persistent={persistent} rep={rep}: {e0.elapsed_time(e1) / iters:.4f} ms/iter rel {info['rel_residual']:.6e}", flush=True)
+        print(f"rank {rank}/{world} n={n} fused={fused} single_reduction={sr} rep={rep}: {e0.elapsed_time(e1) / iters:.4f} ms/iter rel {info['rel_residual']:.6e}", flush=True)
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()

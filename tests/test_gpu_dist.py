@@ -41,6 +41,10 @@ def _worker(rank, world, port, out):
         es.bc.add(loc[plane == world * n[2]], [0.05], [2], 3)
         u, info = es.solve(tol=1e-10)  # fused iterations: reductions + halo pushes through peer memory
         assert info["converged"] and info["fused"] and not info["persistent"], info
+        assert info["single_reduction"], "a small sharded system defaults to the single-reduction form"
+        es.pcg_single_reduction = False  # the classic two-reduction form from here on, unless stated
+        u, info = es.solve(tol=1e-10)
+        assert info["converged"] and not info["single_reduction"], info
         u_peer = u[: part.n_owned * 3].cpu().numpy()
         u2, info2 = es.solve(tol=1e-10)  # second solve on the same communicator (sequence numbers carry on), warm start
         assert info2["converged"], info2
@@ -50,6 +54,14 @@ def _worker(rank, world, port, out):
         es.pcg_persistent = False
         assert info4["converged"] and info4["fused"] and info4["persistent"], info4
         assert np.linalg.norm(u4[: part.n_owned * 3].cpu().numpy() - u_peer) <= 1e-8 * np.linalg.norm(u_peer)
+        es.u.zero_()
+        es.pcg_single_reduction = True  # Chronopoulos-Gear form: one all-reduce per iteration, the halo travels with z
+        u5, info5 = es.solve(tol=1e-10)
+        es.pcg_single_reduction = False
+        assert info5["converged"] and info5["single_reduction"], info5
+        assert np.linalg.norm(u5[: part.n_owned * 3].cpu().numpy() - u_peer) <= 1e-8 * np.linalg.norm(u_peer)
+        u6, info6 = es.solve(tol=1e-10)  # and back to the classic form on the same communicator (sequence numbers carry on)
+        assert info6["converged"], info6
         es.u.zero_()
         es.pcg_fused = False  # NCCL send/recv + all-reduce per iteration: same iterates up to summation order
         u3, info3 = es.solve(tol=1e-10)

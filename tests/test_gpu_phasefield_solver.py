@@ -160,6 +160,15 @@ def test_pcg_elastic_cube(efb):
     x2c, info2c = efb.solver.pcg(K, b, x0=x0, free_mask=~known, tol=1e-8, maxiter=5000, persistent=True)
     assert info2c["fused"] and info2c["persistent"] and abs(info2c["iterations"] - info["iterations"]) <= 25
     assert np.linalg.norm(x2c.cpu().numpy() - x) / np.linalg.norm(x) < 1e-5
+    Kc = efb.asm.DeviceCsr(K.indptr, K.indices, K.data, K.shape)  # generic CSR form (no node graph)
+    # single-reduction (Chronopoulos-Gear) form: same Krylov iterates up to rounding, one all-reduce per iteration
+    x2e, info2e = efb.solver.pcg(K, b, x0=x0, free_mask=~known, tol=1e-8, maxiter=5000, single_reduction=True)
+    assert info2e["converged"] and info2e["single_reduction"] and abs(info2e["iterations"] - info["iterations"]) <= 25, (info, info2e)
+    assert np.linalg.norm(x2e.cpu().numpy() - x) / np.linalg.norm(x) < 1e-5
+    res_e = np.linalg.norm(Ks[free][:, free] @ x2e.cpu().numpy()[free] - rhs) / np.linalg.norm(rhs)
+    assert res_e <= 2e-8, res_e
+    x2f, info2f = efb.solver.pcg(Kc, b, x0=x0, free_mask=~known, tol=1e-8, maxiter=5000, single_reduction=True, check_every=7)
+    assert info2f["converged"] and np.linalg.norm(x2f.cpu().numpy() - x) / np.linalg.norm(x) < 1e-5
     # maxiter is honoured exactly by the persistent kernel
     _, info2d = efb.solver.pcg(K, b, x0=x0, free_mask=~known, tol=1e-30, maxiter=17, persistent=True)
     assert info2d["iterations"] == 17 and not info2d["converged"]
