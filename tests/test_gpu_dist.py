@@ -42,8 +42,11 @@ def _worker(rank, world, port, out):
         u, info = es.solve(tol=1e-10)  # fused iterations: reductions + halo pushes through peer memory
         assert info["converged"] and info["fused"] and not info["persistent"], info
         assert info["single_reduction"], "a small sharded system defaults to the single-reduction form"
+        u_sr = u[: part.n_owned * 3].cpu().numpy()
         es.pcg_single_reduction = False  # the classic two-reduction form from here on, unless stated
+        es.u.zero_()
         u, info = es.solve(tol=1e-10)
+        assert np.linalg.norm(u_sr - u[: part.n_owned * 3].cpu().numpy()) <= 1e-8 * np.linalg.norm(u_sr)
         assert info["converged"] and not info["single_reduction"], info
         u_peer = u[: part.n_owned * 3].cpu().numpy()
         u2, info2 = es.solve(tol=1e-10)  # second solve on the same communicator (sequence numbers carry on), warm start
