@@ -18,9 +18,6 @@ from . import device as dv
 from .assembly import DeviceCsr
 
 
-SINGLE_REDUCTION_MAX_ROWS = 2_000_000  # per-rank rows below which a sharded solve defaults to the single-reduction form
-
-
 def lanes_per_row(nnz: int, nrows: int) -> int:
     """lanes cooperating on one row of the generic CSR product"""
     avg = nnz / max(nrows, 1)
@@ -84,7 +81,7 @@ def _system_struct(A: DeviceCsr, nrows, mask, inv_diag, x, r, z, Ap, partials) -
 
 
 def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: int = None, check_every: int = 25, comm=None,
-        fused: bool = True, persistent: bool = False, single_reduction: bool = None):
+        fused: bool = True, persistent: bool = False, single_reduction: bool = False):
     """Solve A x = b on the free dofs (free_mask True / 1 = unknown; other entries of x keep the values of x0).
 
     A holds the owned rows in LOCAL numbering `[owned | halo]` columns.  Stops when ||r|| <= tol * ||b - A x_known||
@@ -97,9 +94,10 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
     (`efb_pcg_solve_persistent`: grid barriers between the steps, every rank leaves in the same iteration, no host round
     trip at all); measured equal on small systems and ~8 % slower on large ones (profiles/README.md), hence opt-in.
     `single_reduction=True`: the Chronopoulos-Gear form of the same iteration (`efb_pcg_iterate_cg2`) — one all-reduce, two
-    kernels and two cross-GPU sync points per iteration instead of two, three and three; one more vector pass.  Default
-    (None): used for row-sharded solves whose shard is small enough to be bound by the sync points (<= 2 M dofs per rank:
-    8 % faster at 0.2 M dofs on 2 GPUs, 1 % slower at 3 M; same iteration counts on the phase-field systems).
+    kernels and two cross-GPU sync points per iteration instead of two, three and three; one more vector pass.  Opt-in:
+    measured 13 % / 8 % faster at 0.2 M dofs on 1 / 2 GPUs and 1-3 % slower at >= 2 M dofs per rank, identical iteration
+    counts on the phase-field systems, but 18 % SLOWER on config 4 over 8 GPUs (0.33 vs 0.28 s per staggered iteration,
+    one measurement each, profiles/README.md) — not understood yet, so the classic form stays the default.
     `fused=False` keeps
     one collective call per exchange (NCCL through torch.distributed) and one kernel per vector operation — the baseline
     the fused path is measured against (bench.py) and checked against (tests).
@@ -107,8 +105,6 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
     dev = A.data.device
     nrows = A.indptr.numel() - 1
     n_glob = A.shape[1]
-    if single_reduction is None:
-        single_reduction = bool(fused) and comm is not None and nrows <= SINGLE_REDUCTION_MAX_ROWS
     single_reduction = bool(single_reduction) and bool(fused)
     st = dv.stream_ptr
     b = dv.to_device(b)

@@ -103,7 +103,7 @@ class ElasticSolve:
         self.u = torch.zeros(system.n_local * self.dim, dtype=torch.float64, device=dv.device())
         self.pcg_fused = True  # False: one NCCL call per exchange (the baseline of solver.pcg)
         self.pcg_persistent = False  # True: one cooperative kernel per solve instead of three kernels per iteration
-        self.pcg_single_reduction = None  # Chronopoulos-Gear form (one all-reduce per iteration); None: solver.pcg decides
+        self.pcg_single_reduction = False  # True: Chronopoulos-Gear form, one all-reduce per iteration
 
     def assemble(self) -> DeviceCsr:
         scale = self.thickness if self.dim == 2 else 1.0
@@ -140,7 +140,7 @@ class PhaseFieldStaggered:
         self.bc_u = Dirichlet(system.n_local * self.dim)
         self.bc_d = Dirichlet(system.n_local)
         self.pcg_tol, self.pcg_maxiter = pcg_tol, pcg_maxiter
-        self.pcg_fused, self.pcg_persistent, self.pcg_single_reduction = True, False, None
+        self.pcg_fused, self.pcg_persistent, self.pcg_single_reduction = True, False, False
         self._updatedDamage = self._updatedDisplacement = False
         self.info = {}
 
