@@ -538,6 +538,7 @@ __global__ void __launch_bounds__(kRedThreads)
         }
     }
     for (long long i = first; i < n; i += stride) pn[i] = (mask && !mask[i]) ? 0.0 : z[i] + beta * p[i];
+    __syncthreads();  // every thread's stores into the neighbours happen-before thread 0's fence (cumulative), hence before the flag
     if (threadIdx.x == 0) {
         if (P.n_send > 0) fence_sys();
         else __threadfence();
@@ -831,9 +832,11 @@ __global__ void __launch_bounds__(kRedThreads) k_cg2_push(const double* __restri
         const long long j0 = P.send_ptr[sidx], cnt = P.send_ptr[sidx + 1] - j0;
         for (long long j = first; j < cnt; j += stride) dst[j] = zn[P.send_idx[j0 + j]];
     }
-    fence_sys();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = atomicAdd(&own->ticket[2], 1u) == gridDim.x - 1;
+    __syncthreads();  // every thread's stores happen-before thread 0's fence (cumulative), hence before the flag
+    if (threadIdx.x == 0) {
+        fence_sys();
+        is_last = atomicAdd(&own->ticket[2], 1u) == gridDim.x - 1;
+    }
     __syncthreads();
     if (is_last && threadIdx.x == 0) {
         fence_sys();
