@@ -360,7 +360,8 @@ struct PcgCtrl {
 };
 constexpr int kCtrlBytes = 1024;
 static_assert(sizeof(PcgCtrl) <= kCtrlBytes, "control block");
-constexpr long long kSpinTimeoutCycles = 6000000000LL;  // ~3 s at 1.9 GHz: a lost peer must not hang the GPU
+constexpr long long kSpinTimeoutCycles = 20000000000LL;  // ~10 s at 1.9 GHz: a lost peer must not hang the GPU, a rank delayed
+                                                         // by a host-side pause (page-in, GC) must not be mistaken for one
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
     unsigned long long v;
