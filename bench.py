@@ -235,6 +235,9 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
 
+        # stdout carries exactly ONE JSON line: NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION) goes to stdout too
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     n = args.n
