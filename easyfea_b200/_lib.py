@@ -58,6 +58,7 @@ _I32P = ctypes.POINTER(c_i32)
 # name -> argtypes; every function returns int status except the ones listed in _RESTYPES
 SIGNATURES = {
     "efb_geometry": [_GP, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "efb_geometry_parts": [_GP, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp],
     "efb_elastic_Ke": [_GP, c_vp, c_vp, ctypes.c_int, c_f64, c_vp, c_vp],
     "efb_mass_Me": [_GP, c_vp, ctypes.c_int, c_f64, ctypes.c_int, c_f64, c_vp, c_vp],
     "efb_diffusion_Ke": [_GP, c_vp, ctypes.c_int, c_vp, ctypes.c_int, c_f64, c_f64, c_vp, c_vp],

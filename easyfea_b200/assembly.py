@@ -231,5 +231,16 @@ class Assembler:
                              else dict_group_data[g].numel() for g in groups) == 0:
             return sparse.csr_matrix(shape)
         pat = self.pattern(dof_n, isMatrix, Ndof, groups)
-        A = pat.assemble([dict_group_data[g] for g in groups])
+        datas = [dict_group_data[g] for g in groups]
+        if any(np.iscomplexobj(X) if not isinstance(X, torch.Tensor) else X.dtype.is_complex for X in datas):
+            # the reference bincounts the real and imaginary parts separately (_simu.py:1048-1053): two replays
+            if as_device:
+                raise TypeError("complex systems are assembled to scipy matrices only")
+            host = [X.cpu().numpy() if isinstance(X, torch.Tensor) else np.asarray(X) for X in datas]
+            re = dv.to_host(pat.replay([np.ascontiguousarray(X.real) for X in host]))
+            im = dv.to_host(pat.replay([np.ascontiguousarray(X.imag) for X in host]))
+            m = sparse.csr_matrix((re + 1j * im, dv.to_host(pat.indices), dv.to_host(pat.indptr)), shape=pat.shape)
+            m.has_canonical_format = True
+            return m
+        A = pat.assemble(datas)
         return A if as_device else A.to_scipy()

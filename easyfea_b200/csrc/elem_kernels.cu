@@ -68,6 +68,25 @@ static int launch_geometry(const efb_group* g, const GeomOut& o, cudaStream_t st
     return check_launch("efb_geometry");
 }
 
+template <int DIM, int NPE>
+__global__ void __launch_bounds__(256) k_geometry_parts(GroupView g, GeomPartsOut o, int EPB) {
+    extern __shared__ double smem[];
+    geometry_parts_block<DIM, NPE>(g, o, EPB, blockIdx.x, blockDim.x, smem);
+}
+
+template <int DIM, int NPE>
+static int launch_geometry_parts(const efb_group* g, const GeomPartsOut& o, cudaStream_t st) {
+    const bool grad = o.leftDisp || o.diffuse;
+    const int TPE = DIM * NPE, EPB = elems_per_block<DIM, NPE>(TPE, g->nPg, 0, grad);
+    const SmemMap<DIM, NPE> sm(g->nPg, EPB, 0, grad);
+    const size_t bytes = sizeof(double) * sm.total();
+    if (ensure_smem(k_geometry_parts<DIM, NPE>, bytes)) return 1;
+    const long long nblk = (g->Ne + EPB - 1) / EPB;
+    if (nblk == 0) return 0;
+    k_geometry_parts<DIM, NPE><<<(unsigned)nblk, EPB * TPE, bytes, st>>>(view_of(g), o, EPB);
+    return check_launch("efb_geometry_parts");
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Warp-specialised persistent kernel.  CTA = NCW consumer warps (the contraction: FP64 FMAs fed by broadcast LDS) + one
 // producer warp (gather of connectivity/coordinates/C and the per-Gauss-point geometry), decoupled by two geometry
@@ -558,6 +577,20 @@ extern "C" int efb_geometry(const efb_group* g, double* F, double* detF, double*
     if (validate(g)) return 1;
     GeomOut o{F, detF, jac, wJ, invF, dN, B};
 #define X(D, N) EFB_DISPATCH(D, N, (launch_geometry<D, N>(g, o, as_stream(stream))))
+    EFB_FOR_EACH_ELEM(X)
+#undef X
+    EFB_NO_INSTANCE(g)
+}
+
+extern "C" int efb_geometry_parts(const efb_group* g, int dof_n, double* leftDisp, double* reaction, double* diffuse,
+                                  double* source, void* stream) {
+    if (validate(g)) return 1;
+    if (dof_n < 1 || dof_n > 3) {
+        set_error("efb_geometry_parts: dof_n must be 1..3");
+        return 1;
+    }
+    GeomPartsOut o{leftDisp, reaction, diffuse, source, dof_n};
+#define X(D, N) EFB_DISPATCH(D, N, (launch_geometry_parts<D, N>(g, o, as_stream(stream))))
     EFB_FOR_EACH_ELEM(X)
 #undef X
     EFB_NO_INSTANCE(g)

@@ -235,6 +235,66 @@ EFB_D void geometry_block(const GroupView& g, const GeomOut& o, int EPB, long lo
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// G8-G10 export: the cached per-Gauss-point factors of the reference        _group_elem.py:1314-1407
+//   leftDisp (Ne,nPg,nPe*DIM,ns)        = wJ B^T                      Get_leftDispPart_e_pg :1315
+//   reaction (Ne,nPg,nPe*dof_n,nPe*dof_n) = (wJ N^T) N, N block-diagonal Get_ReactionPart_e_pg :1338
+//   diffuse  (Ne,nPg,nPe,DIM)           = wJ dN^T                     Get_DiffusePart_e_pg  :1363
+//   source   (Ne,nPg,nPe*dof_n,dof_n)   = wJ N^T                      Get_SourcePart_e_pg   :1383
+// ---------------------------------------------------------------------------------------------------------
+struct GeomPartsOut {
+    double *leftDisp, *reaction, *diffuse, *source;
+    int dof_n;
+};
+
+template <int DIM, int NPE>
+EFB_D void geometry_parts_block(const GroupView& g, const GeomPartsOut& o, int EPB, long long blockId, int nthreads, double* smem) {
+    constexpr int NS = StrainSize<DIM>::value, NDOF = DIM * NPE;
+    const int TPE = nthreads / EPB;
+    const bool grad = o.leftDisp || o.diffuse;
+    const SmemMap<DIM, NPE> sm(g.nPg, EPB, 0, grad);
+    const long long e0 = blockId * EPB;
+    const int nPg = g.nPg;
+    const double* Nt = smem + sm.off_N();
+    geometry_phases<DIM, NPE>(g, sm, e0, TPE, nthreads, smem, grad);
+    EFB_PHASE(tid, nthreads) {
+        const int el = tid / TPE, t = tid % TPE;
+        const long long e = e0 + el;
+        if (el < EPB && e < g.Ne) {
+            const double* E = sm.elem(smem, el);
+            const double* wJ = E + sm.o_wJ();
+            const double* gN = E + sm.o_gN();
+            constexpr int GS = SmemMap<DIM, NPE>::GS;
+            if (o.leftDisp) {
+                for (int i = t; i < nPg * NDOF * NS; i += TPE) {  // (p, col = a*DIM+d, s)
+                    const int p = i / (NDOF * NS), col = (i / NS) % NDOF, s = i % NS;
+                    o.leftDisp[e * (long long)(nPg * NDOF * NS) + i] = wJ[p] * B_entry<DIM>(s, col % DIM, gN + (p * NPE + col / DIM) * GS);
+                }
+            }
+            if (o.diffuse) {
+                for (int i = t; i < nPg * NPE * DIM; i += TPE) {  // (p, a, d)
+                    const int p = i / (NPE * DIM);
+                    o.diffuse[e * (long long)(nPg * NPE * DIM) + i] = wJ[p] * gN[(i / DIM) * GS + i % DIM];
+                }
+            }
+            const int dn = o.dof_n, nd = NPE * dn;
+            if (o.reaction) {
+                for (int i = t; i < nPg * nd * nd; i += TPE) {  // (p, r, c)
+                    const int p = i / (nd * nd), r = (i / nd) % nd, c = i % nd;
+                    o.reaction[e * (long long)(nPg * nd * nd) + i] =
+                        (r % dn == c % dn) ? (wJ[p] * Nt[p * NPE + r / dn]) * Nt[p * NPE + c / dn] : 0.0;
+                }
+            }
+            if (o.source) {
+                for (int i = t; i < nPg * nd * dn; i += TPE) {  // (p, r, comp)
+                    const int p = i / (nd * dn), r = (i / dn) % nd, comp = i % dn;
+                    o.source[e * (long long)(nPg * nd * dn) + i] = (r % dn == comp) ? wJ[p] * Nt[p * NPE + r / dn] : 0.0;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // O1: K_e = scale * sum_p wJ B^T C B                                   Operators/Bilinear.py:62-79
 //
 // With S = diag(1,..,1, 1/sqrt2,..) the Kelvin-Mandel operator is B = S G, G holding the plain gradients (DIM non-zeros

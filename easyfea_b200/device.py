@@ -29,8 +29,16 @@ def ptr(t) -> ctypes.c_void_p | None:
 def to_device(a, dtype=None) -> torch.Tensor:
     """host array -> contiguous device tensor; floats become float64, integer dtypes are kept unless `dtype` is given"""
     if isinstance(a, torch.Tensor):
-        return a.to(device=device(), dtype=dtype if dtype is not None else a.dtype).contiguous()
+        if dtype is None:  # the kernels read FP64: a float32 / float16 tensor must not travel as it is
+            dtype = torch.float64 if a.dtype.is_floating_point else a.dtype
+        elif not isinstance(dtype, torch.dtype):
+            dtype = getattr(torch, np.dtype(dtype).name)
+        if a.dtype.is_complex:
+            raise TypeError("complex data has no device representation here; split it into real and imaginary parts")
+        return a.to(device=device(), dtype=dtype).contiguous()
     arr = np.asarray(a)
+    if np.iscomplexobj(arr):
+        raise TypeError("complex data has no device representation here; split it into real and imaginary parts")
     if dtype is None:
         dtype = arr.dtype if arr.dtype.kind in "iu" else np.float64
     return torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype)).to(device())

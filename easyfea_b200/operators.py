@@ -78,6 +78,22 @@ def geometry_dev(groupElem, matrixType, want=("jac",)):
     return out
 
 
+def geometry_parts_dev(groupElem, matrixType, want=("leftDisp",), dof_n: int = 1):
+    """The cached per-Gauss-point factors G8-G10 on the device; `want` ⊂ {leftDisp, reaction, diffuse, source}."""
+    dg = device_group(groupElem)
+    mt = _mt(matrixType)
+    nPg, dim, nPe, Ne = dg.nPg(mt), dg.dim, dg.nPe, dg.Ne
+    ns = 3 if dim == 2 else 6
+    dof_n = int(dof_n)
+    nd = nPe * dof_n
+    shapes = {"leftDisp": (Ne, nPg, nPe * dim, ns), "reaction": (Ne, nPg, nd, nd), "diffuse": (Ne, nPg, nPe, dim),
+              "source": (Ne, nPg, nd, dof_n)}
+    out = {k: dv.empty(shapes[k]) for k in want}
+    _lib.call("efb_geometry_parts", dg.cstruct(mt), dof_n, *[dv.ptr(out.get(k)) for k in ("leftDisp", "reaction", "diffuse", "source")],
+              dv.stream_ptr())
+    return out
+
+
 def elastic_Ke_dev(groupElem, C, matrixType=RIGI, scale=1.0, out=None):
     dg = device_group(groupElem)
     mt = _mt(matrixType)
@@ -222,3 +238,23 @@ def _make_getter(name, key):
 
 for _n, _k in _GETTERS.items():
     globals()[_n] = _make_getter(_n, _k)
+
+
+def Get_leftDispPart_e_pg(groupElem, matrixType) -> np.ndarray:
+    """wJ·Bᵀ -> (Ne, nPg, nPe·dim, ns); replaces _group_elem.py:1314-1333."""
+    return dv.to_host(geometry_parts_dev(groupElem, matrixType, ("leftDisp",))["leftDisp"])
+
+
+def Get_ReactionPart_e_pg(groupElem, matrixType, dof_n: int = 1) -> np.ndarray:
+    """wJ·NᵀN (block-diagonal N for dof_n > 1) -> (Ne, nPg, nPe·dof_n, nPe·dof_n); replaces _group_elem.py:1337-1360."""
+    return dv.to_host(geometry_parts_dev(groupElem, matrixType, ("reaction",), dof_n)["reaction"])
+
+
+def Get_DiffusePart_e_pg(groupElem, matrixType) -> np.ndarray:
+    """wJ·∇Nᵀ -> (Ne, nPg, nPe, dim); replaces _group_elem.py:1362-1380."""
+    return dv.to_host(geometry_parts_dev(groupElem, matrixType, ("diffuse",))["diffuse"])
+
+
+def Get_SourcePart_e_pg(groupElem, matrixType, dof_n: int = 1) -> np.ndarray:
+    """wJ·Nᵀ -> (Ne, nPg, nPe·dof_n, dof_n); replaces _group_elem.py:1382-1407."""
+    return dv.to_host(geometry_parts_dev(groupElem, matrixType, ("source",), dof_n)["source"])

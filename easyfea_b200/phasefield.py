@@ -69,6 +69,9 @@ class PhaseFieldModel:
     def __init__(self, material, split, regularization, Gc: float, l0: float, solver="History", A=None):
         self.material = material if isinstance(material, IsotropicMaterial) else IsotropicMaterial.from_reference(material)
         self.split, self.regularization, self.solver = _name(split), _name(regularization), _name(solver)
+        if self.solver not in ("History", "HistoryDamage"):
+            # BoundConstrain is a bound-constrained least-squares solve (scipy lsq_linear, Solvers.py:376-384): not a CG system
+            raise NotImplementedError(f"phase-field solver {self.solver} is outside the device path (History, HistoryDamage)")
         if self.split not in SPLIT_IDS:
             raise NotImplementedError(f"split {self.split} is outside the hot path (Bourdin, Amor, Miehe, Stress, He)")
         assert self.regularization in REGU_IDS, "regu error"
@@ -120,6 +123,18 @@ class PhaseFieldModel:
                   dv.ptr(out.get("psiP")), dv.ptr(out.get("psiM")), dv.ptr(gd), dv.ptr(out.get("Cdeg")), dv.stream_ptr())
         return out
 
+    def sigma_dev(self, eps):
+        """(SigmaP, SigmaM) (Ne,nPg,ns) = (cP eps, cM eps) on the device, Models/_phasefield.py:360-394"""
+        eps = dv.to_device(eps)
+        Ne, nPg, ns = eps.shape
+        c = self.split_dev(eps, ("cP", "cM"))
+        out = []
+        for key in ("cP", "cM"):
+            sig = dv.empty((Ne, nPg, ns))
+            _lib.call("efb_hooke", Ne, nPg, ns, dv.ptr(eps), dv.ptr(c[key]), 2, dv.ptr(sig), dv.stream_ptr())
+            out.append(sig)
+        return out[0], out[1]
+
     def degradation_dev(self, d_n, groupElem, matrixType, k_res=1e-12):
         dg = device_group(groupElem)
         mt = op._mt(matrixType)
@@ -155,9 +170,8 @@ class PhaseFieldModel:
 
     def Calc_Sigma_e_pg(self, Epsilon_e_pg):
         """(SigmaP, SigmaM) (Ne,nPg,ns); replaces :360-394."""
-        eps = np.asarray(Epsilon_e_pg)
-        cP, cM = self.Calc_C(eps)
-        return np.einsum("epij,epj->epi", cP, eps), np.einsum("epij,epj->epi", cM, eps)
+        sP, sM = self.sigma_dev(np.asarray(Epsilon_e_pg))
+        return dv.to_host(sP), dv.to_host(sM)
 
     def Get_g_e_pg(self, d_n, groupElem, matrixType, k_res=1e-12):
         """g = (1 - N d)^2 + k_res (Ne,nPg); replaces :295-317."""

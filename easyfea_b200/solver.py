@@ -113,7 +113,15 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
     if free_mask is not None:
         mask = dv.to_device(free_mask).to(torch.uint8).contiguous()
         assert mask.numel() == nrows
-    maxiter = int(maxiter if maxiter is not None else 10 * n_glob)
+    if maxiter is None:
+        # rank-independent default: every rank must leave the loop in the same iteration (collectives / peer flags pair up)
+        if comm is not None:
+            t = torch.tensor([float(n_glob)], dtype=torch.float64, device=dev)
+            comm.all_reduce_max(t)
+            maxiter = 10 * int(t.item())
+        else:
+            maxiter = 10 * n_glob
+    maxiter = int(maxiter)
     P = _lib.load().efb_pcg_partials_size()
     partials = dv.empty((P,))
     scal = torch.zeros(6, dtype=torch.float64, device=dev)  # [rz, pAp, rz_new, rr, -, -]
@@ -163,7 +171,7 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
         reduce_to(3, 1)
         bnorm2 = float(scal[3].item())
     if bnorm2 == 0.0:
-        return x.clone(), {"iterations": 0, "rel_residual": 0.0, "converged": True}
+        return x.clone(), {"iterations": 0, "rel_residual": 0.0, "converged": True, "rhs_norm": 0.0}
 
     # initial residual with the actual start vector
     if comm is not None:
@@ -241,5 +249,5 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
             if rr != rr:
                 raise _lib.EfbError("PCG broke down (NaN residual): matrix not SPD on the free dofs?")
     rel = (rr / bnorm2) ** 0.5
-    return x.clone(), {"iterations": it, "rel_residual": rel, "converged": rel <= tol, "fused": ws is not None,
+    return x.clone(), {"iterations": it, "rel_residual": rel, "converged": rel <= tol, "rhs_norm": bnorm2 ** 0.5, "fused": ws is not None,
                        "persistent": ws is not None and use_persistent, "single_reduction": ws is not None and bool(single_reduction)}

@@ -72,6 +72,7 @@ class Dirichlet:
         self.n = int(n_dofs_local)
         self.dofs = np.empty(0, dtype=np.int64)
         self.values = np.empty(0)
+        self._dev = None
 
     def add(self, nodes, values, components, dof_n: int):
         """`add_dirichlet(nodes, values, directions)` of the reference (_simu.py `add_dirichlet`): one value per component."""
@@ -79,18 +80,38 @@ class Dirichlet:
         for val, c in zip(values, components):
             self.dofs = np.concatenate([self.dofs, nodes * dof_n + int(c)])
             self.values = np.concatenate([self.values, np.full(nodes.size, float(val))])
+        self._dev = None
+
+    def unique(self):
+        """(dofs, values) with one entry per dof: the LAST prescription wins, as sequential assignment does in the reference
+        (`x[dofs] = values` on the host); a scatter with duplicate indices has no defined winner on the device"""
+        rev_dofs, rev_vals = self.dofs[::-1], self.values[::-1]
+        u, first = np.unique(rev_dofs, return_index=True)
+        return u, rev_vals[first]
 
     def device_arrays(self, n_owned_dofs: int):
-        """(free_mask uint8 (n_owned_dofs), dofs int64 tensor, values tensor) — later entries win, like the reference"""
-        mask = np.ones(n_owned_dofs, dtype=np.uint8)
-        sel = self.dofs < n_owned_dofs
-        mask[self.dofs[sel]] = 0
-        return dv.to_device(mask, np.uint8), dv.to_device(self.dofs, np.int64), dv.to_device(self.values)
+        """(free_mask uint8 (n_owned_dofs), dofs int64 tensor, values tensor), deduplicated and uploaded once per set of
+        conditions"""
+        if self._dev is None or self._dev[0] != n_owned_dofs:
+            dofs, values = self.unique()
+            mask = np.ones(n_owned_dofs, dtype=np.uint8)
+            mask[dofs[dofs < n_owned_dofs]] = 0
+            self._dev = (n_owned_dofs, dv.to_device(mask, np.uint8), dv.to_device(dofs, np.int64), dv.to_device(values))
+        return self._dev[1:]
 
 
 def _apply(x_local: torch.Tensor, dofs: torch.Tensor, values: torch.Tensor) -> None:
     if dofs.numel():
-        x_local[dofs] = values
+        x_local[dofs] = values  # `dofs` is duplicate-free (Dirichlet.unique)
+
+
+def _check(info, what: str):
+    """a solve that stops at `maxiter` must not pass silently (the reference's direct solvers cannot fail this way)"""
+    if not info["converged"]:
+        import warnings
+
+        warnings.warn(f"{what}: Jacobi-PCG stopped after {info['iterations']} iterations at relative residual "
+                      f"{info['rel_residual']:.3e}", RuntimeWarning, stacklevel=3)
 
 
 class ElasticSolve:
@@ -120,6 +141,7 @@ class ElasticSolve:
         rhs = torch.zeros(nown, dtype=torch.float64, device=self.u.device) if b is None else dv.to_device(b)
         x, info = pcg(K, rhs, x0=self.u, free_mask=mask, tol=tol, maxiter=maxiter, comm=self.sys.comm(d), fused=self.pcg_fused,
                       persistent=self.pcg_persistent, single_reduction=self.pcg_single_reduction)
+        _check(info, "ElasticSolve")
         self.u[:nown] = x
         self.sys.refresh_halo(self.u, d)
         return self.u, info
@@ -139,6 +161,7 @@ class PhaseFieldStaggered:
         self.psiP_old = None   # history field, replaced in Save_Iter only (:623-625)
         self.bc_u = Dirichlet(system.n_local * self.dim)
         self.bc_d = Dirichlet(system.n_local)
+        self.f_ext = None      # nodal external forces of the displacement problem (owned dofs), `add_neumann`
         self.pcg_tol, self.pcg_maxiter = pcg_tol, pcg_maxiter
         self.pcg_fused, self.pcg_persistent, self.pcg_single_reduction = True, False, False
         self._updatedDamage = self._updatedDisplacement = False
@@ -147,6 +170,29 @@ class PhaseFieldStaggered:
     def Bc_Init(self):
         self.bc_u = Dirichlet(self.sys.n_local * self.dim)
         self.bc_d = Dirichlet(self.sys.n_local)
+        self.f_ext = None
+
+    def add_neumann(self, nodes, values, components):
+        """`add_neumann(nodes, values, directions)` of the reference (_simu.py:2476-2510): point loads, one value per component
+        applied to every listed node (LOCAL ids; loads on halo nodes belong to their owner rank and are dropped here)"""
+        nown = self.sys.n_owned * self.dim
+        if self.f_ext is None:
+            self.f_ext = torch.zeros(nown, dtype=torch.float64, device=self.u.device)
+        nodes = np.asarray(nodes, dtype=np.int64)
+        nodes = nodes[nodes < self.sys.n_owned]
+        for val, c in zip(values, components):
+            dofs = dv.to_device(nodes * self.dim + int(c), np.int64)
+            self.f_ext.index_add_(0, dofs, torch.full((dofs.numel(),), float(val), dtype=torch.float64, device=self.u.device))
+
+    def Calc_Psi_Ext(self) -> float:
+        """`_Calc_Psi_Ext` (Simulations/_phasefield.py:819-836): u . f over the owned dofs, summed over the ranks"""
+        if self.f_ext is None:
+            return 0.0
+        e = torch.dot(self.u[: self.f_ext.numel()], self.f_ext).reshape(1)
+        c = self.sys.comm(self.dim)
+        if c is not None:
+            c.all_reduce_sum(e)
+        return float(e.item())
 
     def add_dirichlet(self, nodes, values, components, problemType="elastic"):
         if problemType == "damage":
@@ -212,6 +258,7 @@ class PhaseFieldStaggered:
         s.refresh_halo(self.d, 1)
         x, info = pcg(K, F, x0=self.d, free_mask=mask, tol=self.pcg_tol, maxiter=self.pcg_maxiter, comm=s.comm(1),
                       fused=self.pcg_fused, persistent=self.pcg_persistent, single_reduction=self.pcg_single_reduction)
+        _check(info, "PhaseFieldStaggered damage solve")
         self.d[: s.n_owned] = x
         s.refresh_halo(self.d, 1)
         self._updatedDisplacement = False  # new damage -> new displacement matrices (:367-368)
@@ -226,9 +273,10 @@ class PhaseFieldStaggered:
         mask, dofs, vals = self.bc_u.device_arrays(nown)
         _apply(self.u, dofs, vals)
         s.refresh_halo(self.u, dim)
-        rhs = torch.zeros(nown, dtype=torch.float64, device=self.u.device)
+        rhs = torch.zeros(nown, dtype=torch.float64, device=self.u.device) if self.f_ext is None else self.f_ext
         x, info = pcg(K, rhs, x0=self.u, free_mask=mask, tol=self.pcg_tol, maxiter=self.pcg_maxiter, comm=s.comm(dim),
                       fused=self.pcg_fused, persistent=self.pcg_persistent, single_reduction=self.pcg_single_reduction)
+        _check(info, "PhaseFieldStaggered displacement solve")
         self.u[:nown] = x
         s.refresh_halo(self.u, dim)
         self._updatedDamage = False  # new displacement -> new damage matrices (:372-373)
@@ -252,20 +300,21 @@ class PhaseFieldStaggered:
 
     def Solve(self, tolConv=1.0, maxIter=500, convOption=0):
         """(u, d, converged) — `Simulations.PhaseField.Solve` (:300-432).  convOption 0: max |d_np1 - d_n|; 1: relative change
-        of the crack energy; 2: of the total energy (Ambati 2015; no external work: this driver carries no Neumann loads);
+        of the crack energy; 2: of the total energy crack + elastic - external work (Ambati 2015, :354-361, 381-384);
         3: summed relative increments of u and d (Pech 2022)."""
         assert 0 < tolConv <= 1, "tolConv must be between 0 and 1."
         assert maxIter > 1, "Must be > 1."
         assert convOption in (0, 1, 2, 3)
         nd, nu = self.sys.n_owned, self.sys.n_owned * self.dim
         Niter, converged, convIter = 0, False, 0.0
+        old_damage = self.d[:nd].clone() if self.pfm.solver == "HistoryDamage" else None
         while not converged and Niter < maxIter:
             Niter += 1
             d_n, u_n = self.d[:nd].clone(), self.u[:nu].clone()
             if convOption == 1:
                 E_n = self.Calc_Psi_Crack()
             elif convOption == 2:
-                E_n = self.Calc_Psi_Crack() + self.Calc_Psi_Elas()
+                E_n = self.Calc_Psi_Crack() + self.Calc_Psi_Elas() - self.Calc_Psi_Ext()
             self.solve_damage()
             self.solve_elastic()
             d1, u1 = self.d[:nd], self.u[:nu]
@@ -274,7 +323,7 @@ class PhaseFieldStaggered:
             elif convOption in (1, 2):
                 E1 = self.Calc_Psi_Crack()
                 if convOption == 2:
-                    E1 += self.Calc_Psi_Elas()
+                    E1 += self.Calc_Psi_Elas() - self.Calc_Psi_Ext()
                 convIter = abs(E_n - E1) if E1 == 0 else abs((E_n - E1) / E1)
             else:
                 def rel_sum(new, old):
@@ -292,6 +341,11 @@ class PhaseFieldStaggered:
                 converged = convD <= tolConv and convU <= tolConv * 0.999
             else:
                 converged = convIter <= tolConv
+        if old_damage is not None:
+            # HistoryDamage: irreversibility enforced on the nodal field at the end of the solve (:400-404)
+            self.d[:nd] = torch.maximum(old_damage, self.d[:nd])
+            self.sys.refresh_halo(self.d, 1)
+            self._updatedDisplacement = False
         self.Niter, self.convIter = Niter, convIter
         return self.u, self.d, converged
 

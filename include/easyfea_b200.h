@@ -56,6 +56,13 @@ enum { EFB_TENSOR_CONST = 0, EFB_TENSOR_E = 1, EFB_TENSOR_E_PG = 2 };
 int efb_geometry(const efb_group* g, double* F, double* detF, double* jac, double* wJ, double* invF, double* dN,
                  double* B, void* stream);
 
+/* G8-G10, the cached per-Gauss-point factors (_group_elem.py:1314-1407); any output may be NULL:
+ * leftDisp (Ne,nPg,nPe*dim,ns) = wJ B^T  Get_leftDispPart_e_pg :1315;  reaction (Ne,nPg,nPe*dof_n,nPe*dof_n) = wJ N^T N
+ * with the block-diagonal N of Get_N_pg_rep  Get_ReactionPart_e_pg :1338;  diffuse (Ne,nPg,nPe,dim) = wJ dN^T
+ * Get_DiffusePart_e_pg :1363;  source (Ne,nPg,nPe*dof_n,dof_n) = wJ N^T  Get_SourcePart_e_pg :1383.  dof_n in 1..3. */
+int efb_geometry_parts(const efb_group* g, int dof_n, double* leftDisp, double* reaction, double* diffuse, double* source,
+                       void* stream);
+
 /* ---- O1-O4: operators, EasyFEA/FEM/Operators/Bilinear.py, Linear.py ---------------------------------- */
 /* LinearizedElasticity Bilinear.py:62-79: out (Ne,ndof,ndof) = scale * sum_p wJ B^T C B; C (ns,ns) with leading
  * axes per C_mode (device).  A homogeneous C (EFB_TENSOR_CONST) is passed to the kernel by value: give its ns*ns

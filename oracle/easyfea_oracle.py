@@ -111,6 +111,18 @@ def N_rep(N_pg, dof_n):
     return out
 
 
+def geometry_parts(geo, N_pg, dof_n=1):
+    """The cached per-Gauss-point factors of the reference, _group_elem.py:1314-1407:
+    leftDisp = wJ B^T (:1315-1333), reaction = (wJ N^T) N (:1338-1360), diffuse = wJ dN^T (:1363-1380),
+    source = wJ N^T (:1383-1407), N block-diagonal for dof_n > 1."""
+    wJ = geo["wJ"][:, :, None, None]
+    B = B_matrix(geo["dN"])
+    Nr = N_rep(N_pg, dof_n)[None]  # (1, nPg, dof_n, ndof)
+    NrT = np.swapaxes(Nr, -1, -2)
+    return {"leftDisp": wJ * np.swapaxes(B, -1, -2), "reaction": (wJ * NrT) @ Nr,
+            "diffuse": wJ * np.swapaxes(geo["dN"], -1, -2), "source": wJ * NrT}
+
+
 def _lead(coef, Ne, nPg, tail=0):
     """Broadcast rule of FeArray.broadcast, EasyFEA/FEM/_linalg.py:426-476 -> array broadcastable to (Ne,nPg,...)."""
     a = np.asarray(coef, dtype=float)

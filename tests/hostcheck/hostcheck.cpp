@@ -50,6 +50,22 @@ extern "C" int hc_geometry(const efb_group* g, double* F, double* detF, double* 
     return 2;
 }
 
+extern "C" int hc_geometry_parts(const efb_group* g, int dof_n, double* leftDisp, double* reaction, double* diffuse, double* source) {
+    GeomPartsOut o{leftDisp, reaction, diffuse, source, dof_n};
+    const bool grad = leftDisp || diffuse;
+#define X(D, N)                                                                                   \
+    if (g->dim == D && g->nPe == N) {                                                             \
+        const int TPE = D * N, EPB = epb_for(TPE);                                                \
+        SmemMap<D, N> sm(g->nPg, EPB, 0, grad);                                                   \
+        std::vector<double> smem(sm.total());                                                     \
+        for (long long b = 0; b * EPB < g->Ne; ++b) geometry_parts_block<D, N>(view_of(g), o, EPB, b, EPB * TPE, smem.data()); \
+        return 0;                                                                                 \
+    }
+    FOR_EACH(X)
+#undef X
+    return 2;
+}
+
 template <int D, int N, int CMODE>
 static void run_elastic(const efb_group* g, const double* C, double scale, double* out) {
     constexpr int NS = StrainSize<D>::value;

@@ -50,6 +50,22 @@ def test_geometry_getters(efb, elemType, mt):
 
 
 @pytest.mark.parametrize("elemType", list(ELEM_CASES))
+@pytest.mark.parametrize("mt", ["rigi", "mass"])
+def test_geometry_part_getters(efb, elemType, mt):
+    """G8-G10 (_group_elem.py:1314-1407) through the C ABI"""
+    coords, connect = make_mesh(elemType)
+    g = efb.mesh.ElemGroup(elemType, connect, coords)
+    geo, tab = _geo(efb, elemType, coords, connect, mt)
+    op = efb.op
+    for dof_n in (1, g.dim):
+        ref = orc.geometry_parts(geo, tab.N_pg, dof_n)
+        assert rel_err(op.Get_ReactionPart_e_pg(g, mt, dof_n), ref["reaction"]) < TOL
+        assert rel_err(op.Get_SourcePart_e_pg(g, mt, dof_n), ref["source"]) < TOL
+    assert rel_err(op.Get_leftDispPart_e_pg(g, mt), ref["leftDisp"]) < TOL
+    assert rel_err(op.Get_DiffusePart_e_pg(g, mt), ref["diffuse"]) < TOL
+
+
+@pytest.mark.parametrize("elemType", list(ELEM_CASES))
 def test_operators_all_broadcast_modes(efb, elemType):
     rng = np.random.default_rng(3)
     coords, connect = make_mesh(elemType)

@@ -36,6 +36,28 @@ def test_geometry(hostcheck, elemType, mt):
 
 
 @pytest.mark.parametrize("elemType", list(ELEM_CASES))
+@pytest.mark.parametrize("mt", ["rigi", "mass"])
+def test_geometry_parts(hostcheck, elemType, mt):
+    """G8-G10: Get_leftDispPart / ReactionPart / DiffusePart / SourcePart_e_pg (_group_elem.py:1314-1407)"""
+    coords, connect = make_mesh(elemType)
+    g, keep, tab = host_group(elemType, coords, connect, mt)
+    dim, nPe, nPg, Ne = g.dim, g.nPe, g.nPg, g.Ne
+    ns = 3 if dim == 2 else 6
+    geo = _geo(elemType, coords, connect, tab)
+    for dof_n in (1, dim):
+        nd = nPe * dof_n
+        left = np.empty((Ne, nPg, nPe * dim, ns)); reac = np.empty((Ne, nPg, nd, nd))
+        diff = np.empty((Ne, nPg, nPe, dim)); src = np.empty((Ne, nPg, nd, dof_n))
+        assert hostcheck.hc_geometry_parts(ctypes.byref(g), I(dof_n), p(left), p(reac), p(diff), p(src)) == 0
+        ref = orc.geometry_parts(geo, tab.N_pg, dof_n)
+        for name, arr in (("leftDisp", left), ("reaction", reac), ("diffuse", diff), ("source", src)):
+            assert rel_err(arr, ref[name]) < TOL, (name, dof_n)
+    reac = np.empty((Ne, nPg, nPe, nPe))  # outputs are optional: mass-type factors alone need no gradient table
+    assert hostcheck.hc_geometry_parts(ctypes.byref(g), I(1), None, p(reac), None, None) == 0
+    assert rel_err(reac, orc.geometry_parts(geo, tab.N_pg, 1)["reaction"]) < TOL
+
+
+@pytest.mark.parametrize("elemType", list(ELEM_CASES))
 @pytest.mark.parametrize("C_mode", [0, 1, 2])
 def test_elastic_Ke(hostcheck, elemType, C_mode):
     rng = np.random.default_rng(3)
