@@ -81,6 +81,10 @@ SIGNATURES = {
     "efb_csr_compact_rows": [c_i64, c_vp, c_vp, c_vp, c_vp],
     "efb_csr_replay_matrix": [ctypes.c_int, _PP, _I64P, _I32P, ctypes.c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp],
     "efb_csr_replay_vector": [ctypes.c_int, _PP, _I64P, _I32P, ctypes.c_int, c_i64, c_vp, c_vp, c_vp, c_vp],
+    "efb_assemble_elastic": [_GP, c_vp, c_vp, c_f64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
+                             c_vp, c_vp],
+    "efb_assemble_elastic_smem": [ctypes.c_int] * 6,
+    "efb_assemble_elastic_group": [ctypes.c_int] * 3,
     "efb_spmv_csr": [c_i64, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, ctypes.c_int, c_vp],
     "efb_spmv_nodeblock": [c_i64, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, ctypes.c_int, c_vp],
     "efb_csr_diagonal": [c_i64, c_i64, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp],

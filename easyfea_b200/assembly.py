@@ -244,3 +244,170 @@ class Assembler:
             return m
         A = pat.assemble(datas)
         return A if as_device else A.to_scipy()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fused element integration + assembly (homogeneous C): the one-time node schedule of `efb_assemble_elastic`
+# ---------------------------------------------------------------------------------------------------------
+def morton_order(xyz: torch.Tensor, dim: int, return_codes: bool = False):
+    """Permutation that sorts points along a Z-order curve of a point lattice.  The lattice index of a point along an axis
+    is its RANK along that axis divided into m_d equal-population slabs, m_d = the number of lattice planes a box with n
+    points and one spacing h has along that axis (prod_d (ext_d / h + 1) = n): exact for structured meshes (jittered or
+    not: every plane holds the same number of points), population-adaptive for unstructured ones.  Consecutive runs of 2^k
+    points are then compact bricks.  `xyz` (n, >= dim) on any device; stable, deterministic."""
+    n = xyz.shape[0]
+    if n == 0:
+        e = torch.empty(0, dtype=torch.int64, device=xyz.device)
+        return (e, e) if return_codes else e
+    x = xyz[:, :dim].to(torch.float64)
+    lo, hi = x.min(0).values, x.max(0).values
+    ext = [max(float(v), 0.0) for v in (hi - lo).tolist()]
+    big = max(ext) if max(ext) > 0 else 1.0
+    h_lo, h_hi = big * 1e-9, big * 2.0
+    for _ in range(200):  # bisection on the spacing
+        h = 0.5 * (h_lo + h_hi)
+        cells = 1.0
+        for v in ext:
+            cells *= v / h + 1.0
+        if cells > n:
+            h_lo = h
+        else:
+            h_hi = h
+    h = 0.5 * (h_lo + h_hi)
+    nbits = 20 if dim == 3 else 30
+    code = torch.zeros(n, dtype=torch.int64, device=xyz.device)
+    ar = torch.arange(n, dtype=torch.int64, device=xyz.device)
+    for d in range(dim):
+        m = max(int(round(ext[d] / h)) + 1, 1)
+        rank = torch.empty(n, dtype=torch.int64, device=xyz.device)
+        rank[torch.argsort(x[:, d], stable=True)] = ar
+        q = torch.clamp((rank * m) // n, 0, 2**nbits - 1)
+        for bit in range(nbits):
+            code |= ((q >> bit) & 1) << (bit * dim + d)
+    order = torch.argsort(code, stable=True)
+    return (order, code[order]) if return_codes else order
+
+
+class FusedSchedule:
+    """Node clusters + per-cluster element lists + per-task descriptors for `efb_assemble_elastic` (csrc/fused_kernels.cuh).
+    Built once per (group, node graph) with torch tensor ops on the device the graph lives on — preprocessing, like the CSR
+    pattern itself; nothing here runs per assembly."""
+
+    def __init__(self, graph: NodeGraph, n_nodes: int = None, S: int = None, smem_budget: int = 110 * 1024, nPg: int = None):
+        if len(graph.dgs) != 1:
+            raise NotImplementedError("the fused assembly handles one element group")
+        dg = graph.dgs[0]
+        self.graph, self.dg = graph, dg
+        dim, nPe, dev = dg.dim, dg.nPe, graph.rowptr.device
+        n_nodes = graph.Nn if n_nodes is None else min(int(n_nodes), graph.Nn)
+        self.n_nodes, self.dof_n = n_nodes, dim
+        self.nPg = int(dg.nPg("rigi") if nPg is None else nPg)
+        G = _lib.load().efb_assemble_elastic_group(dim, nPe, self.nPg)  # nodes per warp of the kernel instantiation
+        if G < 1:
+            raise NotImplementedError(f"no fused assembly kernel for dim={dim}, nPe={nPe}")
+        rowptr, adjptr = graph.rowptr, graph.adjptr
+        cnt_all = (rowptr[1:n_nodes + 1] - rowptr[:n_nodes])
+        # coordinates per GLOBAL node id (the group stores local rows): scatter through the two connectivities
+        xyz = torch.zeros((graph.Nn, 3), dtype=torch.float64, device=dev)
+        xyz[dg.connect_glob.reshape(-1).long()] = dg.coord[dg.connect.reshape(-1).long()][:, :3]
+        used = torch.nonzero(cnt_all > 0).reshape(-1)
+        perm, codes = morton_order(xyz[used], dim, return_codes=True)
+        order = used[perm]
+        self.order = order
+        nn = int(order.numel())
+        cnt = cnt_all[order]
+        tptr = torch.zeros(nn + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(cnt, 0, out=tptr[1:])
+        n_tasks = int(tptr[-1].item()) if nn else 0
+        knode = torch.repeat_interleave(torch.arange(nn, device=dev), cnt)           # ordered-node index of every task
+        s = rowptr[order][knode] + (torch.arange(n_tasks, device=dev) - tptr[knode])  # its index in qlist
+        q = graph.qlist[s]
+        e, a = q // nPe, q % nPe
+        Ne = dg.Ne
+        max_deg = max(graph.max_deg, 1)
+        ar = torch.arange(nn, device=dev)
+
+        def clusters(Sc):
+            """clusters = the Morton cells of log2(Sc) interleaved bits (a compact brick of the lattice each), cut into runs of at
+            most Sc nodes where a cell holds more: (cluster id, position inside the cluster) of every ordered node"""
+            shift = max(int(Sc).bit_length() - 1, 0)
+            gk = codes >> shift
+            newg = torch.ones(nn, dtype=torch.bool, device=dev)
+            newg[1:] = gk[1:] != gk[:-1]
+            gstart = torch.cummax(torch.where(newg, ar, torch.zeros_like(ar)), 0).values
+            pig = ar - gstart
+            start = newg | (pig % Sc == 0)
+            return torch.cumsum(start.to(torch.int64), 0) - 1, pig % Sc
+
+        # cluster size: the largest power-of-two multiple of G (at most 16 warps) whose biggest cluster fits the budget
+        cands = [S] if S else [c * G for c in (16, 8, 4, 2, 1) if c * G <= 64]
+        chosen = None
+        for Sc in cands:
+            if Sc & (Sc - 1):
+                raise ValueError("the cluster size must be a power of two")
+            cl_node, pos_node = clusters(Sc)
+            ncl = int(cl_node[-1].item()) + 1 if nn else 0
+            cl = cl_node[knode]
+            ukey, inv = torch.unique(cl * Ne + e, sorted=True, return_inverse=True)
+            cl_eptr = torch.searchsorted(ukey // Ne, torch.arange(ncl + 1, device=dev)).to(torch.int64)
+            cap_e = int((cl_eptr[1:] - cl_eptr[:-1]).max().item()) if ncl else 0
+            chosen = (Sc, cl_node, pos_node, cl, ukey, inv, ncl, cl_eptr, cap_e)
+            if S or self._fits(dim, nPe, self.nPg, Sc, cap_e, max_deg, smem_budget):
+                break
+        Sc, cl_node, pos_node, cl, ukey, inv, ncl, cl_eptr, cap_e = chosen
+        self.S, self.n_clusters, self.cap_e, self.max_deg = Sc, ncl, cap_e, max_deg
+        le = inv - cl_eptr[cl]
+        assert cap_e < 65536 and nPe < 256
+        self.desc = (le | (a << 16)).to(torch.int32)
+        self.tpos = graph.pos.reshape(-1, nPe)[q].contiguous()                       # (n_tasks, nPe) int32
+        # coordinate rows of the clusters' elements, one fixed-size slab per cluster (-1 = empty): the kernel finds its slab
+        # from the CTA index alone, so the gather is a two-level chain (connectivity -> coordinates)
+        ucl = ukey // Ne
+        conn = torch.full((ncl * cap_e, nPe), -1, dtype=torch.int32, device=dev)
+        conn[ucl * cap_e + (torch.arange(ukey.numel(), device=dev) - cl_eptr[ucl])] = dg.connect.reshape(-1, nPe)[ukey % Ne]
+        self.cl_conn = conn
+        self.cl_ne = (cl_eptr[1:] - cl_eptr[:-1]).to(torch.int32).contiguous()
+        self.n_integrated = int(ukey.numel())
+        d2 = dim * dim
+        nodes = torch.full((ncl * Sc, 4), -1, dtype=torch.int64, device=dev)
+        nodes[:, 1:] = 0
+        k = cl_node * Sc + pos_node
+        nodes[k, 0] = order
+        nodes[k, 1] = d2 * adjptr[order]
+        nodes[k, 2] = (adjptr[order + 1] - adjptr[order]) | (cnt << 32)
+        nodes[k, 3] = tptr[:-1]
+        self.cl_nodes = nodes.contiguous()
+        self.n_tasks = n_tasks
+
+    @staticmethod
+    def _fits(dim, nPe, nPg, S, cap_e, max_deg, budget) -> bool:
+        need = smem_bytes(dim, nPe, nPg, S, cap_e, max_deg)
+        return need is not None and need <= budget
+
+    def redundancy(self) -> float:
+        """elements integrated per launch / elements of the group (each element is integrated once per cluster touching it)"""
+        return float(self.n_integrated) / max(self.dg.Ne, 1)
+
+
+def smem_bytes(dim, nPe, nPg, S, cap_e, max_deg):
+    """dynamic shared memory of one CTA of the fused kernel (`efb_assemble_elastic_smem`), None without an instantiation"""
+    n = _lib.load().efb_assemble_elastic_smem(int(dim), int(nPe), int(nPg), int(S), int(cap_e), int(max_deg))
+    return None if n < 0 else int(n)
+
+
+def assemble_elastic_fused(sched: FusedSchedule, C, matrixType="rigi", scale: float = 1.0, out: torch.Tensor = None):
+    """CSR `data` of K = Assembly(LinearizedElasticity(group, C)) for a homogeneous C, element matrices never materialised
+    (`efb_assemble_elastic`).  Rows of the scheduled nodes are written; returns `out` (nnz)."""
+    dg, g = sched.dg, sched.graph
+    mt = getattr(matrixType, "value", str(matrixType))
+    C = np.ascontiguousarray(np.asarray(C, dtype=np.float64))
+    ns = 3 if dg.dim == 2 else 6
+    if C.shape != (ns, ns):
+        raise ValueError(f"the fused assembly needs a homogeneous ({ns}, {ns}) C; got {C.shape}")
+    if out is None:
+        out = dv.empty((g.nnz_node * dg.dim * dg.dim,))
+    w = np.ascontiguousarray(dv.to_host(dg.tables(mt)[2]))
+    _lib.call("efb_assemble_elastic", dg.cstruct(mt), ctypes.c_void_p(C.ctypes.data), ctypes.c_void_p(w.ctypes.data), float(scale),
+              sched.n_clusters, sched.S, sched.cap_e, sched.max_deg, dv.ptr(sched.cl_nodes), dv.ptr(sched.cl_ne),
+              dv.ptr(sched.cl_conn), dv.ptr(sched.desc), dv.ptr(sched.tpos), dv.ptr(out), dv.stream_ptr())
+    return out

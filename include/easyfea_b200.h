@@ -172,6 +172,26 @@ int efb_csr_replay_vector(int n_groups, const double* const* data_host, const in
                           const int32_t* nPe_host, int dof_n, int64_t Nn, const int64_t* rowptr, const int64_t* qlist,
                           double* out, void* stream);
 
+/* ---- A3 fused: element integration + assembly in one kernel, homogeneous C -------------------------------------
+ * `Assembly` (_simu.py:1104-1144) of `LinearizedElasticity(group, C)` (Bilinear.py:62-79) for a homogeneous C, without ever
+ * materialising K_e: data_out = CSR data of the rows of the scheduled nodes, summed per slot in ascending element order
+ * (deterministic, no atomics; equal to efb_elastic_Ke + efb_csr_replay_matrix up to the association of the products,
+ * <= 1e-12 relative).  The schedule is built once per (group, node graph) by the host layer (assembly.FusedSchedule):
+ * nodes in clusters of S (spatially compact), cl_nodes (n_clusters*S, 4) int64 = {node id or -1, dim*dim*adjptr[n],
+ * deg | cnt << 32, first task}, cl_ne (n_clusters) / cl_conn (n_clusters, cap_e, nPe) = coordinate rows of every element
+ * touching a cluster (-1 = empty), desc (n_tasks) = element index inside its cluster | local node << 16, tpos (n_tasks, nPe) = slot of every
+ * column node, cap_e = max elements of a cluster, max_deg = max neighbours of a node.  C_host (ns,ns) and w_pg_host (nPg)
+ * are HOST arrays.  Returns 3 (and sets the error string) when the configuration is outside this kernel (element type,
+ * shared-memory budget, non-positive quadrature weights): the caller then uses the two-kernel path. */
+int efb_assemble_elastic(const efb_group* g, const double* C_host, const double* w_pg_host, double scale, int n_clusters, int S,
+                         int cap_e, int max_deg, const int64_t* cl_nodes, const int32_t* cl_ne, const int32_t* cl_conn,
+                         const int32_t* desc, const int32_t* tpos, double* out, void* stream);
+/* dynamic shared memory (bytes) the fused kernel needs for this configuration, or -1 when there is no instantiation */
+int efb_assemble_elastic_smem(int dim, int nPe, int nPg, int S, int cap_e, int max_deg);
+/* nodes per warp of the instantiation that serves (dim, nPe, nPg): S must be a multiple of it and at most 16 times it; -1
+ * when there is no instantiation */
+int efb_assemble_elastic_group(int dim, int nPe, int nPg);
+
 /* ---- consumer: Jacobi-PCG building blocks (north star; the reference dispatches in Solvers.py:225-394) ---- */
 /* All scalars stay on the device; dot products are fixed-order two-stage reductions: producers write
  * efb_pcg_partials_size() doubles of partials, efb_pcg_reduce folds them (deterministic). */

@@ -324,3 +324,37 @@ extern "C" void hc_replay_vector(void* p, int n_groups, const double* const* dat
     make_table(T, n_groups, nullptr, data, Ne, nPe, d);
     for (long long r = 0; r < Nn * d; ++r) replay_vector_item(T, d, r, P->rowptr.data(), P->qlist.data(), out);
 }
+
+// ---- fused element integration + assembly (csrc/fused_kernels.cuh): one emulated CTA per cluster ----
+#include "../../easyfea_b200/csrc/fused_kernels.cuh"
+
+extern "C" int hc_assemble_elastic(const efb_group* g, const double* C, double scale, int n_clusters, int S, int cap_e, int max_deg,
+                                   const int64_t* cl_nodes, const int32_t* cl_ne, const int32_t* cl_conn, const int32_t* desc,
+                                   const int32_t* tpos, double* out) {
+    FusedView f;
+    f.n_clusters = n_clusters; f.S = S; f.cap_e = cap_e; f.max_deg = max_deg;
+    f.cl_nodes = (const long long*)cl_nodes; f.cl_ne = cl_ne; f.cl_conn = cl_conn; f.desc = desc; f.tpos = tpos;
+    f.out = out;
+    FusedTerms terms;
+    memset(&terms, 0, sizeof(terms));
+    CMat C2;
+    memset(&C2, 0, sizeof(C2));
+#define X(D, N, P)                                                                                 \
+    if (g->dim == D && g->nPe == N && (P == g->nPg || P == 0)) {                                   \
+        using FC = Fused<D, N, P>;                                                                 \
+        if (S % FC::G) return 1;                                                                   \
+        const int nwarps = S / FC::G;                                                              \
+        memcpy(C2.v, C, sizeof(double) * StrainSize<D>::value * StrainSize<D>::value);             \
+        prescale_C<D>(C2);                                                                         \
+        fused_terms_from_C2<D>(C2.v, scale, terms);                                                \
+        std::vector<double> smem(FC::total(g->nPg, cap_e, nwarps, max_deg));                       \
+        for (long long c = 0; c < n_clusters; ++c) {                                               \
+            if (terms.ortho) fused_cluster_block<D, N, P, true>(view_of(g), f, terms, c, nwarps * 32, smem.data()); \
+            else fused_cluster_block<D, N, P, false>(view_of(g), f, terms, c, nwarps * 32, smem.data()); \
+        }                                                                                          \
+        return 0;                                                                                  \
+    }
+    X(2, 3, 1) X(2, 4, 4) X(2, 6, 3) X(2, 9, 9) X(3, 4, 1) X(3, 8, 8) X(3, 10, 4) X(2, 3, 0) X(2, 4, 0) X(2, 6, 0) X(2, 9, 0) X(3, 4, 0) X(3, 8, 0) X(3, 10, 0)
+#undef X
+    return 2;
+}

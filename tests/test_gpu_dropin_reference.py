@@ -102,15 +102,19 @@ def test_level4_solve_axb_threshold(ref, dropin):
     simu, _, u0, K0, F0, _ = _cantilever(ref)
     known, unknown = simu.Bc_dofs_known_unknown(simu.problemType)
     Aii = K0[unknown, :][:, unknown].tocsr()
-    bi = np.asarray(F0.toarray()).ravel()[unknown]
-    x_ref = Solvers._Solve_Axb(simu, simu.problemType, Aii, bi, np.zeros(unknown.size), [], [])
+    from scipy import sparse
+
+    bi = np.asarray(simu._Solver_Apply_Neumann(simu.problemType).toarray()).ravel()[unknown]  # the surface load
+    assert np.linalg.norm(bi) > 0
+    bcol = sparse.csr_matrix(bi.reshape(-1, 1))  # `__Solver_1` hands b over as a (n, 1) sparse column
+    x_ref = Solvers._Solve_Axb(simu, simu.problemType, Aii, bcol, np.zeros(unknown.size), [], [])
     dropin.install(ref, levels=(4,), min_dofs=10**9)
     h0 = dropin.stats["host_solves"]
-    x_small = Solvers._Solve_Axb(simu, simu.problemType, Aii, bi, np.zeros(unknown.size), [], [])
+    x_small = Solvers._Solve_Axb(simu, simu.problemType, Aii, bcol, np.zeros(unknown.size), [], [])
     assert dropin.stats["host_solves"] == h0 + 1 and np.array_equal(x_small, x_ref)
     dropin.config["min_dofs"], dropin.config["pcg_tol"] = 1, 1e-12
     d0 = dropin.stats["device_solves"]
-    x_dev = Solvers._Solve_Axb(simu, simu.problemType, Aii, bi, np.zeros(unknown.size), [], [])
+    x_dev = Solvers._Solve_Axb(simu, simu.problemType, Aii, bcol, np.zeros(unknown.size), [], [])
     assert dropin.stats["device_solves"] == d0 + 1
     assert np.linalg.norm(Aii @ x_dev - bi) / np.linalg.norm(bi) < 1e-8 and rel_err(x_dev, x_ref) < 1e-6
 
@@ -172,7 +176,7 @@ def test_phasefield_law_on_reference_objects(ref, dropin):
         simu, sets, _ = rh.phasefield_case(ref, et, n, "Miehe")
         g = simu.mesh.Get_list_groupElem()[0]
         ns = 3 if dim == 2 else 6
-        eps = rng.normal(size=(g.Ne, 3, ns)) * 1e-3
+        eps = ref.FEM.FeArray.asfearray(rng.normal(size=(g.Ne, 3, ns)) * 1e-3)  # the law takes FeArrays (e, p, ns)
         d_n = rng.uniform(0, 1, simu.mesh.Nn)
         for split in ("Amor", "Miehe", "Stress", "He"):
             pfm = Models.PhaseField(simu.phaseFieldModel.material, split, "AT2", 2.7e3, 1e-4)
