@@ -35,11 +35,42 @@ def chunk_bounds(Ne: int, world: int) -> np.ndarray:
     return (np.arange(world + 1, dtype=np.int64) * Ne) // world
 
 
-def node_owners(connect: np.ndarray, Nn: int, world: int) -> np.ndarray:
-    """owner[n] = lowest rank whose element chunk touches node n; -1 for orphan nodes (they have no rows to assemble)."""
+def rcb_element_ranks(centroids: np.ndarray, world: int) -> np.ndarray:
+    """Recursive coordinate bisection of the elements by their centroids (SURVEY.md section 8e "general: RCB on centroids";
+    the reference partitions with gmsh/METIS, `FEM/_mesher.py:2303-2393`): rank of every element, parts of equal size (+-1),
+    each cut along the longest extent of the part.  Independent of the element ORDER up to ties in the cut coordinate (broken by
+    the element id), so a mesh whose elements are stored in a random order gets the same compact parts as a sorted one.
+    Works for any `world` (a part of r ranks is cut r//2 : r - r//2)."""
+    c = np.ascontiguousarray(centroids, dtype=np.float64)
+    Ne = c.shape[0]
+    erank = np.zeros(Ne, dtype=np.int64)
+    stack = [(np.arange(Ne, dtype=np.int64), 0, int(world))]
+    while stack:
+        idx, r0, nr = stack.pop()
+        if nr <= 1 or idx.size == 0:
+            erank[idx] = r0
+            continue
+        pts = c[idx]
+        axis = int(np.argmax(pts.max(0) - pts.min(0))) if idx.size else 0
+        nl = nr // 2
+        k = (idx.size * nl) // nr  # elements of the lower part
+        order = np.lexsort((idx, pts[:, axis]))  # by coordinate, ties by element id
+        stack.append((idx[order[:k]], r0, nl))
+        stack.append((idx[order[k:]], r0 + nl, nr - nl))
+    return erank
+
+
+def chunk_element_ranks(Ne: int, world: int) -> np.ndarray:
+    """contiguous chunks by element index (structured meshes generated slab by slab)"""
+    return np.searchsorted(chunk_bounds(Ne, world), np.arange(Ne), side="right") - 1
+
+
+def node_owners(connect: np.ndarray, Nn: int, world: int, erank: np.ndarray = None) -> np.ndarray:
+    """owner[n] = lowest rank with an element touching node n (the reference's greedy rule, `_mesher.py:2355-2360`); -1 for
+    orphan nodes (they have no rows to assemble).  `erank`: rank of every element (default: contiguous chunks)."""
     Ne = connect.shape[0]
-    b = chunk_bounds(Ne, world)
-    erank = np.searchsorted(b, np.arange(Ne), side="right") - 1
+    if erank is None:
+        erank = chunk_element_ranks(Ne, world)
     owner = np.full(Nn, world, dtype=np.int64)
     np.minimum.at(owner, connect.ravel(), np.repeat(erank, connect.shape[1]))
     owner[owner == world] = -1
@@ -74,7 +105,7 @@ class Partition:
     # -- constructors ----------------------------------------------------------------------------------------
     @classmethod
     def from_candidates(cls, connect: np.ndarray, elem_ids: np.ndarray, owner_of, rank: int, world: int, own_chunk=None,
-                        n_global: int = 0):
+                        n_global: int = 0, erank=None):
         """`connect` (global node ids) and ascending `elem_ids` of a SUPERSET of the rank's local elements;
         `owner_of(ids) -> ranks` gives the owner of global nodes.  Keeps the elements touching an owned node."""
         connect = np.asarray(connect, dtype=np.int64)
@@ -96,18 +127,25 @@ class Partition:
         halo_owner = own_u[order][n_owned:]
         halo_ranks, first = np.unique(halo_owner, return_index=True)
         halo_ptr = np.append(first, halo_owner.size).astype(np.int64)
-        n_own_elems = int(keep.sum()) if own_chunk is None else int(((elem_ids >= own_chunk[0]) & (elem_ids < own_chunk[1])).sum())
+        if erank is not None:  # rank of every CANDIDATE element
+            n_own_elems = int((np.asarray(erank)[keep] == rank).sum())
+        elif own_chunk is not None:
+            n_own_elems = int(((elem_ids >= own_chunk[0]) & (elem_ids < own_chunk[1])).sum())
+        else:
+            n_own_elems = int(keep.sum())
         return cls(rank, world, elem_ids, n_own_elems, new_of_uniq[inv].reshape(connect.shape), nodes, n_owned,
                    halo_ranks.astype(np.int64), halo_ptr, 0, int(n_global))
 
     @classmethod
-    def from_global(cls, connect: np.ndarray, Nn: int, world: int, rank: int):
-        """Every rank sees the whole connectivity (small / medium meshes, tests)."""
+    def from_global(cls, connect: np.ndarray, Nn: int, world: int, rank: int, erank: np.ndarray = None):
+        """Every rank sees the whole connectivity (small / medium meshes, tests).  `erank`: element -> rank (e.g.
+        `rcb_element_ranks`); default: contiguous chunks.  See `from_distributed` for the build that never gathers the mesh."""
         connect = np.asarray(connect, dtype=np.int64)
-        owner = node_owners(connect, Nn, world)
-        b = chunk_bounds(connect.shape[0], world)
-        part = cls.from_candidates(connect, np.arange(connect.shape[0]), lambda ids: owner[ids], rank, world,
-                                   own_chunk=(b[rank], b[rank + 1]), n_global=Nn)
+        if erank is None:
+            erank = chunk_element_ranks(connect.shape[0], world)
+        owner = node_owners(connect, Nn, world, erank)
+        part = cls.from_candidates(connect, np.arange(connect.shape[0]), lambda ids: owner[ids], rank, world, n_global=Nn,
+                                   erank=erank)
         part.owned_offset = int((owner[owner >= 0] < rank).sum())
         # with the whole mesh at hand the send lists need no communication
         for q in range(world):
@@ -142,6 +180,178 @@ class Partition:
                 loc = np.searchsorted(own, their[self.rank])
                 assert np.array_equal(own[loc], their[self.rank]), "a neighbour asks for nodes this rank does not own"
                 self.send[q] = loc
+
+
+# ---------------------------------------------------------------------------------------------------------
+# distributed build: no rank ever holds the whole connectivity
+# ---------------------------------------------------------------------------------------------------------
+def _sortable_u64(x: np.ndarray) -> np.ndarray:
+    """float64 -> uint64 keys with the same order (sign-magnitude to biased), for exact k-th value searches by bisection"""
+    b = np.ascontiguousarray(x, dtype=np.float64).view(np.uint64)
+    neg = (b >> np.uint64(63)).astype(bool)
+    return np.where(neg, ~b, b | np.uint64(1) << np.uint64(63))
+
+
+def _alltoallv(by_dest, group=None, device="cpu", width: int = 1):
+    """exchange int64 rows: `by_dest[q]` (k_q, width) goes to rank q; returns the list of arrays received from every rank.
+    Sizes travel in one all-gather, payloads point to point (works with gloo on CPU tensors and nccl on CUDA tensors)."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    send = [np.ascontiguousarray(by_dest[q], dtype=np.int64).reshape(-1, width) for q in range(world)]
+    sizes = torch.tensor([a.shape[0] for a in send], dtype=torch.int64, device=device)
+    allsz = [torch.zeros(world, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(allsz, sizes, group=group)
+    recv_n = [int(allsz[q][rank].item()) for q in range(world)]
+    recv = [torch.empty((recv_n[q], width), dtype=torch.int64, device=device) for q in range(world)]
+    ops, keep = [], []
+    for q in range(world):
+        if q == rank:
+            recv[q] = torch.from_numpy(send[q]).to(device)
+            continue
+        if send[q].shape[0]:
+            t = torch.from_numpy(send[q]).to(device)
+            keep.append(t)
+            ops.append(dist.P2POp(dist.isend, t, dist.get_global_rank(group, q) if group is not None else q, group=group))
+        if recv_n[q]:
+            ops.append(dist.P2POp(dist.irecv, recv[q], dist.get_global_rank(group, q) if group is not None else q, group=group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return [r.cpu().numpy() for r in recv]
+
+
+def rcb_element_ranks_distributed(centroids: np.ndarray, elem_ids: np.ndarray, world_parts: int, group=None, device="cpu") -> np.ndarray:
+    """`rcb_element_ranks` for elements spread over the ranks of `group` (each rank passes ITS elements' centroids and global
+    ids): the same cuts, found without gathering anything — the k-th smallest coordinate of a part is located by bisection on
+    the ordered bit pattern of the doubles (<= 64 all-reduces of one count per active part), ties by bisection on the element id."""
+    import torch.distributed as dist
+
+    c = np.ascontiguousarray(centroids, dtype=np.float64)
+    ids = np.asarray(elem_ids, dtype=np.int64)
+    n = c.shape[0]
+    part = np.zeros(n, dtype=np.int64)      # first rank of the part each element currently belongs to
+    parts = [(0, int(world_parts))]         # (first rank, number of ranks)
+
+    def allsum(v):
+        t = torch.tensor(v, dtype=torch.int64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return t.cpu().numpy()
+
+    def allred(v, op):
+        t = torch.tensor(v, dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=op, group=group)
+        return t.cpu().numpy()
+
+    while any(nr > 1 for _, nr in parts):
+        act = [(r0, nr) for r0, nr in parts if nr > 1]
+        P = len(act)
+        members = [np.flatnonzero(part == r0) for r0, _ in act]
+        big = np.finfo(np.float64).max
+        dim = c.shape[1]
+        mn = allred([[c[m, a].min() if m.size else big for a in range(dim)] for m in members], dist.ReduceOp.MIN)
+        mx = allred([[c[m, a].max() if m.size else -big for a in range(dim)] for m in members], dist.ReduceOp.MAX)
+        axis = np.argmax(mx - mn, axis=1)
+        cnt = allsum([m.size for m in members])
+        k = np.array([(int(cnt[i]) * (act[i][1] // 2)) // act[i][1] for i in range(P)], dtype=np.int64)  # size of the lower part
+        keys = [_sortable_u64(c[members[i], axis[i]]) for i in range(P)]
+        # smallest key value v with count(key <= v) >= k (k >= 1); parts with k == 0 send everything up
+        lo = np.zeros(P, dtype=np.uint64)
+        hi = np.full(P, np.iinfo(np.uint64).max, dtype=np.uint64)
+        for _ in range(64):
+            mid = lo + (hi - lo) // np.uint64(2)
+            le = allsum([int((keys[i] <= mid[i]).sum()) for i in range(P)])
+            ok = le >= np.maximum(k, 1)
+            hi = np.where(ok, mid, hi)
+            lo = np.where(ok, lo, mid + np.uint64(1))
+        cut = hi
+        lt = allsum([int((keys[i] < cut[i]).sum()) for i in range(P)])
+        need = k - lt  # how many of the ties (key == cut) go down: the ones with the smallest element ids
+        tie_ids = [ids[members[i]][keys[i] == cut[i]] for i in range(P)]
+        ilo = np.zeros(P, dtype=np.int64)
+        ihi = np.full(P, np.iinfo(np.int64).max // 2, dtype=np.int64)
+        for _ in range(62):  # smallest id bound b with count(tie id < b) >= need
+            mid = ilo + (ihi - ilo) // 2
+            below = allsum([int((tie_ids[i] < mid[i]).sum()) for i in range(P)])
+            ok = below >= need
+            ihi = np.where(ok, mid, ihi)
+            ilo = np.where(ok, ilo, mid + 1)
+        new_parts = [(r0, nr) for r0, nr in parts if nr <= 1]
+        for i, (r0, nr) in enumerate(act):
+            m = members[i]
+            nl = nr // 2
+            down = (keys[i] < cut[i]) | ((keys[i] == cut[i]) & (ids[m] < ihi[i])) if k[i] > 0 else np.zeros(m.size, dtype=bool)
+            part[m[~down]] = r0 + nl
+            new_parts += [(r0, nl), (r0 + nl, nr - nl)]
+        parts = new_parts
+    return part
+
+
+def build_partition_distributed(connect_slice: np.ndarray, elem_id0: int, centroids_slice: np.ndarray, Nn: int, group=None,
+                                device="cpu", partitioner: str = "rcb"):
+    """The rank's `Partition` when the mesh arrives in pieces: rank r passes the connectivity (global node ids) and the
+    centroids of ITS contiguous slice of the element list, `[elem_id0, elem_id0 + len)`.  No rank ever holds the whole mesh:
+      1. element -> rank by distributed recursive coordinate bisection (or the slices themselves, `partitioner="chunks"`),
+      2. elements migrate to their rank,
+      3. node owners (lowest rank with an element on the node) are resolved at a directory rank `node % world`,
+      4. a rank that holds an element on a node owned by a LOWER rank sends that element there (the ghost layer),
+    then `Partition.from_candidates` + `plan_exchange`, exactly as in the gathered build: the result is identical to
+    `Partition.from_global(connect, Nn, world, rank, erank=rcb_element_ranks(centroids, world))`."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    conn = np.ascontiguousarray(connect_slice, dtype=np.int64)
+    ne, nPe = conn.shape
+    ids = elem_id0 + np.arange(ne, dtype=np.int64)
+    if partitioner == "rcb":
+        erank = rcb_element_ranks_distributed(centroids_slice, ids, world, group, device)
+    elif partitioner == "chunks":
+        erank = np.full(ne, rank, dtype=np.int64)
+    else:
+        raise ValueError(partitioner)
+    # 2. migration: (id, nodes...) rows to the element's rank
+    rows = np.concatenate([ids[:, None], conn], axis=1)
+    got = _alltoallv([rows[erank == q] for q in range(world)], group, device, width=nPe + 1)
+    mine = np.concatenate(got, axis=0)
+    mine = mine[np.argsort(mine[:, 0], kind="stable")]
+    my_ids, my_conn = mine[:, 0], mine[:, 1:]
+    # 3. owners through the directory
+    touched = np.unique(my_conn.ravel())
+    asked = _alltoallv([touched[touched % world == q] for q in range(world)], group, device)
+    asked = [a.ravel() for a in asked]
+    allnodes = np.concatenate(asked) if asked else np.empty(0, dtype=np.int64)
+    allranks = np.concatenate([np.full(a.size, q, dtype=np.int64) for q, a in enumerate(asked)]) if asked else allnodes
+    u, inv = np.unique(allnodes, return_inverse=True)
+    own_u = np.full(u.size, world, dtype=np.int64)
+    np.minimum.at(own_u, inv, allranks)
+    replies = _alltoallv([np.stack([a, own_u[np.searchsorted(u, a)]], axis=1) if a.size else np.empty((0, 2), dtype=np.int64)
+                          for a in asked], group, device, width=2)
+    rep = np.concatenate(replies, axis=0)
+    rep = rep[np.argsort(rep[:, 0], kind="stable")]
+    assert np.array_equal(rep[:, 0], touched)
+    owner_touched = rep[:, 1]
+    node_owner = owner_touched[np.searchsorted(touched, my_conn)]  # (my elements, nPe)
+    # 4. ghosts: my element goes to every LOWER rank that owns one of its nodes, with the owners of its nodes
+    out_rows = []
+    for q in range(world):
+        sel = (node_owner == q).any(axis=1) if q < rank else np.zeros(my_ids.size, dtype=bool)
+        out_rows.append(np.concatenate([my_ids[sel, None], my_conn[sel], node_owner[sel]], axis=1))
+    ghosts = np.concatenate(_alltoallv(out_rows, group, device, width=1 + 2 * nPe), axis=0)
+    cand_ids = np.concatenate([my_ids, ghosts[:, 0]])
+    cand_conn = np.concatenate([my_conn, ghosts[:, 1:1 + nPe]], axis=0)
+    cand_own = np.concatenate([node_owner, ghosts[:, 1 + nPe:]], axis=0)
+    cand_rank = np.concatenate([np.full(my_ids.size, rank, dtype=np.int64), np.full(ghosts.shape[0], -1, dtype=np.int64)])
+    order = np.argsort(cand_ids, kind="stable")
+    cand_ids, cand_conn, cand_own, cand_rank = cand_ids[order], cand_conn[order], cand_own[order], cand_rank[order]
+    known, first = np.unique(cand_conn.ravel(), return_index=True)
+    known_owner = cand_own.ravel()[first]
+
+    def owner_of(q):
+        return known_owner[np.searchsorted(known, q)]
+
+    part = Partition.from_candidates(cand_conn, cand_ids, owner_of, rank, world, n_global=Nn, erank=cand_rank)
+    part.plan_exchange(group)
+    return part
 
 
 # ---------------------------------------------------------------------------------------------------------

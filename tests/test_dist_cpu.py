@@ -214,3 +214,71 @@ def test_gloo_halo_exchange_and_pcg_pattern(world, elemType, n):
         p.join(timeout=60)
     for rank, status, info in results:
         assert status == "ok", f"rank {rank}: {info}"
+
+
+# ---- RCB partitioning and the distributed build (no rank holds the whole mesh) -------------------------------------------
+def test_rcb_parts_are_balanced_compact_and_order_independent():
+    coords, connect = make_mesh("HEXA8", (8, 8, 8))
+    cent = coords[connect].mean(1)
+    Nn = coords.shape[0]
+    for world in (2, 3, 4, 8):
+        er = efd.rcb_element_ranks(cent, world)
+        cnt = np.bincount(er, minlength=world)
+        assert cnt.max() - cnt.min() <= 1
+        perm = np.random.default_rng(world).permutation(connect.shape[0])
+        assert np.array_equal(efd.rcb_element_ranks(cent[perm], world), er[perm])  # same parts whatever the element order
+        # a randomly ORDERED mesh: contiguous chunks scatter every rank over the whole domain, RCB does not care
+        halo_rcb = max(efd.Partition.from_global(connect[perm], Nn, world, r, erank=er[perm]).n_halo for r in range(world))
+        halo_chunks = max(efd.Partition.from_global(connect[perm], Nn, world, r).n_halo for r in range(world))
+        assert halo_rcb < 0.5 * halo_chunks
+        if world == 8:  # bricks instead of slabs: smaller interfaces even on the sorted mesh
+            halo_slab = max(efd.Partition.from_global(connect, Nn, world, r).n_halo for r in range(world))
+            assert halo_rcb < halo_slab
+
+
+def _dist_build_worker(rank, world, port, elemType, n, out):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        coords, connect = make_mesh(elemType, n)
+        perm = np.random.default_rng(11).permutation(connect.shape[0])  # the mesh file stores the elements in a random order
+        connect = connect[perm]
+        Nn = coords.shape[0]
+        b = efd.chunk_bounds(connect.shape[0], world)
+        sl = slice(int(b[rank]), int(b[rank + 1]))  # this rank READS only its slice
+        part = efd.build_partition_distributed(connect[sl], int(b[rank]), coords[connect[sl]].mean(1), Nn)
+        ref = efd.Partition.from_global(connect, Nn, world, rank, erank=efd.rcb_element_ranks(coords[connect].mean(1), world))
+        ref.plan_exchange()
+        for name in ("elem_ids", "connect", "nodes", "halo_ranks", "halo_ptr"):
+            assert np.array_equal(getattr(part, name), getattr(ref, name)), name
+        assert (part.n_owned, part.n_own_elems, part.owned_offset, part.n_global) == (ref.n_owned, ref.n_own_elems, ref.owned_offset, ref.n_global)
+        assert sorted(part.send) == sorted(ref.send) and all(np.array_equal(part.send[q], ref.send[q]) for q in part.send)
+        out.put((rank, "ok", part.n_halo))
+    except Exception as exc:
+        import traceback
+
+        out.put((rank, "fail", traceback.format_exc() + str(exc)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,elemType,n", [(2, "HEXA8", (4, 4, 4)), (3, "TETRA4", (3, 3, 3)), (4, "TRI3", (8, 8)), (4, "HEXA8", (4, 4, 4))])
+def test_distributed_partition_build_equals_gathered_build(world, elemType, n):
+    """each rank reads a slice of a randomly ordered element list; distributed RCB + migration + owner directory + ghost
+    exchange reproduce `Partition.from_global(..., erank=rcb_element_ranks(...))` field by field (structured lattices: the cut
+    coordinate has many ties, resolved by element id in both builds)"""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dist_build_worker, args=(r, world, port, elemType, n, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, status, info in results:
+        assert status == "ok", f"rank {rank}: {info}"
