@@ -617,7 +617,7 @@ def phase_field_leg(args, rank, world, dist, cfg_id):
     pfm = phasefield.PhaseFieldModel(phasefield.IsotropicMaterial(dim, 210e9, 0.3, planeStress=False, thickness=1.0), split,
                                      "AT2", 2.7e3, l0)
     simu = staggered.PhaseFieldStaggered(sysm, pfm, pcg_tol=1e-8, pcg_maxiter=args.pf_maxiter)
-    simu.pcg_fused = not args.pf_unfused
+    simu.pcg_fused = False if args.pf_unfused else "auto"
     simu.pcg_single_reduction = bool(args.pf_single_reduction)
     ix, iy = np.rint(lattice[nodes, 0] / L * n).astype(np.int64), np.rint(lattice[nodes, 1] / L * n).astype(np.int64)
     loc = np.arange(nodes.size)
@@ -646,7 +646,7 @@ def phase_field_leg(args, rank, world, dist, cfg_id):
             "iterations_timed": its, "pcg_iters_damage": simu.info["damage"]["iterations"],
             "pcg_iters_elastic": simu.info["elastic"]["iterations"],
             "pcg_converged": bool(simu.info["damage"]["converged"] and simu.info["elastic"]["converged"]),
-            "pcg_fused": bool(simu.pcg_fused), "pcg_single_reduction": bool(simu.info["elastic"].get("single_reduction", False)),
+            "pcg_fused": bool(simu.info["elastic"].get("fused", False)), "pcg_single_reduction": bool(simu.info["elastic"].get("single_reduction", False)),
             "last_damage_increment": float(conv.item()), "max_damage": float(dmax.item())}
 
 

@@ -555,6 +555,26 @@ static int launch_internal_force(const efb_group* g, const double* sigma, double
     return check_launch("efb_internal_force");
 }
 
+template <int DIM, int NPE>
+__global__ void __launch_bounds__(256) k_hyper(GroupView g, const int* connect_dof, const double* u, const double* dW, const double* d2W,
+                                               double scale, double* Ke, double* Re, int EPB) {
+    extern __shared__ double smem[];
+    hyper_block<DIM, NPE>(g, connect_dof, u, dW, d2W, scale, Ke, Re, EPB, blockIdx.x, blockDim.x, smem);
+}
+
+template <int DIM, int NPE>
+static int launch_hyper(const efb_group* g, const int* connect_dof, const double* u, const double* dW, const double* d2W, double scale,
+                        double* Ke, double* Re, cudaStream_t st) {
+    const int TPE = DIM * NPE, extra = HyperSmem<DIM, NPE>::extra(g->nPg), EPB = elems_per_block<DIM, NPE>(TPE, g->nPg, extra);
+    const SmemMap<DIM, NPE> sm(g->nPg, EPB, extra);
+    const size_t bytes = sizeof(double) * sm.total();
+    if (ensure_smem(k_hyper<DIM, NPE>, bytes)) return 1;
+    const long long nblk = (g->Ne + EPB - 1) / EPB;
+    if (nblk == 0) return 0;
+    k_hyper<DIM, NPE><<<(unsigned)nblk, EPB * TPE, bytes, st>>>(view_of(g), connect_dof, u, dW, d2W, scale, Ke, Re, EPB);
+    return check_launch("efb_hyperelastic_Ke_Re");
+}
+
 __global__ void k_degradation(const int* connect_dof, const double* d, const double* N_pg, long long Ne, int nPg, int nPe,
                               double k_res, double* out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -566,6 +586,8 @@ __global__ void k_degradation(const int* connect_dof, const double* d, const dou
 
 using namespace efb;
 
+// element types of the hyperelastic operator: one thread keeps a whole K_e column (ndof accumulators) in registers
+#define EFB_FOR_EACH_HYPER(X) X(2, 3) X(2, 4) X(2, 6) X(2, 8) X(2, 9) X(3, 4) X(3, 8) X(3, 10)
 #define EFB_DISPATCH(D, N, CALL) \
     if (g->dim == D && g->nPe == N) return CALL;
 #define EFB_NO_INSTANCE(g)                                                                  \
@@ -672,6 +694,19 @@ extern "C" int efb_strain(const efb_group* g, const int32_t* connect_dof, const 
     if (validate(g)) return 1;
 #define X(D, N) EFB_DISPATCH(D, N, (launch_strain<D, N>(g, connect_dof, u, eps, as_stream(stream))))
     EFB_FOR_EACH_ELEM(X)
+#undef X
+    EFB_NO_INSTANCE(g)
+}
+
+extern "C" int efb_hyperelastic_Ke_Re(const efb_group* g, const int32_t* connect_dof, const double* u, const double* dWde,
+                                      const double* d2Wde, double scale, double* Ke, double* Re, void* stream) {
+    if (validate(g)) return 1;
+    if (!connect_dof || !u || !dWde || !d2Wde || (!Ke && !Re)) {
+        set_error("efb_hyperelastic_Ke_Re: bad arguments");
+        return 1;
+    }
+#define X(D, N) EFB_DISPATCH(D, N, (launch_hyper<D, N>(g, connect_dof, u, dWde, d2Wde, scale, Ke, Re, as_stream(stream))))
+    EFB_FOR_EACH_HYPER(X)
 #undef X
     EFB_NO_INSTANCE(g)
 }

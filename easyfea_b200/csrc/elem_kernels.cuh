@@ -1118,6 +1118,141 @@ EFB_D void internal_force_block(const GroupView& g, const double* EFB_RESTRICT s
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Hyperelastic tangent and residual: `Operators.NonLinear.SecondPiolaKirchhoffStressTensor`
+// and its shared core `__second_piola_block`, EasyFEA/FEM/Operators/NonLinear.py:37-201, with the kinematic operator
+// `HyperElasticState.Compute_De` / `__Build_De`, EasyFEA/Models/HyperElastic/_state.py:320-392:
+//     F = I + grad u,   B[s,(a,i)] = sum_m F[i][m] Blin[s,(a,m)]        (Green-Lagrange strain rate, Kelvin-Mandel rows)
+//     K_e = sum_p wJ ( B^T d2W B  +  delta_ij  dN_a . S . dN_b ),  S = matrix of the Kelvin-Mandel vector dW (2nd Piola-Kirchhoff)
+//     R_e = sum_p wJ B^T dW
+// dW (Ne,nPg,ns) and d2W (Ne,nPg,ns,ns) come from the material law at the same state; outputs are in the interleaved dof
+// order (x1,y1,z1,x2,...) the reference returns after its final reorder.  Thread (element, dof column).
+// ---------------------------------------------------------------------------------------------------------
+template <int DIM>
+EFB_HD void km_to_matrix(const double* v, double (&S)[DIM][DIM]) {  // Project_vector_to_matrix, Models/_utils.py
+    if constexpr (DIM == 2) {
+        S[0][0] = v[0]; S[1][1] = v[1];
+        S[0][1] = S[1][0] = v[2] * kInvSqrt2;
+    } else {
+        S[0][0] = v[0]; S[1][1] = v[1]; S[2][2] = v[2];
+        S[1][2] = S[2][1] = v[3] * kInvSqrt2;
+        S[0][2] = S[2][0] = v[4] * kInvSqrt2;
+        S[0][1] = S[1][0] = v[5] * kInvSqrt2;
+    }
+}
+
+template <int DIM, int NPE>
+struct HyperSmem {  // per-element extras behind SmemMap: u_e | F[p] | Bm[p][s][col]
+    static constexpr int NS = StrainSize<DIM>::value, NDOF = DIM * NPE;
+    EFB_HD static int extra(int nPg) { return NDOF + nPg * DIM * DIM + nPg * NS * NDOF; }
+};
+
+template <int DIM, int NPE>
+EFB_D void hyper_block(const GroupView& g, const int* EFB_RESTRICT connect_dof, const double* EFB_RESTRICT u,
+                       const double* EFB_RESTRICT dW, const double* EFB_RESTRICT d2W, double scale, double* EFB_RESTRICT Ke,
+                       double* EFB_RESTRICT Re, int EPB, long long blockId, int nthreads, double* smem) {
+    constexpr int NS = StrainSize<DIM>::value, NDOF = DIM * NPE, GS = SmemMap<DIM, NPE>::GS;
+    const int nPg = g.nPg;
+    const SmemMap<DIM, NPE> sm(nPg, EPB, HyperSmem<DIM, NPE>::extra(nPg));
+    const long long e0 = blockId * EPB;
+    geometry_phases<DIM, NPE>(g, sm, e0, NDOF, nthreads, smem, true);
+    EFB_PHASE(tid, nthreads) {  // nodal displacements of the element
+        const int el = tid / NDOF, t = tid % NDOF;
+        const long long e = e0 + el;
+        if (el < EPB && e < g.Ne) (sm.elem(smem, el) + sm.o_extra())[t] = u[(long long)connect_dof[e * NPE + t / DIM] * DIM + t % DIM];
+    }
+    EFB_PHASE(tid, nthreads) {  // F[p][i][m] = delta_im + sum_a u_a,i dN_a/dx_m        _state.py:88-143
+        const int el = tid / NDOF, t = tid % NDOF;
+        if (el < EPB && e0 + el < g.Ne) {
+            double* E = sm.elem(smem, el);
+            const double* ue = E + sm.o_extra();
+            const double* gN = E + sm.o_gN();
+            double* Fm = E + sm.o_extra() + NDOF;
+            for (int idx = t; idx < nPg * DIM * DIM; idx += NDOF) {
+                const int p = idx / (DIM * DIM), i = (idx / DIM) % DIM, m = idx % DIM;
+                double s = (i == m) ? 1.0 : 0.0;
+                for (int a = 0; a < NPE; ++a) s += ue[a * DIM + i] * gN[(p * NPE + a) * GS + m];
+                Fm[idx] = s;
+            }
+        }
+    }
+    EFB_PHASE(tid, nthreads) {  // Bm[p][s][(a,i)] = sum_m F[i][m] Blin[s,(a,m)]          NonLinear.py:37-72, _state.py:320-366
+        const int el = tid / NDOF, col = tid % NDOF;
+        if (el < EPB && e0 + el < g.Ne) {
+            double* E = sm.elem(smem, el);
+            const double* gN = E + sm.o_gN();
+            const double* Fm = E + sm.o_extra() + NDOF;
+            double* Bm = E + sm.o_extra() + NDOF + nPg * DIM * DIM;
+            const int a = col / DIM, i = col % DIM;
+            for (int p = 0; p < nPg; ++p) {
+                const double* ga = gN + (p * NPE + a) * GS;
+                for (int s = 0; s < NS; ++s) {
+                    double v = 0.0;
+                    EFB_UNROLL
+                    for (int m = 0; m < DIM; ++m) v += Fm[(p * DIM + i) * DIM + m] * B_entry<DIM>(s, m, ga);
+                    Bm[(p * NS + s) * NDOF + col] = v;
+                }
+            }
+        }
+    }
+    EFB_PHASE(tid, nthreads) {  // column (b,j) of K_e and entry (b,j) of R_e
+        const int el = tid / NDOF, col = tid % NDOF;
+        const long long e = e0 + el;
+        if (el < EPB && e < g.Ne) {
+            const double* E = sm.elem(smem, el);
+            const double* wJ = E + sm.o_wJ();
+            const double* gN = E + sm.o_gN();
+            const double* Bm = E + sm.o_extra() + NDOF + nPg * DIM * DIM;
+            const int b = col / DIM, j = col % DIM;
+            double acc[NDOF];
+            EFB_UNROLL
+            for (int r = 0; r < NDOF; ++r) acc[r] = 0.0;
+            double rcol = 0.0;
+            for (int p = 0; p < nPg; ++p) {
+                const double w = wJ[p];
+                const double* dWp = dW + (e * nPg + p) * (long long)NS;
+                const double* d2Wp = d2W + (e * nPg + p) * (long long)(NS * NS);
+                const double* Bp = Bm + p * NS * NDOF;
+                double tmp[NS];  // w * d2W . B[:, col]
+                double rs = 0.0;
+                EFB_UNROLL
+                for (int s = 0; s < NS; ++s) {
+                    double v = 0.0;
+                    EFB_UNROLL
+                    for (int r = 0; r < NS; ++r) v += d2Wp[s * NS + r] * Bp[r * NDOF + col];
+                    tmp[s] = w * v;
+                    rs += dWp[s] * Bp[s * NDOF + col];
+                }
+                rcol += w * rs;
+                double S[DIM][DIM], Sg[DIM];  // w * S . dN_b
+                km_to_matrix<DIM>(dWp, S);
+                const double* gb = gN + (p * NPE + b) * GS;
+                EFB_UNROLL
+                for (int k = 0; k < DIM; ++k) {
+                    double v = 0.0;
+                    EFB_UNROLL
+                    for (int l = 0; l < DIM; ++l) v += S[k][l] * gb[l];
+                    Sg[k] = w * v;
+                }
+                for (int row = 0; row < NDOF; ++row) {
+                    double v = 0.0;
+                    EFB_UNROLL
+                    for (int s = 0; s < NS; ++s) v += Bp[s * NDOF + row] * tmp[s];
+                    if (row % DIM == j) {  // geometric tangent: same displacement component only
+                        const double* ga = gN + (p * NPE + row / DIM) * GS;
+                        EFB_UNROLL
+                        for (int k = 0; k < DIM; ++k) v += ga[k] * Sg[k];
+                    }
+                    acc[row] += v;
+                }
+            }
+            if (Ke)
+                for (int row = 0; row < NDOF; ++row) Ke[e * (long long)(NDOF * NDOF) + row * NDOF + col] = scale * acc[row];
+            if (Re) Re[e * NDOF + col] = scale * rcol;
+        }
+    }
+}
+
 // no geometry needed: thread per (element, Gauss point)
 EFB_HD double degradation_at(const int* connect_dof, const double* d, const double* N_pg, long long e, int p, int nPe,
                              double k_res) {

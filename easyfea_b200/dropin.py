@@ -6,7 +6,8 @@
     `Get_SourcePart_e_pg` (`FEM/_group_elem.py:832-1407`), kept behind the reference's own `@cache_computed_values`;
   * level 1 — `EasyFEA.FEM.Operators.Bilinear.{LinearizedElasticity, UV, GradUGradV, GradU_A_GradV}` and
     `Operators.Linear.{V, InternalForce}` (looked up at call time by the simulations: `_elastic.py:132,135`,
-    `Simulations/_phasefield.py:472,554,557,560`, `_thermal.py:122,126`);
+    `Simulations/_phasefield.py:472,554,557,560`, `_thermal.py:122,126`) and
+    `Operators.NonLinear.SecondPiolaKirchhoffStressTensor` (`_hyperelastic.py:317`);
   * level 2 — `_Simu._Simu__Get_csr_map` / `_Simu._Simu__Assemble_csr` (`_simu.py:989-1102`);
   * level 3 — `Models.PhaseField.{Calc_C, Calc_psi_e_pg, Calc_Sigma_e_pg, Get_g_e_pg}` for homogeneous isotropic materials
     and the splits on the path (other models fall through to the reference's own code);
@@ -26,7 +27,8 @@ import numpy as np
 from . import assembly, operators, phasefield
 
 _saved = {}
-_LEVEL1 = {"Bilinear": ("LinearizedElasticity", "UV", "GradUGradV", "GradU_A_GradV"), "Linear": ("V", "InternalForce")}
+_LEVEL1 = {"Bilinear": ("LinearizedElasticity", "UV", "GradUGradV", "GradU_A_GradV"), "Linear": ("V", "InternalForce"),
+           "NonLinear": ("SecondPiolaKirchhoffStressTensor",)}
 # level 0: reference getter name -> (device function, takes dof_n)
 _LEVEL0 = ("Get_F_e_pg", "Get_jacobian_e_pg", "Get_invF_e_pg", "Get_dN_e_pg", "Get_B_e_pg", "Get_leftDispPart_e_pg",
            "Get_ReactionPart_e_pg", "Get_DiffusePart_e_pg", "Get_SourcePart_e_pg")
@@ -43,11 +45,11 @@ def _wrap_fearray(EasyFEA, arr):
 def _with_fallback(device_fn, original):
     """device operator that hands groups outside the path (NotImplementedError from the device mirror) to the reference"""
 
-    def op(groupElem, *args, **kwargs):
+    def op(*args, **kwargs):
         try:
-            return device_fn(groupElem, *args, **kwargs)
+            return device_fn(*args, **kwargs)
         except NotImplementedError:
-            return original(groupElem, *args, **kwargs)
+            return original(*args, **kwargs)
 
     op.__name__ = getattr(original, "__name__", device_fn.__name__)
     op.__doc__ = device_fn.__doc__

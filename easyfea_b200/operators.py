@@ -179,6 +179,25 @@ def strain_dev(groupElem, u, matrixType=RIGI, out=None):
     return out
 
 
+def hyperelastic_Ke_Re_dev(groupElem, u, dWde, d2Wde, matrixType=RIGI, scale=1.0, want=("Ke", "Re")):
+    """Tangent and residual of a hyperelastic law at the state `u` from the law's dW/de (Ne,nPg,ns) and d2W/de2 (Ne,nPg,ns,ns)
+    (`__second_piola_block`, Operators/NonLinear.py:124-141): device tensors (K_e (Ne,ndof,ndof), R_e (Ne,ndof)), interleaved dofs."""
+    dg = device_group(groupElem)
+    mt = _mt(matrixType)
+    ns = 3 if dg.dim == 2 else 6
+    nPg, ndof = dg.nPg(mt), dg.nPe * dg.dim
+    ud, dW, d2W = dv.to_device(u), dv.to_device(dWde), dv.to_device(d2Wde)
+    if ud.numel() != dg.Ncoords * dg.dim:
+        raise ValueError("wrong displacement field dimension")  # HyperElasticState._CheckFormat, _state.py:26-32
+    if tuple(dW.shape) != (dg.Ne, nPg, ns) or tuple(d2W.shape) != (dg.Ne, nPg, ns, ns):
+        raise ValueError(f"dWde / d2Wde must be (Ne, nPg, {ns}) / (Ne, nPg, {ns}, {ns}); got {tuple(dW.shape)} / {tuple(d2W.shape)}")
+    Ke = dv.empty((dg.Ne, ndof, ndof)) if "Ke" in want else None
+    Re = dv.empty((dg.Ne, ndof)) if "Re" in want else None
+    _lib.call("efb_hyperelastic_Ke_Re", dg.cstruct(mt), dv.ptr(dg.connect_glob), dv.ptr(ud), dv.ptr(dW), dv.ptr(d2W), float(scale),
+              dv.ptr(Ke), dv.ptr(Re), dv.stream_ptr())
+    return Ke, Re
+
+
 # ---------------------------------------------------------------------------------------------------------
 # reference-shaped API (NumPy in / NumPy out)
 # ---------------------------------------------------------------------------------------------------------
@@ -210,6 +229,19 @@ def V(groupElem, f=1.0, dof_n: int = 1, matrixType=MASS) -> np.ndarray:
 def InternalForce(groupElem, sigma_e_pg, matrixType=RIGI) -> np.ndarray:
     """``∫ σ:ε(v)`` -> (Ne, nPe·dim); replaces Linear.py:38-52."""
     return dv.to_host(internal_force_dev(groupElem, sigma_e_pg, matrixType))
+
+
+def SecondPiolaKirchhoffStressTensor(material, state):
+    """``(K_e, R_e)`` of a hyperelastic constitutive law at `state`, dofs ``(x1,y1,z1,...,xn,yn,zn)``; replaces
+    `Operators.NonLinear.SecondPiolaKirchhoffStressTensor` (Operators/NonLinear.py:144-201).  `material` supplies
+    `Compute_dWde(state)` / `Compute_d2Wde(state)` (Kelvin-Mandel) and `thickness`; `state` is a `HyperElasticState`
+    (`groupElem`, `displacement`, `matrixType`).  The law itself stays the reference's; the kinematic operator, the material and
+    geometric tangents and the residual are integrated on the device."""
+    g = state.groupElem
+    scale = float(material.thickness) if int(g.dim) == 2 else 1.0
+    Ke, Re = hyperelastic_Ke_Re_dev(g, np.asarray(state.displacement), np.asarray(material.Compute_dWde(state)),
+                                    np.asarray(material.Compute_d2Wde(state)), state.matrixType, scale)
+    return dv.to_host(Ke), dv.to_host(Re)
 
 
 def Calc_Epsilon_e_pg(groupElem, sol, matrixType=RIGI) -> np.ndarray:

@@ -80,15 +80,23 @@ def _system_struct(A: DeviceCsr, nrows, mask, inv_diag, x, r, z, Ap, partials) -
     return S
 
 
+# Above this many owned dofs per rank the kernel-per-operation loop (NCCL exchanges when sharded) is the faster one: the
+# iterations are bandwidth-bound and the fused kernels' last-CTA folds and one-wave grids cost 2 % (1 GPU, 24 M dofs) to 12 %
+# (8 GPUs, 24 M dofs each; profiles/r1_bench_n200_8gpu.json).  Below it the sync points dominate and the fused peer-memory
+# form wins (2 GPUs, 1 M dofs each: 0.82 vs 1.69 s per staggered iteration).
+FUSED_MAX_DOFS = 8_000_000
+
+
 def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: int = None, check_every: int = 25, comm=None,
-        fused: bool = True, persistent: bool = False, single_reduction: bool = False):
+        fused="auto", persistent: bool = False, single_reduction: bool = False):
     """Solve A x = b on the free dofs (free_mask True / 1 = unknown; other entries of x keep the values of x0).
 
     A holds the owned rows in LOCAL numbering `[owned | halo]` columns.  Stops when ||r|| <= tol * ||b - A x_known||
     (both restricted to free dofs).  Returns (x_owned, info dict).  `comm` (easyfea_b200.dist.RowComm) supplies the halo
     exchange and scalar all-reduces for row-sharded runs.
 
-    `fused=True` (default): the iterations run on the device, reductions and the halo exchange go through peer memory
+    `fused="auto"` (default): fused below `FUSED_MAX_DOFS` owned dofs per rank, the kernel-per-operation loop above.
+    `fused=True`: the iterations run on the device, reductions and the halo exchange go through peer memory
     inside the kernels: three kernels per iteration, enqueued `check_every` at a time (`efb_pcg_iterate`).  With
     `persistent=True` (matrices assembled by this library) ONE cooperative kernel iterates until convergence instead
     (`efb_pcg_solve_persistent`: grid barriers between the steps, every rank leaves in the same iteration, no host round
@@ -105,6 +113,11 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
     dev = A.data.device
     nrows = A.indptr.numel() - 1
     n_glob = A.shape[1]
+    if fused == "auto":  # the same decision on every rank: the largest shard decides
+        big = torch.tensor([float(nrows)], dtype=torch.float64, device=dev)
+        if comm is not None:
+            comm.all_reduce_max(big)
+        fused = bool(single_reduction or persistent) or float(big.item()) <= FUSED_MAX_DOFS
     single_reduction = bool(single_reduction) and bool(fused)
     st = dv.stream_ptr
     b = dv.to_device(b)

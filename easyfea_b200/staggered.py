@@ -122,7 +122,7 @@ class ElasticSolve:
         self.dim = int(system.group.dim)
         self.bc = Dirichlet(system.n_local * self.dim)
         self.u = torch.zeros(system.n_local * self.dim, dtype=torch.float64, device=dv.device())
-        self.pcg_fused = True  # False: one NCCL call per exchange (the baseline of solver.pcg)
+        self.pcg_fused = "auto"  # True / False force the fused peer-memory form / the kernel-per-operation loop (solver.pcg)
         self.pcg_persistent = False  # True: one cooperative kernel per solve instead of three kernels per iteration
         self.pcg_single_reduction = False  # True: Chronopoulos-Gear form, one all-reduce per iteration
 
@@ -163,7 +163,7 @@ class PhaseFieldStaggered:
         self.bc_d = Dirichlet(system.n_local)
         self.f_ext = None      # nodal external forces of the displacement problem (owned dofs), `add_neumann`
         self.pcg_tol, self.pcg_maxiter = pcg_tol, pcg_maxiter
-        self.pcg_fused, self.pcg_persistent, self.pcg_single_reduction = True, False, False
+        self.pcg_fused, self.pcg_persistent, self.pcg_single_reduction = "auto", False, False
         self._updatedDamage = self._updatedDisplacement = False
         self.info = {}
 

@@ -104,7 +104,7 @@ class TransientSolve:
         self.bc = Dirichlet(n)
         self.K = self.C = self.M = None
         self.algo = "elliptic"
-        self.pcg_tol, self.pcg_maxiter, self.pcg_fused, self.pcg_persistent = 1e-10, None, True, False
+        self.pcg_tol, self.pcg_maxiter, self.pcg_fused, self.pcg_persistent = 1e-10, None, "auto", False
         self.pcg_single_reduction = False
         self.info = {}
 

@@ -85,6 +85,16 @@ int efb_internal_force(const efb_group* g, const double* sigma, double* out, voi
  * eps (Ne,nPg,ns) = B u_e, u (Ndof) nodal vector, dof of node n comp i = n*dim+i, connect_dof (Ne,nPe) GLOBAL ids. */
 int efb_strain(const efb_group* g, const int32_t* connect_dof, const double* u, double* eps, void* stream);
 
+/* Hyperelastic tangent and residual: Operators.NonLinear.SecondPiolaKirchhoffStressTensor and
+ * its core __second_piola_block, EasyFEA/FEM/Operators/NonLinear.py:37-201, with HyperElasticState.Compute_De
+ * (Models/HyperElastic/_state.py:320-392): F = I + grad u, B = De(u) grad,
+ *   Ke (Ne,ndof,ndof) = scale * sum_p wJ (B^T d2Wde B + I (x) dN^T S dN),  Re (Ne,ndof) = scale * sum_p wJ B^T dWde,
+ * dWde (Ne,nPg,ns) / d2Wde (Ne,nPg,ns,ns) = the material law's `Compute_dWde/Compute_d2Wde` at the state of u (Kelvin-Mandel),
+ * S = the symmetric matrix of dWde; u (Ncoords*dim) nodal, connect_dof GLOBAL node ids; dofs interleaved (x1,y1,z1,x2,...)
+ * as the reference returns them.  Ke or Re may be NULL. */
+int efb_hyperelastic_Ke_Re(const efb_group* g, const int32_t* connect_dof, const double* u, const double* dWde, const double* d2Wde,
+                           double scale, double* Ke, double* Re, void* stream);
+
 /* ---- P2-P7: phase-field law, EasyFEA/Models/_phasefield.py ------------------------------------------- */
 enum { EFB_SPLIT_BOURDIN = 0, EFB_SPLIT_AMOR = 1, EFB_SPLIT_MIEHE = 2, EFB_SPLIT_STRESS = 3, EFB_SPLIT_HE = 4 };
 enum { EFB_REGU_AT1 = 1, EFB_REGU_AT2 = 2 };

@@ -893,3 +893,62 @@ def node_values(connect, Nn, result_e):
     cnt = np.asarray(M.sum(axis=1)).reshape(-1, 1)
     out = (M @ r) * 1 / np.where(cnt == 0, 1, cnt)
     return out.ravel() if is1d else out
+
+
+# =========================================================================================================
+# section 8f rank 3: hyperelastic tangent / residual          EasyFEA/FEM/Operators/NonLinear.py:37-201
+# =========================================================================================================
+def hyper_deformation_gradient(geo, u_e, dim):
+    """F = I + grad u at the Gauss points, (Ne,nPg,dim,dim), F[i][m] = delta_im + sum_a u_a,i dN_a/dx_m
+    (`HyperElasticState.Compute_F`, Models/HyperElastic/_state.py:88-143, un-padded)."""
+    ua = u_e.reshape(u_e.shape[0], -1, dim)  # (Ne, nPe, dim)
+    return np.eye(dim)[None, None] + np.einsum("eai,epma->epim", ua, geo["dN"])
+
+
+def hyper_De(G):
+    """`__Build_De` (_state.py:320-366): rows = Kelvin-Mandel components of sym(G^T . d), columns = flat(d) = [d_x u_x, d_y u_x, ...]
+    (component-major, derivative fastest)."""
+    Ne, nPg, dim, _ = G.shape
+    c = 1.0 / SQRT2
+    if dim == 2:
+        D = np.zeros((Ne, nPg, 3, 4))
+        g = lambda i, j: G[:, :, i, j]  # noqa: E731
+        D[:, :, 0, 0], D[:, :, 0, 2] = g(0, 0), g(1, 0)
+        D[:, :, 1, 1], D[:, :, 1, 3] = g(0, 1), g(1, 1)
+        D[:, :, 2, 0], D[:, :, 2, 1], D[:, :, 2, 2], D[:, :, 2, 3] = c * g(0, 1), c * g(0, 0), c * g(1, 1), c * g(1, 0)
+        return D
+    D = np.zeros((Ne, nPg, 6, 9))
+    g = lambda i, j: G[:, :, i, j]  # noqa: E731
+    rows = {0: [(0, (0, 0)), (3, (1, 0)), (6, (2, 0))], 1: [(1, (0, 1)), (4, (1, 1)), (7, (2, 1))],
+            2: [(2, (0, 2)), (5, (1, 2)), (8, (2, 2))],
+            3: [(1, (0, 2)), (2, (0, 1)), (4, (1, 2)), (5, (1, 1)), (7, (2, 2)), (8, (2, 1))],
+            4: [(0, (0, 2)), (2, (0, 0)), (3, (1, 2)), (5, (1, 0)), (6, (2, 2)), (8, (2, 0))],
+            5: [(0, (0, 1)), (1, (0, 0)), (3, (1, 1)), (4, (1, 0)), (6, (2, 1)), (7, (2, 0))]}
+    for r, entries in rows.items():
+        for col, (i, j) in entries:
+            D[:, :, r, col] = (c if r >= 3 else 1.0) * g(i, j)
+    return D
+
+
+def hyper_Ke_Re(geo, u_e, dW, d2W, dim, thickness=1.0):
+    """(K_e, R_e) of `SecondPiolaKirchhoffStressTensor` (NonLinear.py:144-201): B = De(u) grad, K_e = sum_p wJ (B^T d2W B) +
+    geometric tangent `g (x) I` with g = sum_p wJ dN^T S dN (:75-96), R_e = sum_p wJ B^T dW; built component-major like the
+    reference and returned in the interleaved dof order of its final reorder (:99-121)."""
+    dN, wJ = geo["dN"], geo["wJ"]
+    Ne, nPg, _, nPe = dN.shape
+    F = hyper_deformation_gradient(geo, u_e, dim)
+    De = hyper_De(F)
+    grad = np.zeros((Ne, nPg, dim * dim, dim * nPe))  # flat(grad v) row (i, k) <- dof (component i, node a): dN[k][a]
+    for i in range(dim):
+        grad[:, :, i * dim:(i + 1) * dim, i * nPe:(i + 1) * nPe] = dN
+    B = De @ grad
+    A_lin = np.einsum("ep,epji,epjk,epkl->eil", wJ, B, d2W, B, optimize=True)
+    S = _vec_to_mat(dW) if dim == 3 else np.stack([np.stack([dW[..., 0], dW[..., 2] / SQRT2], -1),
+                                                   np.stack([dW[..., 2] / SQRT2, dW[..., 1]], -1)], -2)
+    gmat = np.einsum("ep,epab,epac,epcd->ebd", wJ, dN, S, dN, optimize=True)
+    A_geo = np.einsum("eab,jk->ejakb", gmat, np.eye(dim)).reshape(Ne, dim * nPe, dim * nPe)
+    R = np.einsum("ep,epi,epij->ej", wJ, dW, B, optimize=True)
+    K = (A_lin + A_geo) * thickness
+    R = R * thickness
+    perm = np.arange(nPe * dim).reshape(-1, nPe).T.ravel()
+    return K[:, perm[:, None], perm[None, :]], R[:, perm]

@@ -178,6 +178,22 @@ extern "C" int hc_internal_force(const efb_group* g, const double* sigma, double
     return 2;
 }
 
+extern "C" int hc_hyper(const efb_group* g, const int32_t* connect_dof, const double* u, const double* dW, const double* d2W, double scale,
+                        double* Ke, double* Re) {
+#define X(D, N)                                                                                    \
+    if (g->dim == D && g->nPe == N) {                                                              \
+        const int TPE = D * N, EPB = epb_for(TPE);                                                 \
+        SmemMap<D, N> sm(g->nPg, EPB, HyperSmem<D, N>::extra(g->nPg));                             \
+        std::vector<double> smem(sm.total());                                                      \
+        for (long long b = 0; b * EPB < g->Ne; ++b)                                                \
+            hyper_block<D, N>(view_of(g), connect_dof, u, dW, d2W, scale, Ke, Re, EPB, b, EPB * TPE, smem.data()); \
+        return 0;                                                                                  \
+    }
+    X(2, 3) X(2, 4) X(2, 6) X(2, 9) X(3, 4) X(3, 8) X(3, 10)
+#undef X
+    return 2;
+}
+
 extern "C" int hc_degradation(const efb_group* g, const int32_t* connect_dof, const double* d, double k_res, double* out) {
     for (long long i = 0; i < g->Ne * g->nPg; ++i)
         out[i] = degradation_at(connect_dof, d, g->N_pg, i / g->nPg, (int)(i % g->nPg), g->nPe, k_res);

@@ -34,7 +34,7 @@ def test_install_uninstall_roundtrip():
     solve_before = (Solvers._Solve_Axb, Solvers.Solve_simu, _simu.Solve_simu)
     patched = dropin.install(EasyFEA)
     try:
-        assert dropin.installed() and len(patched) == 9 + 6 + 2 + 4 + 3
+        assert dropin.installed() and len(patched) == 9 + 7 + 2 + 4 + 3
         assert Operators.Bilinear.LinearizedElasticity is not before[("Bilinear", "LinearizedElasticity")]
         assert _Simu.__dict__["_Simu__Assemble_csr"] is not csr_before[1]
         assert _simu.Solve_simu is Solvers.Solve_simu and Solvers.Solve_simu is not solve_before[1]

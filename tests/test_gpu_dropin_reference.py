@@ -280,3 +280,26 @@ def test_level1_falls_back_for_groups_outside_the_path(ref, dropin):
     seg._InitMatrix()
     assert np.array_equal(Ops.Bilinear.UV(seg, 2.0, 1), want)
     assert np.array_equal(np.array(seg.Get_jacobian_e_pg("mass")), want_jac)
+
+
+def test_hyperelastic_operator_on_reference_objects(ref, dropin):
+    """section 8f rank 3: `Operators.NonLinear.SecondPiolaKirchhoffStressTensor` on live `HyperElasticState` / material objects"""
+    from EasyFEA.FEM import MatrixType
+    from EasyFEA.Models.HyperElastic import NeoHookean, SaintVenantKirchhoff
+    from EasyFEA.Models.HyperElastic._state import HyperElasticState
+    from easyfea_b200 import meshgen
+    from tests import ref_helpers as rh
+
+    rng = np.random.default_rng(4)
+    for et, n, dim in (("TETRA4", (3, 3, 2), 3), ("HEXA8", (3, 2, 2), 3), ("QUAD4", (5, 4), 2)):
+        coords, connect = meshgen.structured_mesh(et, n, jitter=0.15, seed=2)
+        mesh = rh.ref_mesh(ref, et, coords, connect)
+        g = mesh.Get_list_groupElem()[0]
+        u = rng.normal(size=mesh.Nn * dim) * 0.03
+        for mat in (SaintVenantKirchhoff(dim, lmbda=121.0, mu=81.0, thickness=0.7), NeoHookean(dim, K=3.0, thickness=0.7)):
+            Op = ref.FEM.Operators.NonLinear
+            K0, R0 = Op.SecondPiolaKirchhoffStressTensor(mat, HyperElasticState(g, u, MatrixType.rigi))
+            dropin.install(ref, levels=(1,))
+            K1, R1 = Op.SecondPiolaKirchhoffStressTensor(mat, HyperElasticState(g, u, MatrixType.rigi))
+            dropin.uninstall()
+            assert K1.shape == K0.shape and rel_err(K1, K0) < 1e-12 and rel_err(R1, R0) < 1e-12

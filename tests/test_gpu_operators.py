@@ -145,3 +145,22 @@ def test_golden_fixtures(efb, name):
     assert rel_err(op.GradU_A_GradV(g, d["A"], 3.0), d["De"]) < TOL
     assert rel_err(op.GradUGradV(g, d["rho_e_pg"][:, :1].repeat(nPg, 1)), d["De0"]) < TOL
     assert rel_err(op.V(g, d["rho_e_pg"], 1), d["Fe"]) < TOL
+
+
+@pytest.mark.parametrize("elemType", ["TRI3", "QUAD4", "QUAD9", "TETRA4", "HEXA8", "TETRA10"])
+def test_hyperelastic_Ke_Re(efb, elemType):
+    """section 8f rank 3 (`efb_hyperelastic_Ke_Re`): material + geometric tangent and residual vs the oracle restatement of
+    Operators/NonLinear.py:37-201, random symmetric d2W / random dW"""
+    rng = np.random.default_rng(12)
+    coords, connect = make_mesh(elemType)
+    g = efb.mesh.ElemGroup(elemType, connect, coords)
+    dim, Ne = g.dim, g.Ne
+    ns = 3 if dim == 2 else 6
+    geo, tab = _geo(efb, elemType, coords, connect, "rigi")
+    u = rng.normal(size=coords.shape[0] * dim) * 0.05
+    dW = rng.normal(size=(Ne, tab.nPg, ns))
+    d2W = rng.normal(size=(Ne, tab.nPg, ns, ns))
+    d2W = d2W + np.swapaxes(d2W, -1, -2)
+    Ke, Re = efb.op.hyperelastic_Ke_Re_dev(g, u, dW, d2W, "rigi", 0.8)
+    K, R = orc.hyper_Ke_Re(geo, orc.locate_sol_e(u, connect, dim), dW, d2W, dim, 0.8)
+    assert rel_err(Ke.cpu().numpy(), K) < TOL and rel_err(Re.cpu().numpy(), R) < TOL

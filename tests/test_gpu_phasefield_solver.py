@@ -59,7 +59,7 @@ def test_split_degenerate_states(efb, dim, split):
     eps[5] = 0.0; eps[5, :, 0] = 1e-3; eps[5, :, 1:dim] = -0.3e-3
     cP, cM = pfm.Calc_C(eps)
     assert np.isfinite(cP).all() and np.isfinite(cM).all()
-    assert rel_err(cP + cM, np.broadcast_to(om.C, cP.shape)) < 1e-11
+    assert rel_err(cP + cM, np.broadcast_to(om.C, cP.shape)) < TOL
     ocP, _ = orc.calc_C(om, split, eps, clamp=True)
     assert rel_err(cP[6:], ocP[6:]) < TOL
 
@@ -100,13 +100,13 @@ def test_simulation_level_builders(efb, elemType, split, regu):
     geo_m = orc.geometry(coords[connect][:, :, :dim], tm.dN_pg, tm.weights)
     Ke = pfm.elastic_Ke_dev(g, u, dmg).cpu().numpy()
     ref = thickness * orc.pf_elastic_Ke(geo_r, tr.N_pg, om, split, u_e, dmg[connect], clamp=True)
-    assert rel_err(Ke, ref) < 1e-11
+    assert rel_err(Ke, ref) < TOL  # measured 1.5e-16 .. 1.9e-13 (Stress split in 3D), profiles/r2_dist2_and_pf_errors.log
     old = rng.uniform(0, 1, (g.Ne, tm.nPg)) * float(np.median(orc.calc_psi(om, split, orc.strain(geo_m, u_e), True)[0]))
     Kd, Fd, psiP = pfm.damage_system_dev(g, u, old)
     rK, rF, rpsi = orc.pf_damage_system(geo_m, tm.N_pg, om, split, regu, 2.7e3, 1e-2, u_e, old, clamp=True)
-    assert rel_err(psiP.cpu().numpy(), rpsi) < 1e-11
-    assert rel_err(Kd.cpu().numpy(), thickness * rK) < 1e-11
-    assert rel_err(Fd.cpu().numpy(), thickness * rF[..., 0]) < 1e-11
+    assert rel_err(psiP.cpu().numpy(), rpsi) < TOL
+    assert rel_err(Kd.cpu().numpy(), thickness * rK) < TOL
+    assert rel_err(Fd.cpu().numpy(), thickness * rF[..., 0]) < TOL
 
 
 def test_pcg_elastic_cube(efb):

@@ -167,3 +167,25 @@ def test_strain_internal_force_degradation(hostcheck, elemType, mt):
     gd = np.empty((Ne, nPg))
     assert hostcheck.hc_degradation(ctypes.byref(g), p(c32), p(d), D(1e-12), p(gd)) == 0
     assert rel_err(gd, orc.degradation(d[connect], tab.N_pg)) < TOL
+
+
+@pytest.mark.parametrize("elemType", ["TRI3", "QUAD4", "TRI6", "QUAD9", "TETRA4", "HEXA8", "TETRA10"])
+def test_hyperelastic_Ke_Re(hostcheck, elemType):
+    """section 8f rank 3: kernel body of `efb_hyperelastic_Ke_Re` (B = De(u) grad, material + geometric tangent, residual) against
+    the oracle restatement of NonLinear.py:37-201, random symmetric d2W and random dW at every Gauss point"""
+    rng = np.random.default_rng(12)
+    coords, connect = make_mesh(elemType)
+    g, keep, tab = host_group(elemType, coords, connect, "rigi")
+    dim, nPe, nPg, Ne = g.dim, g.nPe, g.nPg, g.Ne
+    ns = 3 if dim == 2 else 6
+    Nn = coords.shape[0]
+    u = rng.normal(size=Nn * dim) * 0.05
+    dW = rng.normal(size=(Ne, nPg, ns))
+    d2W = rng.normal(size=(Ne, nPg, ns, ns))
+    d2W = d2W + np.swapaxes(d2W, -1, -2)
+    c32 = np.ascontiguousarray(connect, dtype=np.int32)
+    Ke = np.empty((Ne, nPe * dim, nPe * dim)); Re = np.empty((Ne, nPe * dim))
+    assert hostcheck.hc_hyper(ctypes.byref(g), p(c32), p(u), p(dW), p(d2W), D(0.8), p(Ke), p(Re)) == 0
+    geo = _geo(elemType, coords, connect, tab)
+    K, R = orc.hyper_Ke_Re(geo, orc.locate_sol_e(u, connect, dim), dW, d2W, dim, 0.8)
+    assert rel_err(Ke, K) < TOL and rel_err(Re, R) < TOL

@@ -163,3 +163,29 @@ def test_known_answers_survey_appendix_c():
     G = orc.grad_u_a_grad_v(geo, None, 1.0)[0]
     assert np.allclose(G, [[0.75, -0.25, -0.5], [-0.25, 0.4166666666666667, -0.16666666666666666],
                            [-0.5, -0.16666666666666666, 0.6666666666666666]], rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["TRI3", "QUAD4", "TETRA4", "HEXA8", "TETRA10"])
+@pytest.mark.parametrize("law", ["SaintVenantKirchhoff", "NeoHookean"])
+def test_hyperelastic_tangent_and_residual(ref, name, law):
+    """section 8f rank 3: the oracle restatement of `Operators.NonLinear.SecondPiolaKirchhoffStressTensor` (NonLinear.py:144-201)
+    against the live reference, with the reference's own material law supplying dWde / d2Wde at the same state"""
+    from EasyFEA.Models.HyperElastic import NeoHookean, SaintVenantKirchhoff
+    from EasyFEA.Models.HyperElastic._state import HyperElasticState
+
+    from easyfea_b200 import elements as el
+
+    coords, connect, g, mesh = build(ref, name, seed=9)
+    dim = g.dim
+    thickness = 0.7 if dim == 2 else 1.0
+    mat = (SaintVenantKirchhoff(dim, lmbda=121.0, mu=81.0, thickness=thickness) if law == "SaintVenantKirchhoff"
+           else NeoHookean(dim, K=3.0, thickness=thickness))
+    rng = np.random.default_rng(4)
+    u = rng.normal(size=mesh.Nn * dim) * 0.03
+    state = HyperElasticState(g, u, ref.MatrixType.rigi)
+    K_ref, R_ref = ref.Operators.NonLinear.SecondPiolaKirchhoffStressTensor(mat, state)
+    dW, d2W = np.asarray(mat.Compute_dWde(state)), np.asarray(mat.Compute_d2Wde(state))
+    tab = el.gauss_table(name, "rigi")
+    geo = orc.geometry(coords[connect][:, :, :dim], tab.dN_pg, tab.weights)
+    K, R = orc.hyper_Ke_Re(geo, orc.locate_sol_e(u, connect, dim), dW, d2W, dim, thickness)
+    assert rel_err(K, K_ref) < TOL and rel_err(R, R_ref) < TOL
