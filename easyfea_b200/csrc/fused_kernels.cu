@@ -13,7 +13,8 @@ __global__ void __launch_bounds__(512) k_assemble_elastic(GroupView g, FusedView
     bool first = true;
     for (long long cluster = blockIdx.x; cluster < f.n_clusters; cluster += gridDim.x) {
         if (!first) __syncthreads();  // the accumulators of the previous cluster share memory with this cluster's gather
-        fused_cluster_block<DIM, NPE, NPG, ORTHO>(g, f, terms, cluster, blockDim.x, smem, first);
+        const long long nxt = cluster + gridDim.x;
+        fused_cluster_block<DIM, NPE, NPG, ORTHO>(g, f, terms, cluster, blockDim.x, smem, first, nxt < f.n_clusters ? nxt : -1);
         first = false;
     }
 }

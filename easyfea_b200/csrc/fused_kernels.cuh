@@ -302,7 +302,7 @@ EFB_D void fused_group(const FusedView& f, const FusedTerms& terms, int nPg, con
 // The caller puts a CTA barrier between two clusters of the same CTA (the accumulators share memory with the next gather).
 template <int DIM, int NPE, int NPG, bool ORTHO>
 EFB_D void fused_cluster_block(const GroupView& g, const FusedView& f, const FusedTerms& terms, long long cluster, int nthreads,
-                               double* smem, bool load_tables = true) {
+                               double* smem, bool load_tables = true, long long next_cluster = -1) {
     using FC = Fused<DIM, NPE, NPG>;
     const int nPg = FC::npg(g.nPg), RS = FC::rec(nPg), nwarps = nthreads / 32;
     double* dNt = smem;
@@ -317,6 +317,17 @@ EFB_D void fused_cluster_block(const GroupView& g, const FusedView& f, const Fus
     FusedLane<FC::CHUNK> L[1];
     const long long k0 = cluster * f.S + (long long)(threadIdx.x >> 5) * FC::G;
     fused_load_lane<DIM, NPE, NPG>(f, k0, threadIdx.x & 31, 0, true, L[0]);
+    // the gather of the NEXT cluster of this CTA is a two-level chain (connectivity -> coordinates): its connectivity entries
+    // are read now and its coordinate lines are pulled into L2 once the geometry stage below is done, so that the chain costs
+    // two L2 hits instead of two DRAM round trips at the head of the next cluster
+    int pf_node[2] = {-1, -1};
+    if (next_cluster >= 0) {
+        EFB_UNROLL
+        for (int q = 0; q < 2; ++q) {
+            const int idx = (int)threadIdx.x + q * nthreads;
+            if (idx < f.cap_e * NPE) pf_node[q] = f.cl_conn[next_cluster * f.cap_e * NPE + idx];
+        }
+    }
 #endif
     EFB_PHASE(tid, nthreads) {
         if (load_tables) {
@@ -339,6 +350,9 @@ EFB_D void fused_cluster_block(const GroupView& g, const FusedView& f, const Fus
         }
     }
 #ifdef __CUDACC__
+    EFB_UNROLL
+    for (int q = 0; q < 2; ++q)
+        if (pf_node[q] >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.coord + (long long)pf_node[q] * g.coord_stride));
     fused_group<DIM, NPE, NPG, ORTHO>(f, terms, nPg, recs, region + (threadIdx.x >> 5) * acc_warp, k0, L);
 #else
     for (int wi = 0; wi < nwarps; ++wi) {

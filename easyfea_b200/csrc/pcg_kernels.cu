@@ -1073,9 +1073,21 @@ extern "C" int efb_pcg_iterate(const efb_pcg_system* sys, const efb_pcg_peer* pe
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int g_spmv = min(kRedBlocks, sms * resident_blocks_per_sm(spmv_k));
-    const int g_xr = min(kRedBlocks, sms * resident_blocks_per_sm(k_pcg_update_xr));
-    const int g_p = min(kRedBlocks, sms * resident_blocks_per_sm(k_pcg_update_p));
+    int g_spmv = min(kRedBlocks, sms * resident_blocks_per_sm(spmv_k));
+    int g_xr = min(kRedBlocks, sms * resident_blocks_per_sm(k_pcg_update_xr));
+    int g_p = min(kRedBlocks, sms * resident_blocks_per_sm(k_pcg_update_p));
+    // small systems: a grid-wide fold costs time proportional to the number of CTAs that take part, so the grid shrinks with
+    // the work (at least kMinRowsPerThread rows per thread, never below one CTA per SM)
+    {
+        static const int rows_per_thread = [] { const char* e = getenv("EFB_PCG_ROWS_PER_THREAD"); return e ? atoi(e) : 4; }();
+        if (rows_per_thread > 0) {
+            const long long want = (sys->nrows + (long long)kRedThreads * rows_per_thread - 1) / ((long long)kRedThreads * rows_per_thread);
+            const int cap = (int)max((long long)sms, min((long long)kRedBlocks, want));
+            g_xr = min(g_xr, cap);
+            g_p = min(g_p, cap);
+            g_spmv = min(g_spmv, max(cap, (int)min((long long)kRedBlocks, (a.n * sys->lanes + kRedThreads - 1) / kRedThreads / 2)));
+        }
+    }
     // dev: EFB_PCG_TIMING=1 prints the mean duration of the three kernels of this call (CUDA events between the launches)
     static const bool timing = [] { const char* e = getenv("EFB_PCG_TIMING"); return e && atoi(e) > 0; }();
     cudaEvent_t* ev = nullptr;
