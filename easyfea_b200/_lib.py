@@ -67,6 +67,7 @@ SIGNATURES = {
     "efb_strain": [_GP, c_vp, c_vp, c_vp, c_vp],
     "efb_hyperelastic_Ke_Re": [_GP, c_vp, c_vp, c_vp, c_vp, c_f64, c_vp, c_vp, c_vp],
     "efb_pf_split": [ctypes.POINTER(EfbPfMaterial), c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "efb_pf_elastic_Ke": [ctypes.POINTER(EfbPfMaterial), _GP, c_vp, c_vp, c_vp, c_f64, c_f64, c_vp, c_vp],
     "efb_pf_degradation": [_GP, c_vp, c_vp, c_f64, c_vp, c_vp],
     "efb_pf_history_rf": [c_vp, c_vp, c_i64, ctypes.c_int, c_f64, c_f64, c_vp, c_vp, c_vp],
     "efb_pf_damage_Ke_Fe": [_GP, c_vp, c_vp, c_vp, c_f64, c_f64, c_vp, c_vp, c_vp],

@@ -1,6 +1,8 @@
 // C-ABI entry points of the phase-field law kernels (P2-P7): one thread per Gauss point, everything in registers.
+#include <string.h>
+
 #include "common.cuh"
-#include "pf_math.cuh"
+#include "pf_fused.cuh"
 
 namespace efb {
 
@@ -44,6 +46,14 @@ __global__ void __launch_bounds__(128)
         const double gi = g[i];
         for (int k = 0; k < NC; ++k) Cdeg[i * NC + k] = gi * cP[k] + cM[k];  // Simulations/_phasefield.py:462-469
     }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(128) k_pf_elastic_simplex(PfMat m, GroupView g, const int* __restrict__ connect_dof,
+                                                            const double* __restrict__ u, const double* __restrict__ d, double k_res,
+                                                            double scale, double* __restrict__ Ke) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < g.Ne) pf_elastic_simplex_item<DIM>(m, g, connect_dof, u, d, k_res, scale, e, Ke);
 }
 
 __global__ void k_pf_history_rf(double* __restrict__ psiP, const double* __restrict__ psiP_old, long long n, int regu, double Gc,
@@ -101,6 +111,30 @@ extern "C" int efb_pf_split(const efb_pf_material* m, const double* eps, int64_t
         k_pf_split<3><<<nblk, 128, 0, st>>>(pm, eps, n, nPg, bits, cP, cM, psiP, psiM, g_e_pg, Cdeg);
     }
     return check_launch("efb_pf_split");
+}
+
+extern "C" int efb_pf_elastic_Ke(const efb_pf_material* m, const efb_group* g, const int32_t* connect_dof, const double* u,
+                                 const double* d, double k_res, double scale, double* Ke, void* stream) {
+    if (!m || !g || !connect_dof || !u || !d || !Ke || !g->connect || !g->coord || !g->dN_pg || !g->N_pg || !g->w_pg) {
+        set_error("efb_pf_elastic_Ke: bad arguments");
+        return 1;
+    }
+    if (g->nPg != 1 || g->nPe != g->dim + 1 || m->dim != g->dim || m->split < 0 || m->split > EFB_SPLIT_HE) {
+        set_error("efb_pf_elastic_Ke: one-point simplex elements only (dim %d, nPe %d, nPg %d)", (int)g->dim, (int)g->nPe, (int)g->nPg);
+        return 3;  // the caller composes strain -> degradation -> split -> stiffness instead
+    }
+    if (g->Ne == 0) return 0;
+    PfMat pm;
+    memcpy(&pm, m, sizeof(pm));
+    GroupView v;
+    v.nPg = g->nPg; v.coord_stride = g->coord_stride; v.Ne = g->Ne; v.connect = g->connect; v.coord = g->coord;
+    v.dN_pg = g->dN_pg; v.N_pg = g->N_pg; v.w_pg = g->w_pg;
+    const unsigned nblk = (unsigned)((g->Ne + 127) / 128);
+    if (g->dim == 2)
+        k_pf_elastic_simplex<2><<<nblk, 128, 0, as_stream(stream)>>>(pm, v, connect_dof, u, d, k_res, scale, Ke);
+    else
+        k_pf_elastic_simplex<3><<<nblk, 128, 0, as_stream(stream)>>>(pm, v, connect_dof, u, d, k_res, scale, Ke);
+    return check_launch("efb_pf_elastic_Ke");
 }
 
 extern "C" int efb_pf_history_rf(double* psiP, const double* psiP_old, int64_t n, int regu, double Gc, double l0, double* r,

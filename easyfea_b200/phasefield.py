@@ -186,12 +186,24 @@ class PhaseFieldModel:
         return dv.to_host(self.history_rf_dev(psi, None, False, True)[1])
 
     # -- simulation-level builders, device resident ---------------------------------------------------------------
-    def elastic_Ke_dev(self, groupElem, u, d, matrixType=op.RIGI):
-        """S3: K_e of the displacement sub-problem = LinearizedElasticity(g(d) cP + cM), x thickness in 2D."""
+    def elastic_Ke_dev(self, groupElem, u, d, matrixType=op.RIGI, fused: bool = True):
+        """S3: K_e of the displacement sub-problem = LinearizedElasticity(g(d) cP + cM), x thickness in 2D.  One-point simplex
+        elements (TRI3, TETRA4) take the one-pass kernel `efb_pf_elastic_Ke`; the others the four-kernel composition."""
+        dg = device_group(groupElem)
+        mt = op._mt(matrixType)
+        scale = self.thickness if self.dim == 2 else 1.0
+        if fused and dg.nPg(mt) == 1 and dg.nPe == dg.dim + 1:
+            ud, dd = dv.to_device(u), dv.to_device(d)
+            if ud.numel() != dg.Ncoords * dg.dim or dd.numel() != dg.Ncoords:
+                raise ValueError("Wrong dimension")
+            ndof = dg.nPe * dg.dim
+            Ke = dv.empty((dg.Ne, ndof, ndof))
+            _lib.call("efb_pf_elastic_Ke", self._cmat(), dg.cstruct(mt), dv.ptr(dg.connect_glob), dv.ptr(ud), dv.ptr(dd), 1e-12,
+                      float(scale), dv.ptr(Ke), dv.stream_ptr())
+            return Ke
         eps = op.strain_dev(groupElem, u, matrixType)
         g = self.degradation_dev(d, groupElem, matrixType)
         C = self.split_dev(eps, ("Cdeg",), g)["Cdeg"]
-        scale = self.thickness if self.dim == 2 else 1.0
         return op.elastic_Ke_dev(groupElem, C, matrixType, scale)
 
     def damage_system_dev(self, groupElem, u, psiP_old=None):

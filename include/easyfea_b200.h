@@ -117,6 +117,12 @@ typedef struct efb_pf_material {
 int efb_pf_split(const efb_pf_material* m, const double* eps, int64_t Ne, int32_t nPg,
                  int32_t* elem_bits /* (Ne) int32 workspace; may be NULL in 2D or for Bourdin/Amor */, double* cP,
                  double* cM, double* psiP, double* psiM, const double* g_e_pg, double* Cdeg, void* stream);
+/* S3 in one pass for one-point simplex elements (TRI3, TETRA4): `PhaseField.__Construct_Elastic_Matrix`,
+ * EasyFEA/Simulations/_phasefield.py:444-482 — strain -> split -> C = g(d) cP + cM -> Ke (Ne,ndof,ndof) = scale * wJ B^T C B,
+ * u (Nn*dim) / d (Nn) nodal fields, connect_dof GLOBAL node ids.  The strain, g and C(d) arrays of the composition
+ * efb_strain -> efb_pf_degradation -> efb_pf_split -> efb_elastic_Ke never exist.  Returns 3 for other element types / quadratures. */
+int efb_pf_elastic_Ke(const efb_pf_material* m, const efb_group* g, const int32_t* connect_dof, const double* u, const double* d,
+                      double k_res, double scale, double* Ke, void* stream);
 /* Get_g_e_pg :295-317: g (Ne,nPg) = (1 - N d_e)^2 + k_res, d (Nn) nodal damage. */
 int efb_pf_degradation(const efb_group* g, const int32_t* connect_dof, const double* d, double k_res, double* out,
                        void* stream);

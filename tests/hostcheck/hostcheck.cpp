@@ -341,6 +341,20 @@ extern "C" void hc_replay_vector(void* p, int n_groups, const double* const* dat
     for (long long r = 0; r < Nn * d; ++r) replay_vector_item(T, d, r, P->rowptr.data(), P->qlist.data(), out);
 }
 
+#include "../../easyfea_b200/csrc/pf_fused.cuh"
+
+extern "C" int hc_pf_elastic_Ke(const efb_pf_material* m, const efb_group* g, const int32_t* connect_dof, const double* u, const double* d,
+                                double k_res, double scale, double* Ke) {
+    if (g->nPg != 1 || g->nPe != g->dim + 1) return 3;
+    PfMat pm;
+    memcpy(&pm, m, sizeof(pm));
+    for (long long e = 0; e < g->Ne; ++e) {
+        if (g->dim == 2) pf_elastic_simplex_item<2>(pm, view_of(g), connect_dof, u, d, k_res, scale, e, Ke);
+        else pf_elastic_simplex_item<3>(pm, view_of(g), connect_dof, u, d, k_res, scale, e, Ke);
+    }
+    return 0;
+}
+
 // ---- fused element integration + assembly (csrc/fused_kernels.cuh): one emulated CTA per cluster ----
 #include "../../easyfea_b200/csrc/fused_kernels.cuh"
 

@@ -98,7 +98,9 @@ def test_simulation_level_builders(efb, elemType, split, regu):
     tr, tm = el.gauss_table(elemType, "rigi"), el.gauss_table(elemType, "mass")
     geo_r = orc.geometry(coords[connect][:, :, :dim], tr.dN_pg, tr.weights)
     geo_m = orc.geometry(coords[connect][:, :, :dim], tm.dN_pg, tm.weights)
-    Ke = pfm.elastic_Ke_dev(g, u, dmg).cpu().numpy()
+    Ke = pfm.elastic_Ke_dev(g, u, dmg).cpu().numpy()  # one-pass kernel for TRI3 / TETRA4, composition otherwise
+    Ke4 = pfm.elastic_Ke_dev(g, u, dmg, fused=False).cpu().numpy()  # strain -> degradation -> split -> stiffness
+    assert rel_err(Ke, Ke4) < TOL
     ref = thickness * orc.pf_elastic_Ke(geo_r, tr.N_pg, om, split, u_e, dmg[connect], clamp=True)
     assert rel_err(Ke, ref) < TOL  # measured 1.5e-16 .. 1.9e-13 (Stress split in 3D), profiles/r2_dist2_and_pf_errors.log
     old = rng.uniform(0, 1, (g.Ne, tm.nPg)) * float(np.median(orc.calc_psi(om, split, orc.strain(geo_m, u_e), True)[0]))

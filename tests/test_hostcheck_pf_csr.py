@@ -165,3 +165,27 @@ def test_pattern_two_groups_mixed(hostcheck):
         hostcheck.hc_replay_matrix(P, I(2), dptr, Ne, nPeA, I(d), ctypes.c_int64(Nn), p(out))
         assert np.array_equal(out, orc.assemble_replay([K1, K2], oinv, onnz))
         hostcheck.hc_pattern_free(P)
+
+
+@pytest.mark.parametrize("elemType,dim", [("TRI3", 2), ("TETRA4", 3)])
+@pytest.mark.parametrize("split", list(SPLITS))
+def test_fused_S3_simplex(hostcheck, elemType, dim, split):
+    """`efb_pf_elastic_Ke` body (strain -> split -> g cP + cM -> K_e in one pass, configs 3 and 4) against the oracle composition
+    of Simulations/_phasefield.py:444-482"""
+    from tests.helpers import make_mesh
+
+    rng = np.random.default_rng(8)
+    coords, connect = make_mesh(elemType, (7, 6) if dim == 2 else (4, 3, 3))
+    g, keep, tab = host_group(elemType, coords, connect, "rigi")
+    Nn = coords.shape[0]
+    mat = orc.IsoMaterial(dim, 210e9, 0.3, False)
+    u = rng.normal(size=Nn * dim) * 1e-5
+    dmg = rng.uniform(0, 0.9, Nn)
+    c32 = np.ascontiguousarray(connect, dtype=np.int32)
+    Ke = np.empty((g.Ne, g.nPe * dim, g.nPe * dim))
+    m = c_material(mat, split)
+    assert hostcheck.hc_pf_elastic_Ke(ctypes.byref(m), ctypes.byref(g), p(c32), p(u), p(dmg), ctypes.c_double(1e-12), ctypes.c_double(0.5),
+                                      p(Ke)) == 0
+    geo = orc.geometry(coords[connect][:, :, :dim], tab.dN_pg, tab.weights)
+    ref = 0.5 * orc.pf_elastic_Ke(geo, tab.N_pg, mat, split, orc.locate_sol_e(u, connect, dim), dmg[connect], clamp=True)
+    assert rel_err(Ke, ref) < 1e-12
