@@ -618,7 +618,7 @@ def phase_field_leg(args, rank, world, dist, cfg_id):
                                      "AT2", 2.7e3, l0)
     simu = staggered.PhaseFieldStaggered(sysm, pfm, pcg_tol=1e-8, pcg_maxiter=args.pf_maxiter)
     simu.pcg_fused = False if args.pf_unfused else "auto"
-    simu.pcg_single_reduction = bool(args.pf_single_reduction)
+    simu.pcg_single_reduction = {"auto": "auto", "on": True, "off": False}[args.pf_single_reduction]
     ix, iy = np.rint(lattice[nodes, 0] / L * n).astype(np.int64), np.rint(lattice[nodes, 1] / L * n).astype(np.int64)
     loc = np.arange(nodes.size)
     comps = list(range(dim))
@@ -940,7 +940,8 @@ def main():
     ap.add_argument("--no-transient", action="store_true", help="skip the HEXA27 transient extra (config 5)")
     ap.add_argument("--tr-n", type=int, default=40, help="HEXA27 cells per side (40 -> 64 000 elements, 531 441 nodes)")
     ap.add_argument("--tr-steps", type=int, default=3)
-    ap.add_argument("--pf-single-reduction", action="store_true", help="phase-field solves with the Chronopoulos-Gear PCG form")
+    ap.add_argument("--pf-single-reduction", default="auto", choices=["auto", "on", "off"],
+                    help="phase-field solves with the Chronopoulos-Gear PCG form (auto: small shards)")
     ap.add_argument("--pf-unfused", action="store_true", help="phase-field solves with the NCCL/kernel-per-operation PCG loop")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -47,7 +47,7 @@ class EfbPcgPeer(ctypes.Structure):
     _fields_ = [("world", c_i32), ("rank", c_i32), ("n_send", c_i32), ("n_recv", c_i32), ("send_rank", c_i32 * MAX_RANKS),
                 ("recv_rank", c_i32 * MAX_RANKS), ("send_ptr", c_i64 * (MAX_RANKS + 1)), ("send_dst", c_i64 * MAX_RANKS),
                 ("base", c_vp * MAX_RANKS), ("pbuf_off", (c_i64 * 2) * MAX_RANKS), ("send_idx", c_vp), ("ar_seq", ctypes.c_uint64),
-                ("halo_seq", ctypes.c_uint64)]
+                ("halo_seq", ctypes.c_uint64), ("push_id", c_vp), ("push_ptr", c_vp), ("push_nbr", c_vp), ("push_pos", c_vp)]
 
 
 _GP = ctypes.POINTER(EfbGroup)

@@ -776,9 +776,21 @@ __global__ void __launch_bounds__(kRedThreads)
     k_cg2_update(long long n, const double* __restrict__ zc, double* __restrict__ zn, const double* __restrict__ w, double* __restrict__ p,
                  double* __restrict__ s, double* __restrict__ x, double* __restrict__ r, const double* __restrict__ inv_diag,
                  const unsigned char* __restrict__ mask, double* __restrict__ partials, efb_pcg_peer P, long long it,
-                 unsigned long long ar_done) {
+                 unsigned long long ar_done, unsigned long long halo_done) {
     __shared__ double red[kRedThreads];
+    __shared__ bool is_last;
     PcgCtrl* own = (PcgCtrl*)P.base[P.rank];
+    const int nxt = (int)(it & 1) ^ 1;
+    const int* __restrict__ push_id = P.n_send > 0 ? P.push_id : nullptr;
+    // the thread that produces an interface entry of the new z also stores it into the halo segments of the neighbours
+    auto push = [&](long long i, double zi) {
+        const int c = push_id[i];
+        if (c >= 0)
+            for (long long t = P.push_ptr[c]; t < P.push_ptr[c + 1]; ++t) {
+                const int q = P.send_rank[P.push_nbr[t]];
+                ((double*)((char*)P.base[q] + P.pbuf_off[q][nxt]))[P.push_pos[t]] = zi;
+            }
+    };
     double v[3];  // gamma = r.z, delta = z.Az, r.r of the current iterate
     if (it == 0) {
         v[0] = own->cg2_init[0];
@@ -796,6 +808,7 @@ __global__ void __launch_bounds__(kRedThreads)
     for (long long i = (long long)blockIdx.x * kRedThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kRedThreads) {
         if (mask && !mask[i]) {
             zn[i] = 0.0;
+            if (push_id) push(i, 0.0);
             continue;
         }
         const double pi = zc[i] + beta * p[i];
@@ -807,10 +820,12 @@ __global__ void __launch_bounds__(kRedThreads)
         r[i] = ri;
         const double zi = ri * inv_diag[i];
         zn[i] = zi;
+        if (push_id) push(i, zi);
         s_rz += ri * zi;
         s_rr += ri * ri;
     }
-    const double t0 = block_sum(s_rz, red), t1 = block_sum(s_rr, red);
+    const double t0 = block_sum(s_rz, red), t1 = block_sum(s_rr, red);  // (block_sum ends with a CTA barrier: every thread's
+                                                                       // peer stores happen-before thread 0's fence below)
     if (threadIdx.x == 0) {
         partials[kRedBlocks + blockIdx.x] = t0;      // folded by the SpMV kernel's last CTA together with its z.Az partials
         partials[2 * kRedBlocks + blockIdx.x] = t1;
@@ -818,6 +833,19 @@ __global__ void __launch_bounds__(kRedThreads)
             own->cg2_gam[(it + 1) & 1] = v[0];
             own->cg2_alp[(it + 1) & 1] = alpha;
             own->rr = v[2];
+        }
+    }
+    if (P.n_send > 0) {  // the last CTA raises the neighbours' halo flags: every interface entry of z is in place
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            fence_sys();
+            is_last = atomicAdd(&own->ticket[2], 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (is_last && threadIdx.x == 0) {
+            fence_sys();
+            for (int sidx = 0; sidx < P.n_send; ++sidx) st_release_sys(&((PcgCtrl*)P.base[P.send_rank[sidx]])->halo_flag[P.rank], halo_done + 1ull);
+            own->ticket[2] = 0;
         }
     }
 }
@@ -1169,9 +1197,12 @@ extern "C" int efb_pcg_iterate_cg2(const efb_pcg_system* sys, const efb_pcg_peer
         double* zn = (double*)((char*)P.base[P.rank] + P.pbuf_off[P.rank][nxt]);
         const unsigned long long ar_done = P.ar_seq + (unsigned long long)k, halo_done = P.halo_seq + (unsigned long long)k;
         // p lives in sys->z (z itself lives in the two peer buffers), w in sys->Ap
+        const bool rowwise = P.n_send == 0 || P.push_id != nullptr;  // the update kernel pushes the interface entries itself
+        efb_pcg_peer Pu = P;
+        if (!rowwise) Pu.n_send = 0;  // no row-wise plan given: separate push kernel below
         k_cg2_update<<<g_upd, kRedThreads, 0, st>>>(sys->nrows, zc, zn, sys->Ap, sys->z, sys->s, sys->x, sys->r, sys->inv_diag, sys->free_mask,
-                                                    sys->partials, P, it, ar_done);
-        if (P.n_send > 0) k_cg2_push<<<g_push, kRedThreads, 0, st>>>(zn, P, nxt, halo_done);
+                                                    sys->partials, Pu, it, ar_done, halo_done);
+        if (!rowwise) k_cg2_push<<<g_push, kRedThreads, 0, st>>>(zn, P, nxt, halo_done);
         spmv_k<<<g_spmv, kRedThreads, 0, st>>>(n_spmv, sys->indptr, sys->indices, sys->data, zn, sys->free_mask, sys->Ap, sys->partials, g_upd, P,
                                                ar_done, halo_done + 1ull);
     }

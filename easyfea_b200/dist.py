@@ -483,6 +483,23 @@ def peer_push_plan(comm: "RowComm", recv_lo_of_rank):
     return send_rank, send_ptr, send_dst, recv_rank
 
 
+def row_push_plan(send_idx: np.ndarray, send_ptr, send_dst, n_rows: int):
+    """Invert the per-neighbour send lists into a per-row plan: (push_id (n_rows) int32, push_ptr int64, push_nbr int32,
+    push_pos int64), or None when nothing is sent.  Entry j of neighbour s goes to position send_dst[s] + (j - send_ptr[s])."""
+    send_idx = np.asarray(send_idx, dtype=np.int64)
+    if send_idx.size == 0:
+        return None
+    nbr = np.concatenate([np.full(send_ptr[s + 1] - send_ptr[s], s, dtype=np.int32) for s in range(len(send_ptr) - 1)])
+    pos = np.concatenate([send_dst[s] + np.arange(send_ptr[s + 1] - send_ptr[s], dtype=np.int64) for s in range(len(send_ptr) - 1)])
+    order = np.argsort(send_idx, kind="stable")
+    rows, first, counts = np.unique(send_idx[order], return_index=True, return_counts=True)
+    push_id = np.full(n_rows, -1, dtype=np.int32)
+    push_id[rows] = np.arange(rows.size, dtype=np.int32)
+    push_ptr = np.zeros(rows.size + 1, dtype=np.int64)
+    np.cumsum(counts, out=push_ptr[1:])
+    return push_id, push_ptr, np.ascontiguousarray(nbr[order]), np.ascontiguousarray(pos[order])
+
+
 class LocalWorkspace:
     """Single-GPU workspace of `efb_pcg_iterate`: control block + two p buffers in ordinary device memory."""
 
@@ -581,6 +598,12 @@ class PeerWorkspace(LocalWorkspace):
             P.recv_rank[i] = q
         P.send_idx = comm.send_idx.data_ptr() if comm.send_idx.numel() else None
         P.ar_seq, P.halo_seq = 0, 0
+        # the same plan seen from the rows (single-reduction form: the update kernel stores a row into the neighbours when it
+        # produces it): push_id[row] = -1 | c, entries push_ptr[c]:push_ptr[c+1] of (neighbour index, entry in its vector)
+        self._push = row_push_plan(comm.send_idx.cpu().numpy(), send_ptr, send_dst, part.n_owned * d)
+        if self._push is not None:
+            self._push = tuple(torch.from_numpy(a).to(comm.device) for a in self._push)
+            P.push_id, P.push_ptr, P.push_nbr, P.push_pos = (t.data_ptr() for t in self._push)
         dist.barrier(group=comm.group)  # every region is mapped before anybody stores into it
 
     def close(self):

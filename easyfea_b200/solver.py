@@ -85,10 +85,15 @@ def _system_struct(A: DeviceCsr, nrows, mask, inv_diag, x, r, z, Ap, partials) -
 # (8 GPUs, 24 M dofs each; profiles/r1_bench_n200_8gpu.json).  Below it the sync points dominate and the fused peer-memory
 # form wins (2 GPUs, 1 M dofs each: 0.82 vs 1.69 s per staggered iteration).
 FUSED_MAX_DOFS = 8_000_000
+# Below this many owned dofs per rank an iteration is bound by its kernel launches and grid-wide folds, not by bandwidth: the
+# single-reduction (Chronopoulos-Gear) form runs two kernels and one all-reduce per iteration instead of three and two —
+# 29.6 vs 60.6 us per iteration at 0.25 M dofs on one B200, equal at 2 M dofs (profiles/r2_pcg_small_systems.log).  Its
+# recurrences carry one more rounding error per step, so `single_reduction="auto"` keeps the classic form for tol < 1e-10.
+SINGLE_REDUCTION_MAX_DOFS = 1_500_000
 
 
 def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: int = None, check_every: int = 25, comm=None,
-        fused="auto", persistent: bool = False, single_reduction: bool = False):
+        fused="auto", persistent: bool = False, single_reduction="auto"):
     """Solve A x = b on the free dofs (free_mask True / 1 = unknown; other entries of x keep the values of x0).
 
     A holds the owned rows in LOCAL numbering `[owned | halo]` columns.  Stops when ||r|| <= tol * ||b - A x_known||
@@ -101,6 +106,7 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
     `persistent=True` (matrices assembled by this library) ONE cooperative kernel iterates until convergence instead
     (`efb_pcg_solve_persistent`: grid barriers between the steps, every rank leaves in the same iteration, no host round
     trip at all); measured equal on small systems and ~8 % slower on large ones (profiles/README.md), hence opt-in.
+    `single_reduction="auto"` picks that form for small shards and tol >= 1e-10 (see SINGLE_REDUCTION_MAX_DOFS).
     `single_reduction=True`: the Chronopoulos-Gear form of the same iteration (`efb_pcg_iterate_cg2`) — one all-reduce, two
     kernels and two cross-GPU sync points per iteration instead of two, three and three; one more vector pass.  Opt-in:
     measured 13 % / 8 % faster at 0.2 M dofs on 1 / 2 GPUs and 1-3 % slower at >= 2 M dofs per rank, identical iteration
@@ -117,7 +123,15 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
         big = torch.tensor([float(nrows)], dtype=torch.float64, device=dev)
         if comm is not None:
             comm.all_reduce_max(big)
-        fused = bool(single_reduction or persistent) or float(big.item()) <= FUSED_MAX_DOFS
+        fused = bool(single_reduction is True or persistent) or float(big.item()) <= FUSED_MAX_DOFS
+    else:
+        big = None
+    if single_reduction == "auto":
+        if big is None:
+            big = torch.tensor([float(nrows)], dtype=torch.float64, device=dev)
+            if comm is not None:
+                comm.all_reduce_max(big)
+        single_reduction = bool(fused) and not persistent and tol >= 1e-10 and float(big.item()) <= SINGLE_REDUCTION_MAX_DOFS
     single_reduction = bool(single_reduction) and bool(fused)
     st = dv.stream_ptr
     b = dv.to_device(b)

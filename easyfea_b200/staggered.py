@@ -124,7 +124,7 @@ class ElasticSolve:
         self.u = torch.zeros(system.n_local * self.dim, dtype=torch.float64, device=dv.device())
         self.pcg_fused = "auto"  # True / False force the fused peer-memory form / the kernel-per-operation loop (solver.pcg)
         self.pcg_persistent = False  # True: one cooperative kernel per solve instead of three kernels per iteration
-        self.pcg_single_reduction = False  # True: Chronopoulos-Gear form, one all-reduce per iteration
+        self.pcg_single_reduction = "auto"  # True / False force / forbid the Chronopoulos-Gear form (one all-reduce per iteration)
 
     def assemble(self) -> DeviceCsr:
         scale = self.thickness if self.dim == 2 else 1.0
@@ -163,7 +163,7 @@ class PhaseFieldStaggered:
         self.bc_d = Dirichlet(system.n_local)
         self.f_ext = None      # nodal external forces of the displacement problem (owned dofs), `add_neumann`
         self.pcg_tol, self.pcg_maxiter = pcg_tol, pcg_maxiter
-        self.pcg_fused, self.pcg_persistent, self.pcg_single_reduction = "auto", False, False
+        self.pcg_fused, self.pcg_persistent, self.pcg_single_reduction = "auto", False, "auto"
         self._updatedDamage = self._updatedDisplacement = False
         self.info = {}
 

@@ -105,7 +105,7 @@ class TransientSolve:
         self.K = self.C = self.M = None
         self.algo = "elliptic"
         self.pcg_tol, self.pcg_maxiter, self.pcg_fused, self.pcg_persistent = 1e-10, None, "auto", False
-        self.pcg_single_reduction = False
+        self.pcg_single_reduction = "auto"
         self.info = {}
 
     # -- systems ---------------------------------------------------------------------------------------------------

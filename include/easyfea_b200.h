@@ -279,6 +279,13 @@ typedef struct efb_pcg_peer {
     const int32_t* send_idx;                  /* owned local dof ids to push, concatenated per neighbour */
     uint64_t ar_seq;                          /* reductions already published on this communicator */
     uint64_t halo_seq;                        /* halo pushes already published */
+    /* the same push plan seen from the rows (single-reduction form: the CTA that updates a row also stores it into the
+     * neighbours, no separate push kernel): push_id (nrows) = -1 or c; entries push_ptr[c] .. push_ptr[c+1] of
+     * push_nbr (index into send_rank) / push_pos (entry inside that neighbour's vector).  NULL when n_send == 0. */
+    const int32_t* push_id;
+    const int64_t* push_ptr;
+    const int32_t* push_nbr;
+    const int64_t* push_pos;
 } efb_pcg_peer;
 
 /* a region starts with a control block of efb_pcg_ctrl_bytes() bytes (zero it once); offsets of the device scalars
@@ -291,7 +298,8 @@ int efb_pcg_ctrl_layout(int32_t* out5);
  * The caller advances peer->ar_seq by 2*n_iters and halo_seq by n_iters afterwards. */
 int efb_pcg_iterate(const efb_pcg_system* sys, const efb_pcg_peer* peer, int n_iters, int64_t it0, void* stream);
 /* Single-reduction form (Chronopoulos-Gear): the same iterates with ONE all-reduce per iteration — two kernels (vector
- * update, SpMV) and two cross-GPU sync points per iteration instead of three and three.  z lives in the two peer buffers
+ * update, SpMV) and two cross-GPU sync points per iteration instead of three and three (the interface entries of z are stored into the neighbours by
+ * the update kernel itself, through the row-wise push plan of efb_pcg_peer).  z lives in the two peer buffers
  * (its halo is what travels), p in sys->z, w = A z in sys->Ap, s = A p in sys->s.  Before iteration 0 the caller puts z_0
  * (owned + halo) in buffer 0, w_0 = A z_0 in sys->Ap, zeros in p and s, and (r.z, z.Az, r.r) in the control block
  * (layout out[4]).  The caller advances ar_seq and halo_seq by n_iters afterwards; r.r of the last iterate is in the

@@ -282,3 +282,23 @@ def test_distributed_partition_build_equals_gathered_build(world, elemType, n):
         p.join(timeout=60)
     for rank, status, info in results:
         assert status == "ok", f"rank {rank}: {info}"
+
+
+def test_row_push_plan_inverts_the_send_lists():
+    """the single-reduction PCG pushes interface rows from the update kernel: per-row plan == per-neighbour send lists"""
+    rng = np.random.default_rng(0)
+    n_rows = 50
+    lists = [np.sort(rng.choice(n_rows, size=k, replace=False)) for k in (7, 11, 5)]
+    send_idx = np.concatenate(lists)
+    send_ptr = np.concatenate([[0], np.cumsum([a.size for a in lists])]).tolist()
+    send_dst = [100, 300, 40]
+    push_id, push_ptr, push_nbr, push_pos = efd.row_push_plan(send_idx, send_ptr, send_dst, n_rows)
+    got = set()
+    for row in range(n_rows):
+        c = push_id[row]
+        if c >= 0:
+            for t in range(push_ptr[c], push_ptr[c + 1]):
+                got.add((row, int(push_nbr[t]), int(push_pos[t])))
+    want = {(int(r), s, send_dst[s] + j) for s, a in enumerate(lists) for j, r in enumerate(a)}
+    assert got == want
+    assert efd.row_push_plan(np.empty(0, dtype=np.int64), [0], [], n_rows) is None
