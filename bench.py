@@ -47,6 +47,30 @@ def ncu_traffic(kernel: str, units: int):
         return None
 
 
+_STDOUT_FD = None
+
+
+def quiet_stdout():
+    """stdout must carry exactly ONE JSON line, but native libraries write there too (NCCL prints its version banner on the first
+    communicator, whatever NCCL_DEBUG says in some builds): file descriptor 1 is pointed at stderr for the whole run and the
+    line is written to a saved copy of the original descriptor by `emit`."""
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _STDOUT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_STDOUT_FD, data)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -267,7 +291,7 @@ def run_reference(args):
                              "host_cores": os.cpu_count(), "pattern_build_s": pattern_s, "units_per_step": units_step},
             "e2e": {"value": value, "unit": "GP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t_all0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # -----------------------------------------------------------------------------------------------------------------
@@ -514,7 +538,7 @@ def run_ours(args):
             v, dt, procs, pattern_s, kind = cpu_arm(args.cpu_sample, 1, 3, args.cpu_procs, args.cpu_kind or None)
             line["cpu_baseline"] = {"value": v, "unit": "GP/s", "cores": procs, "kind": kind, "host_cores": os.cpu_count(),
                                     "pattern_build_s": pattern_s, "sample": cpu_sample_text(kind, procs, args.cpu_sample, dt, 3)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -944,6 +968,7 @@ def main():
                     help="phase-field solves with the Chronopoulos-Gear PCG form (auto: small shards)")
     ap.add_argument("--pf-unfused", action="store_true", help="phase-field solves with the NCCL/kernel-per-operation PCG loop")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
