@@ -87,6 +87,9 @@ SIGNATURES = {
                              c_vp, c_vp],
     "efb_assemble_elastic_smem": [ctypes.c_int] * 6,
     "efb_assemble_elastic_group": [ctypes.c_int] * 3,
+    "efb_assemble_elastic_mma": [_GP, c_vp, c_vp, c_f64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                 ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "efb_assemble_elastic_mma_smem": [ctypes.c_int] * 3,
     "efb_spmv_csr": [c_i64, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, ctypes.c_int, c_vp],
     "efb_spmv_nodeblock": [c_i64, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, ctypes.c_int, c_vp],
     "efb_csr_diagonal": [c_i64, c_i64, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp],

@@ -411,3 +411,160 @@ def assemble_elastic_fused(sched: FusedSchedule, C, matrixType="rigi", scale: fl
               sched.n_clusters, sched.S, sched.cap_e, sched.max_deg, dv.ptr(sched.cl_nodes), dv.ptr(sched.cl_ne),
               dv.ptr(sched.cl_conn), dv.ptr(sched.desc), dv.ptr(sched.tpos), dv.ptr(out), dv.stream_ptr())
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# HEXA8 / 8 Gauss points on the FP64 MMA instruction: staging slots + per-cluster gather programs of `efb_assemble_elastic_mma`
+# ---------------------------------------------------------------------------------------------------------
+class MmaSchedule:
+    """One-time schedule of `efb_assemble_elastic_mma` (csrc/fused_mma.cu) on top of a `FusedSchedule` with clusters of 16
+    nodes: element slabs padded to passes of 4, `rowslot` (staging slot | node swizzle of every (cluster element, local node)
+    whose node the cluster owns), round headers and the gather programs (every CSR block of a cluster -> one lane of one
+    round, rounds sorted by the number of contributions, each block's contributions in ascending element order).  torch
+    tensor ops on the schedule's device — preprocessing."""
+
+    S = 16
+    TS = 72            # doubles per staged task (kMmaTS)
+    MAX_TRIPS = 255
+
+    @staticmethod
+    def supports(dg, nPg) -> bool:
+        return dg.dim == 3 and dg.nPe == 8 and int(nPg) == 8
+
+    def __init__(self, graph: NodeGraph, n_nodes: int = None, base: "FusedSchedule" = None, nPg: int = None):
+        sched = base if base is not None and base.S == self.S else FusedSchedule(graph, n_nodes=n_nodes, S=self.S, nPg=nPg)
+        if not self.supports(sched.dg, sched.nPg):
+            raise NotImplementedError("efb_assemble_elastic_mma serves HEXA8 with 8 Gauss points")
+        self.base, self.graph, self.dg = sched, sched.graph, sched.dg
+        S, nPe, cap_e, ncl = self.S, 8, sched.cap_e, sched.n_clusters
+        cap4 = max((cap_e + 3) // 4 * 4, 4)
+        dev = sched.cl_nodes.device
+        nodes = sched.cl_nodes
+        i64 = torch.int64
+        ar = lambda n: torch.arange(n, device=dev, dtype=i64)  # noqa: E731
+        kidx = torch.nonzero(nodes[:, 0] >= 0).reshape(-1)                     # valid cluster slots, = ordered nodes in order
+        cnt = nodes[kidx, 2] >> 32
+        deg = nodes[kidx, 2] & 0xffffffff
+        n_tasks = sched.n_tasks
+        ki_t = torch.repeat_interleave(ar(kidx.numel()), cnt)
+        kt = kidx[ki_t]                                                        # cluster slot of every task
+        cl, iloc_t = kt // S, kt % S
+        cl_task0 = torch.searchsorted(cl, ar(ncl + 1))
+        self.t_cap = int((cl_task0[1:] - cl_task0[:-1]).max().item()) if ncl else 0
+        # staging slot: tasks of a cluster in order, the tasks of nodes 8..15 swapped pairwise (slot parity then differs
+        # between node i and node i + 8: with the column swizzle b ^ (i & 7) the 16 nodes of a cluster sit in 16 distinct
+        # 8-byte bank classes, so a gather round whose lanes do the same thing for different nodes is conflict-free)
+        node_t0 = torch.zeros(kidx.numel() + 1, dtype=i64, device=dev)
+        torch.cumsum(cnt, 0, out=node_t0[1:])
+        j = ar(n_tasks) - node_t0[ki_t]
+        jswap = torch.where((j ^ 1) < cnt[ki_t], j ^ 1, j)
+        j2 = torch.where(((iloc_t >> 3) & 1) == 1, jswap, j)
+        t_loc = node_t0[ki_t] + j2 - cl_task0[cl]
+        xs_t = iloc_t & 7
+        desc = sched.desc.to(i64)
+        le, a = desc & 0xffff, desc >> 16
+        rowslot = torch.full((ncl * cap4 * nPe,), -1, dtype=torch.int16, device=dev)
+        rowslot[(cl * cap4 + le) * nPe + a] = (t_loc | (xs_t << 8)).to(torch.int16)
+        # pairs of local nodes (2j, 2j+1) with an owned node: the row tiles the kernel computes
+        self.n_row_tiles = int((rowslot.view(torch.int32) != -1).sum().item())
+        # ---- blocks of every cluster, sorted by (cluster, contributions descending, slot, node in cluster) ----
+        bptr = torch.zeros(kidx.numel() + 1, dtype=i64, device=dev)
+        torch.cumsum(deg, 0, out=bptr[1:])
+        nb = int(bptr[-1].item())
+        bk = torch.repeat_interleave(ar(kidx.numel()), deg)                    # index into kidx of every block
+        slot = ar(nb) - bptr[bk]
+        node_blk0 = nodes[kidx, 1] // 9                                        # adjptr[node]: global id of the node's first block
+        gb = node_blk0[bk] + slot
+        gb_c = (node_blk0[ki_t].reshape(-1, 1) + sched.tpos.to(i64)).reshape(-1)   # contributions (task, b) -> global block id
+        nnzb = int(graph.nnz_node)
+        cntb = torch.bincount(gb_c, minlength=nnzb)
+        cb = cntb[gb]
+        maxc = int(cb.max().item()) if nb else 0
+        if maxc > self.MAX_TRIPS:
+            raise NotImplementedError("a CSR block with more than 255 element contributions")
+        bcl = kidx[bk] // S
+        iloc = kidx[bk] % S
+        key = ((bcl * (maxc + 1) + (maxc - cb)) * (sched.max_deg + 1) + slot) * S + iloc
+        border = torch.argsort(key, stable=True)
+        del key
+        bcl_s, cb_s = bcl[border], cb[border]
+        cl_blk0 = torch.searchsorted(bcl_s, ar(ncl + 1))
+        rank = ar(nb) - cl_blk0[bcl_s]
+        R_c = (cl_blk0[1:] - cl_blk0[:-1] + 31) // 32
+        self.rmax = max(int(R_c.max().item()) if ncl else 1, 1)
+        rptr = torch.zeros(ncl + 1, dtype=i64, device=dev)
+        torch.cumsum(R_c, 0, out=rptr[1:])
+        n_rounds = int(rptr[-1].item())
+        rcl = torch.repeat_interleave(ar(ncl), R_c)                            # cluster of every round
+        rin = ar(n_rounds) - rptr[rcl]                                         # round index inside its cluster
+        c_round = cb_s[cl_blk0[rcl] + rin * 32]                                # trip count = contributions of its first block
+        cpad = torch.where(c_round <= 1, 1, torch.where(c_round <= 2, 2, torch.where(c_round <= 4, 4, (c_round + 7) // 8 * 8)))
+        rwords = 32 + 16 * cpad
+        cs = torch.zeros(n_rounds + 1, dtype=i64, device=dev)
+        torch.cumsum(rwords, 0, out=cs[1:])
+        prog_off = cs[rptr]                                                    # (ncl + 1) word offset of every cluster program
+        roff_in = cs[:-1] - prog_off[rcl]                                      # offset of the round inside the cluster program
+        total = int(cs[-1].item())
+        # one record per cluster (streamed into shared memory by one bulk copy): conn | rowslot | nodes | hdr
+        o_rs, o_nodes = cap4 * 8, cap4 * 12
+        o_hdr = o_nodes + 4 * S
+        self.rec_words = (o_hdr + 1 + self.rmax + 3) // 4 * 4
+        recs = torch.zeros((ncl, self.rec_words), dtype=torch.int32, device=dev)
+        recs[:, :o_rs] = -1
+        recs[:, :o_rs].view(ncl, cap4, nPe)[:, :cap_e] = sched.cl_conn.reshape(ncl, cap_e, nPe)
+        recs[:, o_rs:o_nodes] = rowslot.view(torch.int32).reshape(ncl, cap4 * 4)
+        nrec = torch.stack([torch.where(nodes[:, 0] < 0, torch.full_like(nodes[:, 1], -1), nodes[:, 1]), nodes[:, 2] & 0xffffffff], 1)
+        recs[:, o_nodes:o_hdr] = nrec.contiguous().view(torch.int32).reshape(ncl, 4 * S)
+        recs[:, o_hdr] = R_c.to(torch.int32)
+        recs[rcl, o_hdr + 1 + rin] = ((roff_in << 8) | c_round).to(torch.int32)
+        self.recs = recs.contiguous()
+        self.pw_max = int((prog_off[1:] - prog_off[:-1]).max().item()) if ncl else 4
+        prog = torch.full((total + 4,), -1, dtype=torch.int32, device=dev)     # dest -1 = no block, sources 0xffff = none
+        bround = rptr[bcl_s] + rank // 32                                      # global round of every sorted block
+        blane = rank % 32
+        prog[cs[bround] + blane] = ((iloc[border] << 16) | slot[border]).to(torch.int32)
+        bpos = torch.full((nnzb,), -1, dtype=i64, device=dev)                  # position of every global block in the sorted order
+        bpos[gb[border]] = ar(nb)
+        del border
+        # contributions: rank inside their block in ascending task (= element) order
+        corder = torch.argsort(gb_c, stable=True)
+        bstart = torch.zeros(nnzb + 1, dtype=i64, device=dev)
+        torch.cumsum(cntb, 0, out=bstart[1:])
+        it = torch.empty_like(gb_c)
+        it[corder] = ar(gb_c.numel()) - bstart[gb_c[corder]]
+        del corder, bstart
+        pos_c = bpos[gb_c]
+        rc = bround[pos_c]
+        b8 = ar(8)
+        src = (t_loc.reshape(-1, 1) * self.TS + (b8.reshape(1, -1) ^ xs_t.reshape(-1, 1))).reshape(-1)
+        u16 = prog.view(torch.int16)
+        u16[(cs[rc] + 32) * 2 + blane[pos_c] * cpad[rc] + it] = src.to(torch.int16)
+        self.prog, self.prog_off = prog, prog_off.contiguous()
+        self.n_rounds, self.n_blocks = n_rounds, nb
+        self.n_clusters, self.cap_e, self.cap4 = ncl, cap_e, cap4
+
+    def smem_bytes(self) -> int:
+        return int(_lib.load().efb_assemble_elastic_mma_smem(int(self.t_cap), int(self.rec_words), int(self.pw_max)))
+
+    def fits(self) -> bool:
+        return 0 < self.t_cap <= 256 and self.t_cap * self.TS + 8 < 65535 and self.smem_bytes() <= 227 * 1024
+
+    def redundancy(self) -> float:
+        return self.base.redundancy()
+
+
+def assemble_elastic_mma(ms: MmaSchedule, C, matrixType="rigi", scale: float = 1.0, out: torch.Tensor = None):
+    """CSR `data` of K = Assembly(LinearizedElasticity(group, C)) for HEXA8 / 8 Gauss points and a homogeneous C through
+    `efb_assemble_elastic_mma` (FP64 MMA form of the fused assembly).  Rows of the scheduled nodes are written."""
+    sched, dg, g = ms.base, ms.dg, ms.graph
+    mt = getattr(matrixType, "value", str(matrixType))
+    C = np.ascontiguousarray(np.asarray(C, dtype=np.float64))
+    if C.shape != (6, 6):
+        raise ValueError(f"the fused assembly needs a homogeneous (6, 6) C; got {C.shape}")
+    if out is None:
+        out = dv.empty((g.nnz_node * 9,))
+    w = np.ascontiguousarray(dv.to_host(dg.tables(mt)[2]))
+    _lib.call("efb_assemble_elastic_mma", dg.cstruct(mt), ctypes.c_void_p(C.ctypes.data), ctypes.c_void_p(w.ctypes.data), float(scale),
+              ms.n_clusters, ms.cap4, ms.t_cap, ms.rmax, ms.rec_words, ms.pw_max, dv.ptr(ms.recs), dv.ptr(ms.prog_off), dv.ptr(ms.prog),
+              dv.ptr(out), dv.stream_ptr())
+    return out

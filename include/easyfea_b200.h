@@ -208,6 +208,26 @@ int efb_assemble_elastic_smem(int dim, int nPe, int nPg, int S, int cap_e, int m
  * when there is no instantiation */
 int efb_assemble_elastic_group(int dim, int nPe, int nPg);
 
+/* ---- A3 fused, HEXA8 with 8 Gauss points on the FP64 tensor-core instruction (DMMA.8x8x4) ------------------------
+ * Same contract as efb_assemble_elastic (`Assembly` of `LinearizedElasticity(group, C)`, _simu.py:1104-1144 with
+ * Bilinear.py:62-79, homogeneous C, K_e never materialised, every CSR slot summed in ascending element order by one lane, no
+ * atomics) for clusters of 16 nodes: the element contraction T_e = G^T G runs as m8n8k4 FP64 MMAs, the T rows of the owned
+ * nodes are staged in shared memory and a per-cluster gather program (built once by assembly.MmaSchedule) sums them per CSR
+ * block.  recs (n_clusters, rec_words) int32 = one record per cluster, streamed into shared memory by bulk copies:
+ *   conn (cap4, 8) coordinate rows of the cluster's elements, -1 = empty, cap4 a multiple of 4 |
+ *   rowslot (cap4, 8) int16 = staging slot | (node-in-cluster & 7) << 8 of (element, local node), -1 = node not owned |
+ *   nodes (16, 2) int64 = {dim*dim*adjptr[n] (-1: padding), deg} |
+ *   hdr (1 + rmax) = rounds R of the cluster, then per round (word offset inside the cluster program << 8) | trips;
+ * rec_words a multiple of 4; t_cap = max tasks of a cluster (<= 256); prog_off (n_clusters + 1) int64 = offsets in int32 words
+ * of the clusters' programs inside `prog`, pw_max = the longest program; a round of c trips is [dest of the 32 lanes =
+ * node-in-cluster << 16 | slot, -1 = none][32 x cpad uint16 sources = staging offset in doubles of the contribution, 0xffff =
+ * none], cpad = c rounded up to 1, 2, 4 or a multiple of 8.  Returns 3 when the configuration is outside the kernel. */
+int efb_assemble_elastic_mma(const efb_group* g, const double* C_host, const double* w_pg_host, double scale, int n_clusters,
+                             int cap4, int t_cap, int rmax, int rec_words, int pw_max, const int32_t* recs,
+                             const int64_t* prog_off, const int32_t* prog, double* out, void* stream);
+/* dynamic shared memory (bytes) of the CTA of efb_assemble_elastic_mma for this configuration */
+int efb_assemble_elastic_mma_smem(int t_cap, int rec_words, int pw_max);
+
 /* ---- consumer: Jacobi-PCG building blocks (north star; the reference dispatches in Solvers.py:225-394) ---- */
 /* All scalars stay on the device; dot products are fixed-order two-stage reductions: producers write
  * efb_pcg_partials_size() doubles of partials, efb_pcg_reduce folds them (deterministic). */

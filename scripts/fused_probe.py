@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--elem", default="HEXA8")
     ap.add_argument("--no-two", action="store_true")
+    ap.add_argument("--no-mma", action="store_true")
     args = ap.parse_args()
     et = args.elem
     coords, connect = meshgen.structured_mesh(et, args.n, jitter=0.2, seed=0)
@@ -72,6 +73,20 @@ def main():
             del sched
         except Exception as exc:
             out[f"fused_S{S}"] = {"error": repr(exc)[:300]}
+    if et == "HEXA8" and not args.no_mma:
+        import time
+
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ms_ = assembly.MmaSchedule(pat.graph)
+        torch.cuda.synchronize()
+        t_sched = time.perf_counter() - t0
+        t = timed(lambda: assembly.assemble_elastic_mma(ms_, C, out=data), args.reps)
+        err = float((data - ref).norm() / ref.norm()) if ref is not None else None
+        out["mma"] = {"ms": t, "t_cap": ms_.t_cap, "cap4": ms_.cap4, "rmax": ms_.rmax, "redundancy": ms_.redundancy(), "smem": ms_.smem_bytes(), "rec_words": ms_.rec_words, "pw_max": ms_.pw_max,
+                      "n_clusters": ms_.n_clusters, "rounds_per_cluster": ms_.n_rounds / max(ms_.n_clusters, 1),
+                      "row_tiles_per_element": ms_.n_row_tiles / g.Ne, "prog_bytes": ms_.prog.numel() * 4,
+                      "schedule_s": t_sched, "rel_err_vs_two_kernel": err}
     print(json.dumps(out))
 
 

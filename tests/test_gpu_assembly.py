@@ -190,6 +190,41 @@ def test_fused_assembly_vs_two_kernel_path(efb, elemType, n, general_C):
     assert torch.equal(efb.asm.assemble_elastic_fused(sched, C, "rigi", 1.3), fused)
 
 
+@pytest.mark.parametrize("n", [(7, 6, 5), (12, 9, 10), (3, 2, 2)])
+@pytest.mark.parametrize("general_C", [False, True])
+def test_mma_assembly_vs_oracle_and_two_kernel_path(efb, n, general_C):
+    """`efb_assemble_elastic_mma` (HEXA8, 8 Gauss points, FP64 MMA): values <= 1e-12 against the oracle's K_e + np.bincount and
+    against the two-kernel device path, bit-identical run to run, owned-row prefix respected"""
+    import torch
+
+    from easyfea_b200 import elements as el
+
+    rng = np.random.default_rng(5)
+    coords, connect = make_mesh("HEXA8", n)
+    g = efb.mesh.ElemGroup("HEXA8", connect, coords)
+    Nn = coords.shape[0]
+    C = orc.IsoMaterial(3, 210000.0, 0.3).C
+    if general_C:
+        C = C * rng.uniform(0.5, 2.0, C.shape) + rng.uniform(1e3, 1e4, C.shape)
+    pat = efb.asm.Assembler().pattern(3, True, Nn * 3, (g,))
+    two = pat.replay([efb.op.elastic_Ke_dev(g, C, "rigi", 1.3)])
+    ms = efb.asm.MmaSchedule(pat.graph)
+    assert ms.fits()
+    got = efb.asm.assemble_elastic_mma(ms, C, "rigi", 1.3)
+    assert got.shape == two.shape
+    assert rel_err(got.cpu().numpy(), two.cpu().numpy()) < 1e-12
+    tab = el.gauss_table("HEXA8", "rigi")
+    Ke = 1.3 * orc.linearized_elasticity(orc.geometry(coords[connect], tab.dN_pg, tab.weights), C)
+    inv, indices, indptr, nnz = orc.csr_map([connect], 3, Nn * 3, True)
+    assert rel_err(got.cpu().numpy(), orc.assemble_replay([Ke], inv, nnz)) < 1e-12
+    assert torch.equal(efb.asm.assemble_elastic_mma(ms, C, "rigi", 1.3), got)
+    n_own = Nn // 3
+    out = torch.full_like(got, -7.0)
+    efb.asm.assemble_elastic_mma(efb.asm.MmaSchedule(pat.graph, n_nodes=n_own), C, "rigi", 1.3, out=out)
+    nz = int(pat.indptr[n_own * 3].item())
+    assert torch.equal(out[:nz], got[:nz]) and bool((out[nz:] == -7.0).all())
+
+
 def test_fused_assembly_owned_rows_prefix(efb):
     """sharded runs assemble the rows of the owned nodes only: the fused kernel leaves the other rows untouched"""
     import torch
