@@ -296,6 +296,7 @@ def run_reference(args):
 
 # -----------------------------------------------------------------------------------------------------------------
 FP64_PEAK_TFLOPS = 36.9  # measured on this pool with scripts/micro/dfma_peak.cu (pure DFMA, 32 warps/SM); nominal 37.2
+FP64_DMMA_PEAK_TFLOPS = 37.1  # measured on this pool with scripts/micro/dmma_peak.cu (mma.sync m8n8k4 f64: same pipe, same rate as DFMA)
 FLOPS_PER_GP = 4695      # HEXA8 structure-aware count of the general contraction, SURVEY.md section 8d
 FLOPS_PER_GP_EXECUTED = 2150  # what k_elastic_w<3,8,sym,ortho> issues: 8 lanes x (15 DMUL + 105 DFMA) + geometry (~380)
 
@@ -341,12 +342,21 @@ def run_ours(args):
     sched = assembly.FusedSchedule(pat.graph, n_nodes=part.n_owned)
     torch.cuda.synchronize()
     t_sched = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    msched = assembly.MmaSchedule(pat.graph, n_nodes=part.n_owned, base=sched if sched.S == 16 else None)
+    torch.cuda.synchronize()
+    t_msched = time.perf_counter() - t0
+    if not msched.fits():
+        msched = None
     nnz_owned = int(pat.indptr[part.n_owned * 3].item())
     n_entries = Ne * ndof * ndof
     data = dv.empty((pat.nnz,))
 
     def step_fused():
         assembly.assemble_elastic_fused(sched, C, "rigi", 1.0, out=data)
+
+    def step_mma():
+        assembly.assemble_elastic_mma(msched, C, "rigi", 1.0, out=data)
 
     Ke_box = {}
 
@@ -365,20 +375,27 @@ def run_ours(args):
         torch.cuda.synchronize()
         return ev[0].elapsed_time(ev[k]), [ev[i].elapsed_time(ev[i + 1]) for i in range(k)]
 
-    # which path is the step: --path fused | two | auto (auto: the faster of the two on this mesh, decided in the warm-up)
+    # which path is the step: --path mma | fused | two | auto (auto: the fastest on this mesh, decided in the warm-up)
     path = args.path
+    paths = {"fused": step_fused, "two": step_two}
+    if msched is not None:
+        paths["mma"] = step_mma
+    elif path == "mma":
+        raise SystemExit("--path mma: the mesh does not fit efb_assemble_elastic_mma")
     for _ in range(2):
-        step_fused()
-        step_two()
+        for fn in paths.values():
+            fn()
     torch.cuda.synchronize()
-    probe = {"fused": time_steps(step_fused, 3)[0] / 3, "two": time_steps(step_two, 3)[0] / 3}
+    probe = {name: time_steps(fn, 3)[0] / 3 for name, fn in paths.items()}
     if path == "auto":
+        names = sorted(paths)
         path = min(probe, key=probe.get)
         if world > 1:  # every rank takes the same decision: rank 0's
-            t = torch.tensor([0 if path == "fused" else 1], device=dev)
+            t = torch.tensor([names.index(path)], device=dev)
             dist.broadcast(t, 0)
-            path = "fused" if int(t.item()) == 0 else "two"
-    step, other = (step_fused, step_two) if path == "fused" else (step_two, step_fused)
+            path = names[int(t.item())]
+    step = paths[path]
+    single = path in ("fused", "mma")  # one kernel per step
 
     # the clock sampler starts before the warm-up (nvidia-smi needs ~1 s to come up on an 8-GPU box) and keeps sampling
     # through warm-up + timed steps: the same kernels, the same load
@@ -396,9 +413,9 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        if path == "fused":
-            total_ms, per = time_steps(step_fused, K)
-            t_fused = float(np.mean(per))
+        if single:
+            total_ms, per = time_steps(step, K)
+            t_single = float(np.mean(per))
         else:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K + 1)]
             ev[0].record()
@@ -417,11 +434,11 @@ def run_ours(args):
     # units processed = elements of the ranks' OWN chunks (ghost elements are integrated too, but not counted twice)
     value = float(world * n_own * nPg) * K / (total_ms * 1e-3)
 
-    # ---- the other path, timed beside the headline (fewer steps) ----
+    # ---- the other paths, timed beside the headline (fewer steps) ----
     k_other = max(2, min(K, 5))
-    other()
+    step_two()
     torch.cuda.synchronize()
-    if path == "fused":
+    if single:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * k_other + 1)]
         ev[0].record()
         for k in range(k_other):
@@ -432,12 +449,15 @@ def run_ours(args):
         torch.cuda.synchronize()
         Kt = k_other
     else:
-        t_fused = time_steps(step_fused, k_other)[0] / k_other
         Kt = K
+    t_fused = t_single if path == "fused" else time_steps(step_fused, k_other)[0] / k_other
+    t_mma = None
+    if msched is not None:
+        t_mma = t_single if path == "mma" else time_steps(step_mma, k_other)[0] / k_other
     t_ke = float(np.mean([ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(Kt)]))
     t_rp = float(np.mean([ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(Kt)]))
-    Ke_box.clear()  # 36.9 GB at 8 M elements: the fused path never allocates it
-    step_fused()    # `data` = the fused assembly for the legs below
+    Ke_box.clear()  # 36.9 GB at 8 M elements: the fused paths never allocate it
+    (step_mma if path == "mma" else step_fused)()    # `data` = the fused assembly for the legs below
     torch.cuda.synchronize()
 
     # ---- roofline of the dominant kernel (per launch, this rank) ----
@@ -451,7 +471,26 @@ def run_ours(args):
     # executed FP64 work of the fused kernel per Gauss point of an OWNED element: 64 node-pair blocks x 9 FMA + geometry of
     # `redundancy` elements (~330 flop each: F, det, inverse, gradients)
     fused_flops_gp = 2 * 64 * 9 + sched.redundancy() * 330
-    if path == "fused":
+    # MMA form: algorithmic FP64 work per element = 8 Gauss points x (64 node-pair blocks x 9 FMA + 204 FMA of geometry: F, det,
+    # inverse, gradients); executed = the DMMA instructions the schedule issues (6 per needed row tile, 12 per pass of 4
+    # elements, 512 flop each) + ~200 scalar FP64 instructions per lane and pass
+    mma_flops_alg = n_own * nPg * (64 * 9 + 204) * 2.0
+    mma_flops_exec = None
+    bytes_mma = None
+    if msched is not None:
+        n_pass = msched.n_clusters * (msched.cap4 // 4)
+        mma_flops_exec = (msched.n_row_tiles * 6 + n_pass * 12) * 512.0 + n_pass * 200 * 64.0
+        bytes_mma = nnz_owned * 8 + msched.recs.numel() * 4 + msched.prog.numel() * 4 + Nn * 24
+    if path == "mma":
+        roof = {"kernel": "k_assemble_hexa8_mma<ortho>", "bound": "tensor", "achieved": mma_flops_alg / (t_mma * 1e-3) / 1e12,
+                "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "traffic": ncu_traffic("k_assemble_hexa8_mma<1>", part.n_owned),
+                "executed_TFLOPs": mma_flops_exec / (t_mma * 1e-3) / 1e12,
+                "hbm_GBps": bytes_mma / (t_mma * 1e-3) / 1e9, "hbm_frac": bytes_mma / (t_mma * 1e-3) / 1e9 / peak,
+                "note": "fused integration + assembly on the FP64 MMA instruction (DMMA.8x8x4, FP64 pipe): peak = the DMMA rate measured "
+                        "on this pool's B200 (scripts/micro/dmma_peak.cu: 37.1 TFLOP/s, the same as DFMA); achieved = ALGORITHMIC flops "
+                        "(12 480 per element); the node-owned form executes ~2.4x that (elements are integrated once per cluster that "
+                        "touches them) and is bound by latency at 16 warps per SM (DESIGN.md section 4.7)"}
+    elif path == "fused":
         roof = {"kernel": "k_assemble_elastic<3,8,8,ortho>", "bound": "hbm", "achieved": bytes_fused / (t_fused * 1e-3) / 1e9, "peak": peak,
                 "unit": "GB/s", "traffic": ncu_traffic("k_assemble_elastic<3,8,8,1>", part.n_owned),
                 "note": "fused integration + assembly: DRAM traffic is the CSR data once; the kernel is bound by instruction issue / "
@@ -463,7 +502,7 @@ def run_ours(args):
         roof = {"kernel": "k_elastic_w<3,8,sym,ortho>", "bound": "hbm", "achieved": bytes_ke / (t_ke * 1e-3) / 1e9, "peak": peak,
                 "unit": "GB/s", "traffic": ncu_traffic("k_elastic_w<3,8,1,1>", Ne)}
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof["peak_source"] = peak_src
+    roof["peak_source"] = peak_src if roof["bound"] == "hbm" else "measured FP64 DMMA rate (scripts/micro/dmma_peak.cu, profiles/r2_dmma_peak.log)"
 
     cfg = workload_config(n, world)
     line = {"metric": METRIC, "value": value, "unit": "GP/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -489,8 +528,14 @@ def run_ours(args):
                         "replay_ms": t_rp, "replay_GBps": bytes_replay / (t_rp * 1e-3) / 1e9,
                         "replay_hbm_frac": bytes_replay / (t_rp * 1e-3) / 1e9 / peak,
                         "replay_GBps_survey_formula": (n_entries * 12 + nnz_owned * 8) / (t_rp * 1e-3) / 1e9,
-                        "pattern_build_s": t_pattern, "fused_schedule_build_s": t_sched},
-            "gpu_launches": (1 if path == "fused" else 2) * K, "clocks": clk.summary()}
+                        "mma_kernel": "k_assemble_hexa8_mma<ortho> (T_e = G^T G as FP64 m8n8k4 MMAs, staged T rows + gather programs, "
+                                      "warp-specialised persistent CTA)",
+                        "mma_ms": t_mma, "mma_GPps": None if t_mma is None else n_own * nPg / (t_mma * 1e-3),
+                        "mma_TFLOPs_algorithmic": None if t_mma is None else mma_flops_alg / (t_mma * 1e-3) / 1e12,
+                        "mma_TFLOPs_executed": None if t_mma is None else mma_flops_exec / (t_mma * 1e-3) / 1e12,
+                        "mma_bytes_per_launch": bytes_mma, "fp64_dmma_peak_tflops": FP64_DMMA_PEAK_TFLOPS,
+                        "pattern_build_s": t_pattern, "fused_schedule_build_s": t_sched, "mma_schedule_build_s": t_msched},
+            "gpu_launches": (1 if single else 2) * K, "clocks": clk.summary()}
 
     extras = {}
     if not args.no_solve:
@@ -500,10 +545,10 @@ def run_ours(args):
             extras["pcg"] = {"error": repr(exc)[:300]}
     # ---- e2e through the host-buffer boundary (pinned in, pinned out), every rank at once ----
     try:
-        line["e2e"] = e2e_leg(args, g, part, C, pat, sched, data, world, dist, path)
+        line["e2e"] = e2e_leg(args, g, part, C, pat, sched, data, world, dist, path, msched)
     except Exception as exc:
         line["e2e"] = {"error": repr(exc)[:300]}
-    del data, sched, pat, A
+    del data, sched, msched, pat, A
     torch.cuda.empty_cache()
     if not args.no_pf:
         for cfg_id in ([3, 4] if args.pf_config == 0 else [args.pf_config]):
@@ -751,7 +796,7 @@ def transient_leg(args, rank, world, dist):
     return out
 
 
-def e2e_leg(args, g, part, C, pat, sched, data, world, dist, path):
+def e2e_leg(args, g, part, C, pat, sched, data, world, dist, path, msched=None):
     """Same step through host buffers, on EVERY rank at once: pinned (connect int32, coords) -> device, integration + assembly,
     owned CSR data -> pinned host; wall time between barriers, max over ranks."""
     import torch
@@ -766,13 +811,15 @@ def e2e_leg(args, g, part, C, pat, sched, data, world, dist, path):
     nz = int(pat.indptr[part.n_owned * 3].item())
     h_out = torch.empty(nz, dtype=torch.float64).pin_memory()
     Ke = None
-    if path != "fused":
+    if path == "two":
         Ke = dv.empty((g.Ne, 24, 24))
 
     def one():
         dg.connect.copy_(h_conn, non_blocking=True)  # the element kernel reads these buffers
         dg.coord.copy_(h_coord, non_blocking=True)
-        if path == "fused":  # the schedule holds its own copy of the connectivity (built once, like the CSR pattern)
+        if path == "mma":  # the schedules hold their own copy of the connectivity (built once, like the CSR pattern)
+            assembly.assemble_elastic_mma(msched, C, "rigi", 1.0, out=data)
+        elif path == "fused":
             assembly.assemble_elastic_fused(sched, C, "rigi", 1.0, out=data)
         else:
             operators.elastic_Ke_dev(g, C, "rigi", 1.0, out=Ke)
@@ -837,6 +884,7 @@ def parity_leg(args):
     Ke = operators.elastic_Ke_dev(g, C)
     two = pat.replay([Ke]).cpu().numpy()
     fused = assembly.assemble_elastic_fused(assembly.FusedSchedule(pat.graph), C).cpu().numpy()
+    mma = assembly.assemble_elastic_mma(assembly.MmaSchedule(pat.graph), C).cpu().numpy()
     replay_ref = pat.replay([torch.from_numpy(np.ascontiguousarray(Ke_ref))]).cpu().numpy()  # the CPU path's own K_e, replayed on the device
     rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))  # noqa: E731
     return {"against": against, "mesh": f"HEXA8 {n}^3 = {n**3} elements, {Nn} nodes", "cpu_seconds": t_cpu,
@@ -844,6 +892,7 @@ def parity_leg(args):
             "indices_equal": bool(np.array_equal(pat.indices.cpu().numpy(), Kref.indices)),
             "Ke_rel_err": rel(Ke.cpu().numpy(), np.asarray(Ke_ref)),
             "data_rel_err_two_kernel": rel(two, Kref.data), "data_rel_err_fused": rel(fused, Kref.data),
+            "data_rel_err_mma": rel(mma, Kref.data),
             "replay_of_cpu_Ke_bit_identical": bool(np.array_equal(replay_ref, Kref.data)), "tolerance": 1e-12}
 
 
@@ -953,8 +1002,9 @@ def main():
                     help="phase-field extras: 0 = both (default), 3 = config 3 only (TRI3, Miehe), 4 = config 4 only (TETRA4, He)")
     ap.add_argument("--pf-n", type=int, default=0, help="config 3 cells per side (default 1000 -> 2.0 M TRI3)")
     ap.add_argument("--pf-n4", type=int, default=0, help="config 4 cells per side (default 119 -> 10.1 M TETRA4)")
-    ap.add_argument("--path", default="auto", choices=["auto", "fused", "two"],
-                    help="the step: fused integration+assembly kernel, the two-kernel path (K_e, then replay), or the faster of the two")
+    ap.add_argument("--path", default="auto", choices=["auto", "mma", "fused", "two"],
+                    help="the step: fused integration+assembly on the FP64 MMA instruction, the DFMA fused kernel, the two-kernel path "
+                         "(K_e, then replay), or the fastest of them")
     ap.add_argument("--cpu-kind", default="", choices=["", "reference", "port"], help="CPU arm: live reference or NumPy port (default: reference if importable)")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity / e2e_solve / config 1 legs")
     ap.add_argument("--parity-n", type=int, default=16, help="cells per side of the common-size parity mesh")

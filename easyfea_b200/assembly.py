@@ -519,7 +519,16 @@ class MmaSchedule:
         recs[rcl, o_hdr + 1 + rin] = ((roff_in << 8) | c_round).to(torch.int32)
         self.recs = recs.contiguous()
         self.pw_max = int((prog_off[1:] - prog_off[:-1]).max().item()) if ncl else 4
-        prog = torch.full((total + 4,), -1, dtype=torch.int32, device=dev)     # dest -1 = no block, sources 0xffff = none
+        prog = torch.full((total + 4,), -1, dtype=torch.int32, device=dev)     # dest -1 = no block
+        # sources of lanes without a contribution: the zero block behind the staged tasks
+        zsrc = self.t_cap * self.TS
+        zw = torch.tensor(zsrc | (zsrc << 16), dtype=torch.int64, device=dev).to(torch.int32)
+        smask = torch.zeros(total + 4, dtype=torch.bool, device=dev)
+        sidx = (cs[:-1] + 32).repeat_interleave(16 * cpad) + (ar(int((16 * cpad).sum().item())) - torch.repeat_interleave(
+            torch.cumsum(16 * cpad, 0) - 16 * cpad, 16 * cpad))
+        smask[sidx] = True
+        prog[smask] = zw
+        del smask, sidx
         bround = rptr[bcl_s] + rank // 32                                      # global round of every sorted block
         blane = rank % 32
         prog[cs[bround] + blane] = ((iloc[border] << 16) | slot[border]).to(torch.int32)

@@ -49,11 +49,12 @@ struct MmaView {
 
 constexpr int kMmaS = 16;                   // nodes per cluster
 constexpr int kMmaTS = 72;                  // doubles per staged task: [k*3+l][b]
+constexpr int kMmaZero = 72;                // zero tail of a staging buffer
 constexpr int kMmaGE = 192;                 // doubles of the gradient table of one element: [p][l][b ^ swizzle(p)]
 constexpr int kMmaWarpBuf = 2 * kMmaGE;     // per-warp scratch: two tables (element e + 1 is written while e is read)
-constexpr int kMmaP2 = 12;                  // integration warps (three per SM sub-partition)
-constexpr int kMmaP3 = 4;                   // gather warps
-constexpr int kMmaStages = 3;               // ring slots
+constexpr int kMmaP2 = 12;                  // integration warps (16 warps per CTA: 128 registers per thread)
+constexpr int kMmaP3 = 3;                   // gather warps
+constexpr int kMmaStages = 4;               // ring slots
 constexpr int kMmaThreads = (kMmaP2 + kMmaP3 + 1) * 32;
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
@@ -77,7 +78,7 @@ __host__ __device__ inline size_t mma_slot_words(int rec_words, int pw_max) { re
 template <bool ORTHO>
 __global__ void __launch_bounds__(kMmaThreads, 1) k_assemble_hexa8_mma(GroupView g, MmaView f, FusedTerms terms) {
     extern __shared__ __align__(16) double smem[];
-    const int stage_doubles = f.t_cap * kMmaTS;
+    const int stage_doubles = f.t_cap * kMmaTS + kMmaZero;  // + a block of zeros: the source of lanes without a contribution
     double* stage0 = smem;                                            // [2][t_cap * 72]
     double* gbuf0 = stage0 + 2 * (size_t)stage_doubles;               // [P2 warps][kMmaWarpBuf]
     int* ring0 = reinterpret_cast<int*>(gbuf0 + kMmaP2 * kMmaWarpBuf); // [stages][rec_words + pw_max]
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_assemble_hexa8_mma(GroupView
     unsigned long long* sempty = bars + 2 * kMmaStages + 2; // [2] the gather warps have consumed the buffer
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 2 * kMmaZero) stage0[(size_t)(threadIdx.x / kMmaZero) * stage_doubles + f.t_cap * kMmaTS + threadIdx.x % kMmaZero] = 0.0;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kMmaStages; ++s) {
             mbar_init(&full[s], 1);
@@ -142,19 +144,11 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_assemble_hexa8_mma(GroupView
                 double acc[9];
                 EFB_UNROLL
                 for (int q = 0; q < 9; ++q) acc[q] = 0.0;
-#pragma unroll 1
-                for (int it0 = 0; it0 < c; it0 += 4) {
-                    unsigned sv[4];
+#pragma unroll 2
+                for (int it = 0; it < c; ++it) {  // lanes with fewer contributions read the zero block
+                    const double* q0 = stage + sp[it];
                     EFB_UNROLL
-                    for (int u = 0; u < 4; ++u) sv[u] = it0 + u < c ? sp[it0 + u] : 0xffffu;
-                    EFB_UNROLL
-                    for (int u = 0; u < 4; ++u) {
-                        if (sv[u] != 0xffffu) {
-                            const double* q0 = stage + sv[u];
-                            EFB_UNROLL
-                            for (int q = 0; q < 9; ++q) acc[q] += q0[q * 8];
-                        }
-                    }
+                    for (int q = 0; q < 9; ++q) acc[q] += q0[q * 8];
                 }
                 if (dest >= 0) {
                     const int i = dest >> 16, sl = dest & 0xffff;
@@ -217,9 +211,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_assemble_hexa8_mma(GroupView
             x[2] = ldg_f64(c0 + 2);
             x[3] = ldg_f64(c1 + 2);
         };
-        // one pass: 4 elements, coordinates x (B fragments of the Jacobian GEMM), staging slots rsp (4 x 8 int16)
-        auto do_pass = [&](const double (&x)[4], const int* rsp, double* stage) {
-            double H[9];  // lane (p = lq, e = lr): sqrt(w |det F|) F^-1 of (element e, Gauss point p)
+                // lane (p = lq, e = lr): H = sqrt(w |det F|) F^-1 of (element e, Gauss point p) of the pass with coordinates x
+        auto pass_jacobians = [&](const double (&x)[4], double (&H)[9]) {
             {
                 const double z0 = cpar ? 0.0 : x[2], z1 = cpar ? 0.0 : x[3];
                 double F[9];
@@ -239,6 +232,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_assemble_hexa8_mma(GroupView
                 EFB_UNROLL
                 for (int i = 0; i < 9; ++i) H[i] *= sw;
             }
+        };
+        // gradient tables, row tiles and staging of the 4 elements of a pass; rsp = their staging slots (4 x 8 int16)
+        auto pass_tiles = [&](const double (&H)[9], const int* rsp, double* stage) {
             // gradient table of element e: the four lanes of Gauss point p fetch F^-1 of (e, p) from lane (p, e) and write two
             // columns each
             auto write_table = [&](int e, double* gt) {
@@ -280,14 +276,19 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_assemble_hexa8_mma(GroupView
                         double* d0 = stage + (on ? (v & 0xff) : 0) * kMmaTS + st_row;
                         double* d1 = d0 + ((2 * lr + 1) ^ xs);
                         d0 += (2 * lr) ^ xs;
+                        double c[3][2];
                         EFB_UNROLL
                         for (int l = 0; l < 3; ++l) {
-                            double c0 = 0.0, c1 = 0.0;
-                            dmma(c0, c1, gA0, gB[0][l]);
-                            dmma(c0, c1, gA1, gB[1][l]);
-                            if (on) {
-                                d0[l * 8] = c0;
-                                d1[l * 8] = c1;
+                            c[l][0] = c[l][1] = 0.0;
+                            dmma(c[l][0], c[l][1], gA0, gB[0][l]);
+                        }
+                        EFB_UNROLL
+                        for (int l = 0; l < 3; ++l) dmma(c[l][0], c[l][1], gA1, gB[1][l]);
+                        if (on) {
+                            EFB_UNROLL
+                            for (int l = 0; l < 3; ++l) {
+                                d0[l * 8] = c[l][0];
+                                d1[l * 8] = c[l][1];
                             }
                         }
                     }
@@ -296,10 +297,16 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_assemble_hexa8_mma(GroupView
             }
         };
 
-        // this warp's passes: global pass sequence gp = warp, warp + P2, ... ; (kn, in) = the next pass, xn its coordinates
-        long long gp = warp;
-        long long kn = gp / npass;
-        int in = (int)(gp - kn * npass);
+        // this warp's passes: pass i of cluster k belongs to warp (k (npass + 1) + i) mod P2 — the assignment rotates from cluster
+        // to cluster, so that light passes (boundary elements, the last partly filled pass) and heavy ones visit every warp;
+        // (kn, in) = the next pass of this warp, xn its coordinates
+        auto first_in = [&](long long k) { return (int)((warp + kMmaP2 - (int)((k * (npass + 1)) % kMmaP2)) % kMmaP2); };
+        long long kn = 0;
+        int in = first_in(0);
+        while (kn < nk && in >= npass) {
+            ++kn;
+            in = first_in(kn);
+        }
         double xn[4] = {0.0, 0.0, 0.0, 0.0};
         bool have = false;  // xn holds the coordinates of pass (kn, in)
 #pragma unroll 1
@@ -311,24 +318,22 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_assemble_hexa8_mma(GroupView
             mbar_wait(&sempty[b], (unsigned)(((k >> 1) & 1) ^ 1));
 #pragma unroll 1
             while (kn == k) {
-                double x[4];
-                if (have) {
-                    EFB_UNROLL
-                    for (int q = 0; q < 4; ++q) x[q] = xn[q];
-                } else {
-                    load_coords(slot, in, x);
-                }
+                if (!have) load_coords(slot, in, xn);
+                double H[9];
+                pass_jacobians(xn, H);
                 const int i = in;
-                gp += kMmaP2;
-                kn = gp / npass;
-                in = (int)(gp - kn * npass);
+                in += kMmaP2;
+                while (kn < nk && in >= npass) {
+                    ++kn;
+                    in = first_in(kn);
+                }
                 have = false;
                 if (kn < nk && kn - k < kMmaStages) {  // the next pass's coordinates travel while this pass is computed
                     if (kn != k) mbar_wait(&full[kn % kMmaStages], (unsigned)((kn / kMmaStages) & 1));
                     load_coords(ring0 + (size_t)(kn % kMmaStages) * slot_words, in, xn);
                     have = true;
                 }
-                do_pass(x, slot + o_rs + i * 16, stage);
+                pass_tiles(H, slot + o_rs + i * 16, stage);
             }
             __syncwarp();
             if (lane == 0) {
@@ -340,7 +345,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_assemble_hexa8_mma(GroupView
 }
 
 static size_t mma_smem_bytes(int t_cap, int rec_words, int pw_max) {
-    return sizeof(double) * (2 * (size_t)t_cap * kMmaTS + (size_t)kMmaP2 * kMmaWarpBuf) +
+    return sizeof(double) * (2 * ((size_t)t_cap * kMmaTS + kMmaZero) + (size_t)kMmaP2 * kMmaWarpBuf) +
            sizeof(int) * kMmaStages * mma_slot_words(rec_words, pw_max) + sizeof(unsigned long long) * (2 * kMmaStages + 4);
 }
 

@@ -220,8 +220,8 @@ int efb_assemble_elastic_group(int dim, int nPe, int nPg);
  *   hdr (1 + rmax) = rounds R of the cluster, then per round (word offset inside the cluster program << 8) | trips;
  * rec_words a multiple of 4; t_cap = max tasks of a cluster (<= 256); prog_off (n_clusters + 1) int64 = offsets in int32 words
  * of the clusters' programs inside `prog`, pw_max = the longest program; a round of c trips is [dest of the 32 lanes =
- * node-in-cluster << 16 | slot, -1 = none][32 x cpad uint16 sources = staging offset in doubles of the contribution, 0xffff =
- * none], cpad = c rounded up to 1, 2, 4 or a multiple of 8.  Returns 3 when the configuration is outside the kernel. */
+ * node-in-cluster << 16 | slot, -1 = none][32 x cpad uint16 sources = staging offset in doubles of the contribution,
+ * t_cap*72 (a block of zeros) for lanes without one], cpad = c rounded up to 1, 2, 4 or a multiple of 8.  Returns 3 when the configuration is outside the kernel. */
 int efb_assemble_elastic_mma(const efb_group* g, const double* C_host, const double* w_pg_host, double scale, int n_clusters,
                              int cap4, int t_cap, int rmax, int rec_words, int pw_max, const int32_t* recs,
                              const int64_t* prog_off, const int32_t* prog, double* out, void* stream);
