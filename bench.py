@@ -688,6 +688,7 @@ def phase_field_leg(args, rank, world, dist, cfg_id):
     simu = staggered.PhaseFieldStaggered(sysm, pfm, pcg_tol=1e-8, pcg_maxiter=args.pf_maxiter)
     simu.pcg_fused = False if args.pf_unfused else "auto"
     simu.pcg_single_reduction = {"auto": "auto", "on": True, "off": False}[args.pf_single_reduction]
+    simu.pcg_precond_degree = "auto" if args.pf_degree == "auto" else int(args.pf_degree)
     ix, iy = np.rint(lattice[nodes, 0] / L * n).astype(np.int64), np.rint(lattice[nodes, 1] / L * n).astype(np.int64)
     loc = np.arange(nodes.size)
     comps = list(range(dim))
@@ -716,6 +717,7 @@ def phase_field_leg(args, rank, world, dist, cfg_id):
             "pcg_iters_elastic": simu.info["elastic"]["iterations"],
             "pcg_converged": bool(simu.info["damage"]["converged"] and simu.info["elastic"]["converged"]),
             "pcg_fused": bool(simu.info["elastic"].get("fused", False)), "pcg_single_reduction": bool(simu.info["elastic"].get("single_reduction", False)),
+            "pcg_precond_degree": {"damage": simu.info["damage"].get("precond_degree", 1), "elastic": simu.info["elastic"].get("precond_degree", 1)},
             "last_damage_increment": float(conv.item()), "max_damage": float(dmax.item())}
 
 
@@ -1016,6 +1018,7 @@ def main():
     ap.add_argument("--tr-steps", type=int, default=3)
     ap.add_argument("--pf-single-reduction", default="auto", choices=["auto", "on", "off"],
                     help="phase-field solves with the Chronopoulos-Gear PCG form (auto: small shards)")
+    ap.add_argument("--pf-degree", default="auto", help="phase-field solves: Chebyshev-Jacobi polynomial degree m (1 = plain Jacobi, auto = by shard size)")
     ap.add_argument("--pf-unfused", action="store_true", help="phase-field solves with the NCCL/kernel-per-operation PCG loop")
     args = ap.parse_args()
     quiet_stdout()

@@ -46,7 +46,7 @@ class EfbPcgPeer(ctypes.Structure):
 
     _fields_ = [("world", c_i32), ("rank", c_i32), ("n_send", c_i32), ("n_recv", c_i32), ("send_rank", c_i32 * MAX_RANKS),
                 ("recv_rank", c_i32 * MAX_RANKS), ("send_ptr", c_i64 * (MAX_RANKS + 1)), ("send_dst", c_i64 * MAX_RANKS),
-                ("base", c_vp * MAX_RANKS), ("pbuf_off", (c_i64 * 2) * MAX_RANKS), ("send_idx", c_vp), ("ar_seq", ctypes.c_uint64),
+                ("base", c_vp * MAX_RANKS), ("pbuf_off", (c_i64 * 4) * MAX_RANKS), ("send_idx", c_vp), ("ar_seq", ctypes.c_uint64),
                 ("halo_seq", ctypes.c_uint64), ("push_id", c_vp), ("push_ptr", c_vp), ("push_nbr", c_vp), ("push_pos", c_vp)]
 
 
@@ -108,6 +108,9 @@ SIGNATURES = {
     "efb_pcg_ctrl_bytes": [],
     "efb_pcg_ctrl_layout": [_I32P],
     "efb_pcg_iterate": [ctypes.POINTER(EfbPcgSystem), ctypes.POINTER(EfbPcgPeer), ctypes.c_int, c_i64, c_vp],
+    "efb_pcg_iterate_cheb": [ctypes.POINTER(EfbPcgSystem), ctypes.POINTER(EfbPcgPeer), ctypes.c_int, c_i64, ctypes.c_int, c_f64, c_f64,
+                             c_vp, c_vp],
+    "efb_pcg_cheb_update": [c_i64, c_vp, c_vp, c_vp, c_f64, c_f64, c_vp, c_vp, c_vp],
     "efb_pcg_iterate_cg2": [ctypes.POINTER(EfbPcgSystem), ctypes.POINTER(EfbPcgPeer), ctypes.c_int, c_i64, c_vp],
     "efb_pcg_solve_persistent": [ctypes.POINTER(EfbPcgSystem), ctypes.POINTER(EfbPcgPeer), c_i64, c_i64, c_f64, c_vp],
     "efb_peer_alloc": [c_i64, _PP],

@@ -28,11 +28,24 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return s;
 }
 
+// what happens to a finished row of the product (called by the lane that holds the row sum; masked rows arrive as 0):
+// the default stores it and returns the row's part of x_row . y
+struct EpiStore {
+    const double* __restrict__ x;
+    long long x_row_offset;
+    double* __restrict__ y;
+    bool want_dot;
+    __device__ __forceinline__ double operator()(long long r, double v) const {
+        y[r] = v;
+        return want_dot ? x[x_row_offset + r] * v : 0.0;
+    }
+};
+
 // y[r] = sum_k data[k] x[indices[k]] for local rows; LPR lanes cooperate on one row; returns the thread's part of x_row . y
-template <class IDX, int LPR>
-__device__ __forceinline__ double spmv_rows(long long nrows, const IDX* __restrict__ indptr, const IDX* __restrict__ indices,
-                                            const double* __restrict__ data, const double* __restrict__ x, long long x_row_offset,
-                                            const unsigned char* __restrict__ row_mask, double* __restrict__ y, bool want_dot) {
+template <class IDX, int LPR, class EPI>
+__device__ __forceinline__ double spmv_rows_epi(long long nrows, const IDX* __restrict__ indptr, const IDX* __restrict__ indices,
+                                                const double* __restrict__ data, const double* __restrict__ x,
+                                                const unsigned char* __restrict__ row_mask, EPI& epi) {
     const int lane = threadIdx.x % LPR;
     constexpr int RPB = kRedThreads / LPR;  // rows per CTA per pass
     double local = 0.0;
@@ -47,12 +60,17 @@ __device__ __forceinline__ double spmv_rows(long long nrows, const IDX* __restri
         }
 #pragma unroll
         for (int off = LPR / 2; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off, LPR);
-        if (live && lane == 0) {
-            y[r] = s;
-            if (want_dot) local += x[x_row_offset + r] * s;
-        }
+        if (live && lane == 0) local += epi(r, s);
     }
     return local;
+}
+
+template <class IDX, int LPR>
+__device__ __forceinline__ double spmv_rows(long long nrows, const IDX* __restrict__ indptr, const IDX* __restrict__ indices,
+                                            const double* __restrict__ data, const double* __restrict__ x, long long x_row_offset,
+                                            const unsigned char* __restrict__ row_mask, double* __restrict__ y, bool want_dot) {
+    EpiStore epi{x, x_row_offset, y, want_dot};
+    return spmv_rows_epi<IDX, LPR>(nrows, indptr, indices, data, x, row_mask, epi);
 }
 
 template <class IDX, int LPR>
@@ -75,10 +93,10 @@ __global__ void __launch_bounds__(kRedThreads)
 // Software-pipelined form: the adjacency pointers and the first PF column ids of a lane's NEXT node are loaded while the
 // current node is processed, so the only dependent load left on a node's critical path is the gather of x (the plain
 // form pays adjptr -> adj -> x, three DRAM latencies, per node and is latency-bound at ~55 % of HBM bandwidth).
-template <int D, int LPN, int PF>
+template <int D, int LPN, int PF, class EPI>
 __device__ __forceinline__ double spmv_nodes_pipe(long long n_nodes, const long long* __restrict__ adjptr, const int* __restrict__ adj,
-                                                  const double* __restrict__ data, const double* __restrict__ x, long long x_row_offset,
-                                                  const unsigned char* __restrict__ row_mask, double* __restrict__ y, bool want_dot) {
+                                                  const double* __restrict__ data, const double* __restrict__ x,
+                                                  const unsigned char* __restrict__ row_mask, EPI& epi) {
     const int lane = threadIdx.x % LPN;
     constexpr int NPB = kRedThreads / LPN;  // nodes per CTA per pass
     const long long stride = (long long)gridDim.x * NPB;
@@ -147,8 +165,7 @@ __device__ __forceinline__ double spmv_nodes_pipe(long long n_nodes, const long 
             for (int i = 0; i < D; ++i) {
                 const long long r = n * D + i;
                 const double v = (!row_mask || row_mask[r]) ? s[i] : 0.0;
-                y[r] = v;
-                if (want_dot) local += x[x_row_offset + r] * v;
+                local += epi(r, v);
             }
         }
         n = nn;
@@ -170,7 +187,8 @@ template <int D, int LPN>
 __device__ __forceinline__ double spmv_nodes(long long n_nodes, const long long* __restrict__ adjptr, const int* __restrict__ adj,
                                              const double* __restrict__ data, const double* __restrict__ x, long long x_row_offset,
                                              const unsigned char* __restrict__ row_mask, double* __restrict__ y, bool want_dot) {
-    return spmv_nodes_pipe<D, LPN, EFB_SPMV_PF(LPN)>(n_nodes, adjptr, adj, data, x, x_row_offset, row_mask, y, want_dot);
+    EpiStore epi{x, x_row_offset, y, want_dot};
+    return spmv_nodes_pipe<D, LPN, EFB_SPMV_PF(LPN)>(n_nodes, adjptr, adj, data, x, row_mask, epi);
 }
 
 template <int D, int LPN>
@@ -560,6 +578,151 @@ __global__ void __launch_bounds__(kRedThreads)
 
 using SpmvKernel = void (*)(long long, const void*, const void*, const double*, const double*, const unsigned char*, double*, double*,
                             efb_pcg_peer, unsigned long long, unsigned long long);
+
+// ---------------------------------------------------------------------------------------------------------------
+// Chebyshev-Jacobi polynomial preconditioner inside the fused iterations (efb_pcg_iterate_cheb): z = q(D^-1 A) D^-1 r with q the
+// degree m-1 Chebyshev polynomial of the interval [lmin, lmax] of D^-1 A.  Same CG, m-1 more products per iteration, ~m
+// times fewer iterations (profiles/README.md): the iteration count is what bounds strong-scaled shards, because every
+// iteration costs two all-reduces and three grid-wide sync points whatever the shard size; the inner products need neither
+// (one neighbour-to-neighbour halo flag each).  Recurrence (theta = (lmax+lmin)/2, delta = (lmax-lmin)/2, sigma = theta/delta,
+// rho_0 = 1/sigma):  d_0 = D^-1 r / theta, z_1 = d_0;  rho_k = 1/(2 sigma - rho_{k-1}),
+// d_k = rho_k rho_{k-1} d_{k-1} + (2 rho_k / delta) D^-1 (r - A z_k),  z_{k+1} = z_k + d_k,  k = 1 .. m-1.
+// z_k lives over [owned | halo] in two more peer buffers (pbuf_off[.][2 + (k-1 & 1)]); the thread that produces an interface
+// entry stores it into the neighbours' halo segments (row-wise push plan), the last CTA raises their halo flags.
+// ---------------------------------------------------------------------------------------------------------------
+// interface entry i of a new vector into the neighbours' buffers `which`
+__device__ __forceinline__ void push_entry(const efb_pcg_peer& P, const int* __restrict__ push_id, int which, long long i, double v) {
+    const int c = push_id[i];
+    if (c >= 0)
+        for (long long t = P.push_ptr[c]; t < P.push_ptr[c + 1]; ++t) {
+            const int q = P.send_rank[P.push_nbr[t]];
+            ((double*)((char*)P.base[q] + P.pbuf_off[q][which]))[P.push_pos[t]] = v;
+        }
+}
+
+// the last CTA of a kernel that pushed interface entries raises the neighbours' halo flags to `value`
+__device__ __forceinline__ void raise_halo_flags(const efb_pcg_peer& P, PcgCtrl* own, int ticket_id, unsigned long long value) {
+    __shared__ bool last_push;
+    __syncthreads();  // every thread's peer stores happen-before thread 0's fence (cumulative), hence before the flag
+    if (threadIdx.x == 0) {
+        fence_sys();
+        last_push = atomicAdd(&own->ticket[ticket_id], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last_push && threadIdx.x == 0) {
+        fence_sys();
+        for (int sidx = 0; sidx < P.n_send; ++sidx) st_release_sys(&((PcgCtrl*)P.base[P.send_rank[sidx]])->halo_flag[P.rank], value);
+        own->ticket[ticket_id] = 0;
+    }
+}
+
+// (2c) alpha = r.z / p.Ap ; x += alpha p ; r -= alpha Ap ; d_0 = D^-1 r / theta ; z_1 = d_0 (owned rows + the neighbours' halos)
+__global__ void __launch_bounds__(kRedThreads)
+    k_pcg_update_xr_cheb(long long n, const double* __restrict__ p, double* __restrict__ x, double* __restrict__ r, double* __restrict__ d,
+                         double* __restrict__ z1, const double* __restrict__ Ap, const double* __restrict__ inv_diag,
+                         const unsigned char* __restrict__ mask, double inv_theta, efb_pcg_peer P, long long it, unsigned long long ar_done,
+                         unsigned long long halo_done) {
+    __shared__ double red[kRedThreads];
+    PcgCtrl* own = (PcgCtrl*)P.base[P.rank];
+    double pAp[1];
+    gather_reduction<1>(P, own, ar_done + 1ull, pAp, red);
+    const double alpha = own->rz[it & 1] / pAp[0];
+    const int* __restrict__ push_id = P.n_send > 0 ? P.push_id : nullptr;
+    for (long long i = (long long)blockIdx.x * kRedThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kRedThreads) {
+        double di = 0.0;
+        if (!mask || mask[i]) {
+            x[i] += alpha * p[i];
+            const double ri = r[i] - alpha * Ap[i];
+            r[i] = ri;
+            di = ri * inv_diag[i] * inv_theta;
+        }
+        d[i] = di;
+        z1[i] = di;
+        if (push_id) push_entry(P, push_id, 2, i, di);
+    }
+    if (P.n_send > 0) raise_halo_flags(P, own, 1, halo_done + 1ull);
+}
+
+// epilogue of a Chebyshev step: row i of t = A z_k arrives; d, z_{k+1} and (last step) the partial sums of r.z and r.r
+struct EpiCheb {
+    const double* __restrict__ r;
+    const double* __restrict__ inv_diag;
+    const double* __restrict__ zin;
+    double* __restrict__ d;
+    double* __restrict__ zout;
+    const int* __restrict__ push_id;  // nullptr: nothing to push (no neighbours, or the last step)
+    const efb_pcg_peer* P;
+    double c1, c2;
+    int which;  // peer buffer of z_{k+1}
+    double s_rz, s_rr;
+    __device__ __forceinline__ double operator()(long long i, double t) {
+        const double ri = r[i];
+        const double di = c1 * d[i] + c2 * inv_diag[i] * (ri - t);  // inv_diag is 0 on constrained rows: d and z stay 0 there
+        const double zi = zin[i] + di;
+        d[i] = di;
+        zout[i] = zi;
+        if (push_id) push_entry(*P, push_id, which, i, zi);
+        s_rz += ri * zi;
+        s_rr += ri * ri;
+        return 0.0;
+    }
+};
+
+// (2d) Chebyshev step k: waits for the neighbours' halo entries of z_k, t = A z_k, d_k, z_{k+1}; the last step publishes (r.z, r.r)
+template <int KIND, int A, int B>
+__global__ void __launch_bounds__(kRedThreads, EFB_PCG_SPMV_MINB)
+    k_pcg_cheb(long long n, const void* __restrict__ indptr, const void* __restrict__ indices, const double* __restrict__ data,
+               const double* __restrict__ zin, double* __restrict__ zout, const double* __restrict__ r, const double* __restrict__ inv_diag,
+               double* __restrict__ d, const unsigned char* __restrict__ mask, double* __restrict__ partials, double c1, double c2, int which,
+               int last, efb_pcg_peer P, unsigned long long ar_done, unsigned long long halo_wait) {
+    __shared__ double red[kRedThreads];
+    PcgCtrl* own = (PcgCtrl*)P.base[P.rank];
+    if (P.n_recv > 0) {
+        if (threadIdx.x == 0)
+            for (int i = 0; i < P.n_recv; ++i) spin_until(&own->halo_flag[P.recv_rank[i]], halo_wait, own);
+        __syncthreads();
+    }
+    EpiCheb epi{r, inv_diag, zin, d, zout, (P.n_send > 0 && !last) ? P.push_id : nullptr, &P, c1, c2, which, 0.0, 0.0};
+    if constexpr (KIND == 0) {
+        if constexpr (A == 4)
+            spmv_rows_epi<int, B>(n, (const int*)indptr, (const int*)indices, data, zin, mask, epi);
+        else
+            spmv_rows_epi<long long, B>(n, (const long long*)indptr, (const long long*)indices, data, zin, mask, epi);
+    } else {
+        spmv_nodes_pipe<A, B, EFB_SPMV_PF(B)>(n, (const long long*)indptr, (const int*)indices, data, zin, mask, epi);
+    }
+    if (last) {
+        double mine[2], total[2];
+        mine[0] = block_sum(epi.s_rz, red);
+        mine[1] = block_sum(epi.s_rr, red);
+        publish_reduction<2>(P, own, partials, mine, 1, ar_done + 2ull, red, total);
+    } else if (P.n_send > 0) {
+        raise_halo_flags(P, own, 1, halo_wait + 1ull);
+    }
+}
+
+using ChebKernel = void (*)(long long, const void*, const void*, const double*, const double*, double*, const double*, const double*, double*,
+                            const unsigned char*, double*, double, double, int, int, efb_pcg_peer, unsigned long long, unsigned long long);
+template <int KIND, int A>
+static ChebKernel pcg_cheb_kernel(int lanes) {
+    switch (lanes) {
+        case 4: return k_pcg_cheb<KIND, A, 4>;
+        case 8: return k_pcg_cheb<KIND, A, 8>;
+        case 16: return k_pcg_cheb<KIND, A, 16>;
+        default: return k_pcg_cheb<KIND, A, 32>;
+    }
+}
+
+// unfused building block of the same recurrence: d = c1 d + c2 D^-1 (r - t), z += d  (t = A z of the caller's product)
+__global__ void k_cheb_update(long long n, const double* __restrict__ r, const double* __restrict__ t, const double* __restrict__ inv_diag,
+                              double c1, double c2, double* __restrict__ d, double* __restrict__ z) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double di = c1 * d[i] + c2 * inv_diag[i] * (r[i] - (t ? t[i] : 0.0));
+        d[i] = di;
+        z[i] += di;
+    }
+}
+
 
 template <int KIND, int A>
 static SpmvKernel pcg_spmv_kernel(int lanes) {
@@ -1150,6 +1313,137 @@ extern "C" int efb_pcg_iterate(const efb_pcg_system* sys, const efb_pcg_peer* pe
         delete[] ev;
     }
     return check_launch("efb_pcg_iterate");
+}
+
+extern "C" int efb_pcg_cheb_update(int64_t n, const double* r, const double* t, const double* inv_diag, double c1, double c2, double* d,
+                                   double* z, void* stream) {
+    if (n == 0) return 0;
+    const long long want = (n + 255) / 256;
+    const unsigned grid = (unsigned)(want < kRedBlocks ? want : kRedBlocks);
+    k_cheb_update<<<grid, 256, 0, as_stream(stream)>>>(n, r, t, inv_diag, c1, c2, d, z);
+    return check_launch("efb_pcg_cheb_update");
+}
+
+extern "C" int efb_pcg_iterate_cheb(const efb_pcg_system* sys, const efb_pcg_peer* peer, int n_iters, int64_t it0, int degree, double lmin,
+                                    double lmax, double* d_vec, void* stream) {
+    const efb_pcg_peer& P = *peer;
+    if (P.world < 1 || P.world > EFB_MAX_RANKS || P.rank < 0 || P.rank >= P.world || P.n_send < 0 || P.n_send > EFB_MAX_RANKS ||
+        P.n_recv < 0 || P.n_recv > EFB_MAX_RANKS) {
+        set_error("efb_pcg_iterate_cheb: bad communicator (world %d, rank %d)", P.world, P.rank);
+        return 1;
+    }
+    if (degree < 2 || degree > 16 || !(lmin > 0.0) || !(lmax > lmin) || !d_vec) {
+        set_error("efb_pcg_iterate_cheb: degree in 2..16 and 0 < lmin < lmax (degree %d, [%g, %g])", degree, lmin, lmax);
+        return 1;
+    }
+    if (P.n_send > 0 && !P.push_id) {
+        set_error("efb_pcg_iterate_cheb: the communicator has no row-wise push plan");
+        return 1;
+    }
+    if (sys->nrows == 0 && P.world == 1) return 0;
+    cudaStream_t st = as_stream(stream);
+    SpmvArgs a{0, sys->indptr, sys->indices, sys->data, sys->free_mask, sys->Ap, sys->partials};
+    if (sys->kind == 1) {
+        if (sys->dof_n < 1 || sys->dof_n > 3 || sys->nrows % sys->dof_n) {
+            set_error("efb_pcg_iterate_cheb: node-block systems need dof_n in 1..3 dividing nrows");
+            return 1;
+        }
+        a.n = sys->nrows / sys->dof_n;
+    } else if (sys->kind == 0 && (sys->index_bytes == 4 || sys->index_bytes == 8)) {
+        a.n = sys->nrows;
+    } else {
+        set_error("efb_pcg_iterate_cheb: kind must be 0 (CSR, 4- or 8-byte indices) or 1 (node blocks)");
+        return 1;
+    }
+    SpmvKernel spmv_k;
+    ChebKernel cheb_k;
+    if (sys->kind == 1) {
+        spmv_k = sys->dof_n == 1 ? pcg_spmv_kernel<1, 1>(sys->lanes) : sys->dof_n == 2 ? pcg_spmv_kernel<1, 2>(sys->lanes) : pcg_spmv_kernel<1, 3>(sys->lanes);
+        cheb_k = sys->dof_n == 1 ? pcg_cheb_kernel<1, 1>(sys->lanes) : sys->dof_n == 2 ? pcg_cheb_kernel<1, 2>(sys->lanes) : pcg_cheb_kernel<1, 3>(sys->lanes);
+    } else {
+        spmv_k = sys->index_bytes == 4 ? pcg_spmv_kernel<0, 4>(sys->lanes) : pcg_spmv_kernel<0, 8>(sys->lanes);
+        cheb_k = sys->index_bytes == 4 ? pcg_cheb_kernel<0, 4>(sys->lanes) : pcg_cheb_kernel<0, 8>(sys->lanes);
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int g_spmv = min(kRedBlocks, sms * resident_blocks_per_sm(spmv_k));
+    int g_cheb = min(kRedBlocks, sms * resident_blocks_per_sm(cheb_k));
+    int g_xr = min(kRedBlocks, sms * resident_blocks_per_sm(k_pcg_update_xr_cheb));
+    int g_p = min(kRedBlocks, sms * resident_blocks_per_sm(k_pcg_update_p));
+    {
+        static const int rows_per_thread = [] { const char* e = getenv("EFB_PCG_ROWS_PER_THREAD"); return e ? atoi(e) : 4; }();
+        if (rows_per_thread > 0) {
+            const long long want = (sys->nrows + (long long)kRedThreads * rows_per_thread - 1) / ((long long)kRedThreads * rows_per_thread);
+            const int cap = (int)max((long long)sms, min((long long)kRedBlocks, want));
+            g_xr = min(g_xr, cap);
+            g_p = min(g_p, cap);
+            const int cap_s = max(cap, (int)min((long long)kRedBlocks, (a.n * sys->lanes + kRedThreads - 1) / kRedThreads / 2));
+            g_spmv = min(g_spmv, cap_s);
+            g_cheb = min(g_cheb, cap_s);
+        }
+    }
+    // coefficients of the recurrence
+    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+    double c1[16], c2[16];
+    {
+        double rho = 1.0 / sigma;
+        for (int k = 1; k < degree; ++k) {
+            const double rho_n = 1.0 / (2.0 * sigma - rho);
+            c1[k] = rho_n * rho;
+            c2[k] = 2.0 * rho_n / delta;
+            rho = rho_n;
+        }
+    }
+    char* own = (char*)P.base[P.rank];
+    double* zb[2] = {(double*)(own + P.pbuf_off[P.rank][2]), (double*)(own + P.pbuf_off[P.rank][3])};
+    // dev: EFB_PCG_TIMING=1 prints the mean duration of the kernels of this call (CUDA events between the launches)
+    static const bool timing = [] { const char* e = getenv("EFB_PCG_TIMING"); return e && atoi(e) > 0; }();
+    const int per_it = degree + 2;
+    cudaEvent_t* ev = nullptr;
+    int ne = 0;
+    if (timing) {
+        ev = new cudaEvent_t[per_it * n_iters + 1];
+        for (int i = 0; i <= per_it * n_iters; ++i) cudaEventCreate(&ev[i]);
+        cudaEventRecord(ev[ne++], st);
+    }
+    for (int k = 0; k < n_iters; ++k) {
+        const long long it = it0 + k;
+        const double* p = (const double*)(own + P.pbuf_off[P.rank][it & 1]);
+        double* pn = (double*)(own + P.pbuf_off[P.rank][(it & 1) ^ 1]);
+        const unsigned long long ar_done = P.ar_seq + 2ull * (unsigned long long)k;
+        const unsigned long long halo_done = P.halo_seq + (unsigned long long)degree * (unsigned long long)k;
+        spmv_k<<<g_spmv, kRedThreads, 0, st>>>(a.n, a.indptr, a.indices, a.data, p, a.mask, a.Ap, a.partials, P, ar_done, halo_done);
+        if (timing) cudaEventRecord(ev[ne++], st);
+        k_pcg_update_xr_cheb<<<g_xr, kRedThreads, 0, st>>>(sys->nrows, p, sys->x, sys->r, d_vec, zb[0], sys->Ap, sys->inv_diag, sys->free_mask,
+                                                            1.0 / theta, P, it, ar_done, halo_done);
+        if (timing) cudaEventRecord(ev[ne++], st);
+        for (int j = 1; j < degree; ++j) {  // z_j in zb[(j-1) & 1] -> z_{j+1} in zb[j & 1]
+            cheb_k<<<g_cheb, kRedThreads, 0, st>>>(a.n, a.indptr, a.indices, a.data, zb[(j - 1) & 1], zb[j & 1], sys->r, sys->inv_diag, d_vec,
+                                                    a.mask, a.partials, c1[j], c2[j], 2 + (j & 1), j == degree - 1 ? 1 : 0, P, ar_done,
+                                                    halo_done + (unsigned long long)j);
+            if (timing) cudaEventRecord(ev[ne++], st);
+        }
+        // p' = z_m + beta p ; its halo push is push number `degree` of this iteration
+        k_pcg_update_p<<<g_p, kRedThreads, 0, st>>>(sys->nrows, zb[(degree - 1) & 1], sys->free_mask, p, pn, P, it, ar_done,
+                                                     halo_done + (unsigned long long)(degree - 1));
+        if (timing) cudaEventRecord(ev[ne++], st);
+    }
+    if (timing) {
+        cudaEventSynchronize(ev[ne - 1]);
+        float t[18] = {0}, ms;
+        for (int i = 0; i + 1 < ne; ++i) {
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            t[i % per_it] += ms;
+        }
+        fprintf(stderr, "[efb_pcg_iterate_cheb rank %d] %d iterations, degree %d, grids %d/%d/%d/%d us per kernel: spmv %.1f, xr %.1f, cheb", P.rank,
+                n_iters, degree, g_spmv, g_xr, g_cheb, g_p, 1e3 * t[0] / n_iters, 1e3 * t[1] / n_iters);
+        for (int j = 1; j < degree; ++j) fprintf(stderr, " %.1f", 1e3 * t[1 + j] / n_iters);
+        fprintf(stderr, ", update_p %.1f\n", 1e3 * t[degree + 1] / n_iters);
+        for (int i = 0; i < ne; ++i) cudaEventDestroy(ev[i]);
+        delete[] ev;
+    }
+    return check_launch("efb_pcg_iterate_cheb");
 }
 
 extern "C" int efb_pcg_iterate_cg2(const efb_pcg_system* sys, const efb_pcg_peer* peer, int n_iters, int64_t it0, void* stream) {

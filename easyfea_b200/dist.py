@@ -514,10 +514,12 @@ class LocalWorkspace:
         self.rz_off, self.rr_off, self.err_off, self.iters_off = int(lay[0]), int(lay[1]), int(lay[2]), int(lay[3])
         self.cg2_init_off = int(lay[4])
         self.ctrl_bytes = ctrl
-        self.pbuf_off = (ctrl, ctrl + _pad256(self.n * 8))
-        self.nbytes = ctrl + 2 * _pad256(self.n * 8)
+        # two p buffers, two z buffers (Chebyshev form): each over [owned | halo]
+        self.pbuf_off = tuple(ctrl + k * _pad256(self.n * 8) for k in range(4))
+        self.nbytes = ctrl + 4 * _pad256(self.n * 8)
         self._alloc()
-        self.p = [self.f64[o // 8: o // 8 + self.n] for o in self.pbuf_off]
+        self.p = [self.f64[o // 8: o // 8 + self.n] for o in self.pbuf_off[:2]]
+        self.zb = [self.f64[o // 8: o // 8 + self.n] for o in self.pbuf_off[2:]]
         self.ctrl = self.f64[: ctrl // 8]
         self.peer = _lib.EfbPcgPeer()
         self._fill_peer()
@@ -530,7 +532,8 @@ class LocalWorkspace:
         P = self.peer
         P.world, P.rank, P.n_send, P.n_recv = 1, 0, 0, 0
         P.base[0] = self.base
-        P.pbuf_off[0][0], P.pbuf_off[0][1] = self.pbuf_off
+        for k in range(4):
+            P.pbuf_off[0][k] = self.pbuf_off[k]
         P.send_idx = None
         P.ar_seq, P.halo_seq = 0, 0
 
@@ -539,9 +542,9 @@ class LocalWorkspace:
         c = self.ctrl.cpu().numpy()
         return float(c[self.rr_off]), int(c.view(np.uint32)[self.err_off]), int(c.view(np.uint64)[self.iters_off])
 
-    def advance(self, n_iters: int, reductions_per_iter: int = 2):
+    def advance(self, n_iters: int, reductions_per_iter: int = 2, halos_per_iter: int = 1):
         self.peer.ar_seq += reductions_per_iter * n_iters
-        self.peer.halo_seq += n_iters
+        self.peer.halo_seq += halos_per_iter * n_iters
 
 
 class PeerWorkspace(LocalWorkspace):
@@ -587,7 +590,8 @@ class PeerWorkspace(LocalWorkspace):
                 _lib.call("efb_peer_open", hb, ctypes.byref(ptr))
                 self._opened.append(int(ptr.value))
                 P.base[q] = int(ptr.value)
-            P.pbuf_off[q][0], P.pbuf_off[q][1] = int(off[0]), int(off[1])
+            for k in range(4):
+                P.pbuf_off[q][k] = int(off[k])
         send_rank, send_ptr, send_dst, recv_rank = peer_push_plan(comm, [g[2] for g in gathered])
         P.n_send, P.n_recv = len(send_rank), len(recv_rank)
         for i, q in enumerate(send_rank):

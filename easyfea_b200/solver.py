@@ -90,10 +90,70 @@ FUSED_MAX_DOFS = 8_000_000
 # 29.6 vs 60.6 us per iteration at 0.25 M dofs on one B200, equal at 2 M dofs (profiles/r2_pcg_small_systems.log).  Its
 # recurrences carry one more rounding error per step, so `single_reduction="auto"` keeps the classic form for tol < 1e-10.
 SINGLE_REDUCTION_MAX_DOFS = 1_500_000
+# Chebyshev-Jacobi polynomial preconditioner (`precond_degree`): z = q(D^-1 A) D^-1 r with q the Chebyshev polynomial of degree
+# m - 1 on [lmax / CHEB_RATIO, lmax], lmax = CHEB_SAFETY x a power-iteration estimate of the largest eigenvalue of D^-1 A.
+# m = 4 cuts the iterations ~3.6x for 1.1x the products (TRI3 / TETRA4 / HEXA8 elasticity with a degraded band,
+# profiles/README.md): fewer all-reduces and grid-wide sync points, which is what bounds small and strong-scaled systems.
+CHEB_DEGREE = 4
+CHEB_RATIO = 30.0
+CHEB_SAFETY = 1.25      # on the power-iteration estimate (converges from below; a stale or low lmax makes the polynomial indefinite)
+CHEB_POWER_ITERS = 10   # per solve: the matrix of a staggered / Newton loop changes between solves, and so does lmax
+# "auto" picks the polynomial for shards of at most this many matrix entries (a product of <= ~70 us): above, an iteration is
+# bound by the product itself and the polynomial's 1.1x products + heavier epilogue cost more than the saved reductions
+# (HEXA8 3 M dofs on one B200: 0.60 s against 0.49 s with plain Jacobi; TETRA4 2.6 M dofs per rank on two: 0.69 against 0.62 s)
+CHEB_MAX_NNZ = 32_000_000
+CHEB_STALL_ITERS = 400  # outer iterations without a new minimum of |r|: the polynomial is dropped for plain Jacobi
+
+
+def cheb_coefficients(degree: int, lmin: float, lmax: float):
+    """(theta, [(c1_k, c2_k) for k = 1 .. degree-1]) of the recurrence d_k = c1_k d_{k-1} + c2_k D^-1 (r - A z_k)"""
+    theta, delta = 0.5 * (lmax + lmin), 0.5 * (lmax - lmin)
+    sigma = theta / delta
+    rho, out = 1.0 / sigma, []
+    for _ in range(1, degree):
+        rho_n = 1.0 / (2.0 * sigma - rho)
+        out.append((rho_n * rho, 2.0 * rho_n / delta))
+        rho = rho_n
+    return theta, out
+
+
+def estimate_lmax(A: DeviceCsr, inv_diag, mask, comm=None, iters: int = CHEB_POWER_ITERS) -> float:
+    """largest eigenvalue of D^-1 A on the free dofs by power iteration (set-up of the polynomial preconditioner; the estimate
+    converges from below — the caller applies CHEB_SAFETY).  Everything stays on the device until the final read."""
+    dev = A.data.device
+    nrows = A.indptr.numel() - 1
+    n_glob = A.shape[1]
+    rank = 0 if comm is None else int(comm.part.rank)
+    i = torch.arange(nrows, dtype=torch.float64, device=dev)
+    v = torch.frac(torch.sin(i * 12.9898 + 78.233 * (rank + 1)) * 43758.5453) * 2.0 - 1.0  # deterministic, rank-dependent
+    if mask is not None:
+        v = v * mask.to(torch.float64)
+    full = torch.zeros(n_glob, dtype=torch.float64, device=dev)
+    w = dv.empty((nrows,))
+    t = torch.zeros(1, dtype=torch.float64, device=dev)
+    lam = torch.ones(1, dtype=torch.float64, device=dev)
+
+    def norm(x):
+        t[0] = x @ x
+        if comm is not None:
+            comm.all_reduce_sum(t)
+        return torch.sqrt(t)
+
+    nv = norm(v)
+    for _ in range(iters):
+        full[:nrows] = v / torch.clamp(nv, min=1e-300)
+        if comm is not None:
+            comm.halo_exchange(full)
+        spmv(A, full, w, 0, mask)
+        v = w * inv_diag
+        nv = norm(v)
+        lam = nv.clone()  # |D^-1 A u| with |u| = 1
+    out = float(lam.item())
+    return out if out > 0.0 and out == out else 1.0
 
 
 def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: int = None, check_every: int = 25, comm=None,
-        fused="auto", persistent: bool = False, single_reduction="auto"):
+        fused="auto", persistent: bool = False, single_reduction="auto", precond_degree="auto"):
     """Solve A x = b on the free dofs (free_mask True / 1 = unknown; other entries of x keep the values of x0).
 
     A holds the owned rows in LOCAL numbering `[owned | halo]` columns.  Stops when ||r|| <= tol * ||b - A x_known||
@@ -112,6 +172,9 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
     measured 13 % / 8 % faster at 0.2 M dofs on 1 / 2 GPUs and 1-3 % slower at >= 2 M dofs per rank, identical iteration
     counts on the phase-field systems, but 18 % SLOWER on config 4 over 8 GPUs (0.33 vs 0.28 s per staggered iteration,
     one measurement each, profiles/README.md) — not understood yet, so the classic form stays the default.
+    `precond_degree` = m: Chebyshev-Jacobi polynomial preconditioner of degree m - 1 in D^-1 A (m = 1: plain Jacobi); "auto" =
+    CHEB_DEGREE unless the single-reduction or persistent form is forced.  Inside the fused iterations
+    (`efb_pcg_iterate_cheb`) the m - 1 extra products cost one neighbour halo flag each and no all-reduce.
     `fused=False` keeps
     one collective call per exchange (NCCL through torch.distributed) and one kernel per vector operation — the baseline
     the fused path is measured against (bench.py) and checked against (tests).
@@ -119,19 +182,32 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
     dev = A.data.device
     nrows = A.indptr.numel() - 1
     n_glob = A.shape[1]
-    if fused == "auto":  # the same decision on every rank: the largest shard decides
-        big = torch.tensor([float(nrows)], dtype=torch.float64, device=dev)
-        if comm is not None:
-            comm.all_reduce_max(big)
-        fused = bool(single_reduction is True or persistent) or float(big.item()) <= FUSED_MAX_DOFS
-    else:
-        big = None
-    if single_reduction == "auto":
-        if big is None:
+    big = None
+
+    def largest_shard():
+        nonlocal big
+        if big is None:  # the same decision on every rank: the largest shard decides
             big = torch.tensor([float(nrows)], dtype=torch.float64, device=dev)
             if comm is not None:
                 comm.all_reduce_max(big)
-        single_reduction = bool(fused) and not persistent and tol >= 1e-10 and float(big.item()) <= SINGLE_REDUCTION_MAX_DOFS
+            big = float(big.item())
+        return big
+
+    if precond_degree == "auto":  # an explicitly requested single-reduction / persistent form keeps plain Jacobi
+        if single_reduction is True or persistent:
+            precond_degree = 1
+        else:
+            t = torch.tensor([float(A.nnz)], dtype=torch.float64, device=dev)
+            if comm is not None:
+                comm.all_reduce_max(t)
+            precond_degree = CHEB_DEGREE if float(t.item()) <= CHEB_MAX_NNZ else 1
+    degree = max(1, int(precond_degree))
+    if degree > 1:
+        single_reduction, persistent = False, False
+    if fused == "auto":
+        fused = bool(single_reduction is True or persistent) or largest_shard() <= FUSED_MAX_DOFS
+    if single_reduction == "auto":
+        single_reduction = bool(fused) and not persistent and tol >= 1e-10 and largest_shard() <= SINGLE_REDUCTION_MAX_DOFS
     single_reduction = bool(single_reduction) and bool(fused)
     st = dv.stream_ptr
     b = dv.to_device(b)
@@ -182,6 +258,27 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
         if comm is not None:
             comm.all_reduce_sum(scal[slot:slot + m])
 
+    lmin = lmax = None
+    if degree > 1:
+        lmax = CHEB_SAFETY * estimate_lmax(A, inv_diag, mask, comm)
+        lmin = lmax / CHEB_RATIO
+        theta, coefs = cheb_coefficients(degree, lmin, lmax)
+        d_vec = torch.zeros(nrows, dtype=torch.float64, device=dev)
+        z_full = ws.zb[0] if ws is not None else torch.zeros(n_glob, dtype=torch.float64, device=dev)
+
+        def cheb_apply(r_vec):
+            """z_full[:nrows] = q(D^-1 A) D^-1 r (kernel-per-operation form: set-up of the fused loop, body of the unfused one)"""
+            z_full.zero_()
+            d_vec.zero_()
+            zo = z_full[:nrows]
+            _lib.call("efb_pcg_cheb_update", nrows, dv.ptr(r_vec), None, dv.ptr(inv_diag), 0.0, 1.0 / theta, dv.ptr(d_vec), dv.ptr(zo), st())
+            for c1, c2 in coefs:
+                if comm is not None:
+                    comm.halo_exchange(z_full)
+                spmv(A, z_full, Ap, 0, mask)
+                _lib.call("efb_pcg_cheb_update", nrows, dv.ptr(r_vec), dv.ptr(Ap), dv.ptr(inv_diag), c1, c2, dv.ptr(d_vec), dv.ptr(zo), st())
+            return zo
+
     # reference norm: || b - A x_known || on the free dofs (x_known = x0 on constrained dofs, 0 elsewhere)
     if mask is not None:
         xk = torch.zeros_like(x_full)
@@ -207,6 +304,12 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
     _lib.call("efb_pcg_init", nrows, dv.ptr(b), dv.ptr(Ap), dv.ptr(inv_diag), dv.ptr(mask), dv.ptr(r), dv.ptr(z), dv.ptr(p),
               dv.ptr(partials), st())
     reduce_to(2, 2)  # scal[2] = r.z, scal[3] = r.r
+    if degree > 1:  # z_0 = q(D^-1 A) D^-1 r_0, p_0 = z_0, r.z with the polynomial preconditioner
+        z0 = cheb_apply(r)
+        z.copy_(z0)
+        p.copy_(z0)
+        _lib.call("efb_pcg_dot", nrows, dv.ptr(r), dv.ptr(z), dv.ptr(partials), st())
+        reduce_to(2, 1)
     scal[0:1].copy_(scal[2:3])
     it = 0
     rr = float(scal[3].item())
@@ -229,6 +332,7 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
             z.zero_()  # the `z` vector of the system holds p in this form
             s_vec = torch.zeros(nrows, dtype=torch.float64, device=dev)
             S.s = s_vec.data_ptr()
+        best_rr, best_it, stalled = rr, 0, False
         while rr > target and it < maxiter:
             if single_reduction:
                 k = min(int(check_every), maxiter - it)
@@ -240,6 +344,21 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
                     raise _lib.EfbError("PCG: a wait on a neighbour rank timed out (peer process lost?)")
                 if rr != rr:
                     raise _lib.EfbError("PCG broke down (NaN residual): matrix not SPD on the free dofs?")
+                continue
+            if degree > 1:
+                k = min(int(check_every), maxiter - it)
+                _lib.call("efb_pcg_iterate_cheb", ctypes.byref(S), ctypes.byref(ws.peer), k, it, degree, float(lmin), float(lmax), dv.ptr(d_vec),
+                          st())
+                rr, err, _ = ws.status()
+                ws.advance(k, 2, degree)
+                it += k
+                if err:
+                    raise _lib.EfbError("PCG: a wait on a neighbour rank timed out (peer process lost?)")
+                if rr == rr and rr < best_rr:
+                    best_rr, best_it = rr, it
+                if rr != rr or it - best_it >= CHEB_STALL_ITERS:  # lmax underestimated: the polynomial is not positive
+                    stalled = True
+                    break
                 continue
             if use_persistent:
                 _lib.call("efb_pcg_solve_persistent", ctypes.byref(S), ctypes.byref(ws.peer), it, maxiter - it, float(target), st())
@@ -260,6 +379,7 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
             if rr != rr:
                 raise _lib.EfbError("PCG broke down (NaN residual): matrix not SPD on the free dofs?")
     else:
+        best_rr, best_it, stalled = rr, 0, False
         while rr > target and it < maxiter:
             for _ in range(min(int(check_every), maxiter - it)):
                 if comm is not None:
@@ -269,12 +389,37 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
                 _lib.call("efb_pcg_update_xr", nrows, s_ptr(0), s_ptr(1), dv.ptr(p), dv.ptr(Ap), dv.ptr(x), dv.ptr(r), dv.ptr(inv_diag),
                           dv.ptr(mask), dv.ptr(z), dv.ptr(partials), st())
                 reduce_to(2, 2)  # rz_new, rr
+                if degree > 1:
+                    z.copy_(cheb_apply(r))
+                    _lib.call("efb_pcg_dot", nrows, dv.ptr(r), dv.ptr(z), dv.ptr(partials), st())
+                    reduce_to(2, 1)  # rz_new with the polynomial preconditioner
                 _lib.call("efb_pcg_update_p", nrows, s_ptr(2), s_ptr(0), dv.ptr(z), dv.ptr(mask), dv.ptr(p), st())
                 scal[0:1].copy_(scal[2:3])
                 it += 1
             rr = float(scal[3].item())
+            if degree > 1:
+                if rr == rr and rr < best_rr:
+                    best_rr, best_it = rr, it
+                if rr != rr or it - best_it >= CHEB_STALL_ITERS:
+                    stalled = True
+                    break
             if rr != rr:
                 raise _lib.EfbError("PCG broke down (NaN residual): matrix not SPD on the free dofs?")
+    if degree > 1 and stalled:
+        # continue from the best we have with plain Jacobi (x holds the current iterate; a NaN iterate restarts from x0)
+        import warnings
+
+        warnings.warn(f"PCG: the Chebyshev-Jacobi preconditioner stalled after {it} iterations (lmax = {lmax:.3g} too small?); "
+                      "continuing with plain Jacobi", RuntimeWarning)
+        xs = x if bool(torch.isfinite(x).all()) else (dv.to_device(x0).reshape(-1)[:nrows] if x0 is not None else torch.zeros_like(x))
+        # (the reference norm depends on the constrained entries of the start vector only: the same tolerance applies)
+        x2, info2 = pcg(A, b, x0=xs.clone(), free_mask=free_mask, tol=tol, maxiter=max(maxiter - it, 1), check_every=check_every, comm=comm,
+                        fused=fused, precond_degree=1)
+        info2["iterations"] += it
+        info2["precond_degree"] = degree
+        info2["fell_back_to_jacobi"] = True
+        return x2, info2
     rel = (rr / bnorm2) ** 0.5
     return x.clone(), {"iterations": it, "rel_residual": rel, "converged": rel <= tol, "rhs_norm": bnorm2 ** 0.5, "fused": ws is not None,
-                       "persistent": ws is not None and use_persistent, "single_reduction": ws is not None and bool(single_reduction)}
+                       "persistent": ws is not None and use_persistent, "single_reduction": ws is not None and bool(single_reduction),
+                       "precond_degree": degree, "lmax": lmax}

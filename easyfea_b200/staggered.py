@@ -125,6 +125,7 @@ class ElasticSolve:
         self.pcg_fused = "auto"  # True / False force the fused peer-memory form / the kernel-per-operation loop (solver.pcg)
         self.pcg_persistent = False  # True: one cooperative kernel per solve instead of three kernels per iteration
         self.pcg_single_reduction = "auto"  # True / False force / forbid the Chronopoulos-Gear form (one all-reduce per iteration)
+        self.pcg_precond_degree = "auto"  # m: Chebyshev-Jacobi polynomial preconditioner of degree m - 1 (1 = plain Jacobi), solver.pcg
 
     def assemble(self) -> DeviceCsr:
         scale = self.thickness if self.dim == 2 else 1.0
@@ -140,7 +141,7 @@ class ElasticSolve:
         self.sys.refresh_halo(self.u, d)
         rhs = torch.zeros(nown, dtype=torch.float64, device=self.u.device) if b is None else dv.to_device(b)
         x, info = pcg(K, rhs, x0=self.u, free_mask=mask, tol=tol, maxiter=maxiter, comm=self.sys.comm(d), fused=self.pcg_fused,
-                      persistent=self.pcg_persistent, single_reduction=self.pcg_single_reduction)
+                      persistent=self.pcg_persistent, single_reduction=self.pcg_single_reduction, precond_degree=self.pcg_precond_degree)
         _check(info, "ElasticSolve")
         self.u[:nown] = x
         self.sys.refresh_halo(self.u, d)
@@ -164,6 +165,7 @@ class PhaseFieldStaggered:
         self.f_ext = None      # nodal external forces of the displacement problem (owned dofs), `add_neumann`
         self.pcg_tol, self.pcg_maxiter = pcg_tol, pcg_maxiter
         self.pcg_fused, self.pcg_persistent, self.pcg_single_reduction = "auto", False, "auto"
+        self.pcg_precond_degree = "auto"
         self._updatedDamage = self._updatedDisplacement = False
         self.info = {}
 
@@ -257,7 +259,7 @@ class PhaseFieldStaggered:
         _apply(self.d, dofs, vals)
         s.refresh_halo(self.d, 1)
         x, info = pcg(K, F, x0=self.d, free_mask=mask, tol=self.pcg_tol, maxiter=self.pcg_maxiter, comm=s.comm(1),
-                      fused=self.pcg_fused, persistent=self.pcg_persistent, single_reduction=self.pcg_single_reduction)
+                      fused=self.pcg_fused, persistent=self.pcg_persistent, single_reduction=self.pcg_single_reduction, precond_degree=self.pcg_precond_degree)
         _check(info, "PhaseFieldStaggered damage solve")
         self.d[: s.n_owned] = x
         s.refresh_halo(self.d, 1)
@@ -275,7 +277,7 @@ class PhaseFieldStaggered:
         s.refresh_halo(self.u, dim)
         rhs = torch.zeros(nown, dtype=torch.float64, device=self.u.device) if self.f_ext is None else self.f_ext
         x, info = pcg(K, rhs, x0=self.u, free_mask=mask, tol=self.pcg_tol, maxiter=self.pcg_maxiter, comm=s.comm(dim),
-                      fused=self.pcg_fused, persistent=self.pcg_persistent, single_reduction=self.pcg_single_reduction)
+                      fused=self.pcg_fused, persistent=self.pcg_persistent, single_reduction=self.pcg_single_reduction, precond_degree=self.pcg_precond_degree)
         _check(info, "PhaseFieldStaggered displacement solve")
         self.u[:nown] = x
         s.refresh_halo(self.u, dim)

@@ -106,6 +106,7 @@ class TransientSolve:
         self.algo = "elliptic"
         self.pcg_tol, self.pcg_maxiter, self.pcg_fused, self.pcg_persistent = 1e-10, None, "auto", False
         self.pcg_single_reduction = "auto"
+        self.pcg_precond_degree = "auto"
         self.info = {}
 
     # -- systems ---------------------------------------------------------------------------------------------------
@@ -214,7 +215,7 @@ class TransientSolve:
         _apply(x0, dofs, torch.zeros_like(vals) if explicit else vals)
         s.refresh_halo(x0, d)
         x, info = pcg(A, b, x0=x0, free_mask=mask, tol=self.pcg_tol, maxiter=self.pcg_maxiter, comm=s.comm(d), fused=self.pcg_fused,
-                      persistent=self.pcg_persistent, single_reduction=self.pcg_single_reduction)
+                      persistent=self.pcg_persistent, single_reduction=self.pcg_single_reduction, precond_degree=self.pcg_precond_degree)
         self.info = info
         x0[:n_own] = x
         s.refresh_halo(x0, d)

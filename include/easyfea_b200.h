@@ -295,7 +295,7 @@ typedef struct efb_pcg_peer {
     int64_t send_ptr[EFB_MAX_RANKS + 1];      /* send_idx[send_ptr[i] : send_ptr[i+1]] goes to send_rank[i] */
     int64_t send_dst[EFB_MAX_RANKS];          /* first entry of this rank's segment inside that neighbour's p buffers */
     void* base[EFB_MAX_RANKS];                /* region of every rank as mapped HERE (own region at [rank]) */
-    int64_t pbuf_off[EFB_MAX_RANKS][2];       /* byte offsets of the two p buffers inside each region */
+    int64_t pbuf_off[EFB_MAX_RANKS][4];       /* byte offsets of the two p buffers and the two z buffers (Chebyshev form) inside each region */
     const int32_t* send_idx;                  /* owned local dof ids to push, concatenated per neighbour */
     uint64_t ar_seq;                          /* reductions already published on this communicator */
     uint64_t halo_seq;                        /* halo pushes already published */
@@ -317,6 +317,18 @@ int efb_pcg_ctrl_layout(int32_t* out5);
 /* enqueue n_iters iterations starting at iteration `it0` (p_it lives in p buffer it & 1, r.z of it in rz[it & 1]).
  * The caller advances peer->ar_seq by 2*n_iters and halo_seq by n_iters afterwards. */
 int efb_pcg_iterate(const efb_pcg_system* sys, const efb_pcg_peer* peer, int n_iters, int64_t it0, void* stream);
+/* The same iterations with a Chebyshev-Jacobi polynomial preconditioner: z = q(D^-1 A) D^-1 r, q the degree `degree`-1
+ * Chebyshev polynomial of [lmin, lmax] (bounds of the spectrum of D^-1 A the polynomial damps; lmax must not be below the
+ * largest eigenvalue).  `degree` - 1 more products per iteration (each with one neighbour halo flag, no all-reduce), about
+ * `degree` times fewer iterations: what strong-scaled shards need, since an iteration costs two all-reduces whatever the
+ * shard size.  d_vec (nrows) is scratch; z lives in peer buffers 2 and 3 of efb_pcg_peer (with halos), p as in
+ * efb_pcg_iterate.  Before iteration 0 the caller puts p_0 = z_0 = q(D^-1 A) D^-1 r_0 (owned + halo) in p buffer 0 and r.z in
+ * the control block.  The caller advances ar_seq by 2*n_iters and halo_seq by degree*n_iters afterwards. */
+int efb_pcg_iterate_cheb(const efb_pcg_system* sys, const efb_pcg_peer* peer, int n_iters, int64_t it0, int degree, double lmin,
+                         double lmax, double* d_vec, void* stream);
+/* unfused building block of the same recurrence: d = c1 d + c2 D^-1 (r - t), z += d; t = A z of the caller (NULL: 0) */
+int efb_pcg_cheb_update(int64_t n, const double* r, const double* t, const double* inv_diag, double c1, double c2, double* d, double* z,
+                        void* stream);
 /* Single-reduction form (Chronopoulos-Gear): the same iterates with ONE all-reduce per iteration — two kernels (vector
  * update, SpMV) and two cross-GPU sync points per iteration instead of three and three (the interface entries of z are stored into the neighbours by
  * the update kernel itself, through the row-wise push plan of efb_pcg_peer).  z lives in the two peer buffers

@@ -138,9 +138,21 @@ def test_pcg_elastic_cube(efb):
     known[right * 3] = True
     x0[right * 3] = 0.1
     b = np.zeros(Ndof)
-    x, info = efb.solver.pcg(K, b, x0=x0, free_mask=~known, tol=1e-8, maxiter=5000)
-    assert info["converged"], info
+    # default: Chebyshev-Jacobi polynomial preconditioner inside the fused iterations (efb_pcg_iterate_cheb)
+    xc, infoc = efb.solver.pcg(K, b, x0=x0, free_mask=~known, tol=1e-8, maxiter=5000)
+    assert infoc["converged"] and infoc["fused"] and infoc["precond_degree"] == efb.solver.CHEB_DEGREE, infoc
+    # plain Jacobi (degree 1): the reference of the variants below
+    x, info = efb.solver.pcg(K, b, x0=x0, free_mask=~known, tol=1e-8, maxiter=5000, precond_degree=1)
+    assert info["converged"] and info["precond_degree"] == 1, info
+    assert infoc["iterations"] * 2 < info["iterations"], (infoc, info)  # ~3.6x fewer iterations at degree 4
     x = x.cpu().numpy()
+    assert np.linalg.norm(xc.cpu().numpy() - x) / np.linalg.norm(x) < 1e-5
+    # the kernel-per-operation loop with the same polynomial: same iterates up to the summation order
+    xcu, infocu = efb.solver.pcg(K, b, x0=x0, free_mask=~known, tol=1e-8, maxiter=5000, fused=False)
+    assert infocu["converged"] and not infocu["fused"] and abs(infocu["iterations"] - infoc["iterations"]) <= 25, (infoc, infocu)
+    assert np.linalg.norm(xcu.cpu().numpy() - x) / np.linalg.norm(x) < 1e-5
+    xc2, infoc2 = efb.solver.pcg(K, b, x0=x0, free_mask=~known, tol=1e-8, maxiter=5000)
+    assert infoc2["iterations"] == infoc["iterations"] and np.array_equal(xc2.cpu().numpy(), xc.cpu().numpy())  # reproducible
     Ks = K.to_scipy()
     free = ~known
     rhs = (b - Ks @ (x0 * known))[free]
@@ -152,10 +164,10 @@ def test_pcg_elastic_cube(efb):
     # the fused iterations (3 kernels each, reductions folded by the last CTA) follow the kernel-per-operation loop up to
     # the summation order of the dot products (one-wave grids), and are reproducible run to run
     assert info["fused"]
-    x2, info2 = efb.solver.pcg(K, b, x0=x0, free_mask=~known, tol=1e-8, maxiter=5000, fused=False)
+    x2, info2 = efb.solver.pcg(K, b, x0=x0, free_mask=~known, tol=1e-8, maxiter=5000, fused=False, precond_degree=1)
     assert not info2["fused"] and abs(info2["iterations"] - info["iterations"]) <= 25
     assert np.linalg.norm(x2.cpu().numpy() - x) / np.linalg.norm(x) < 1e-5
-    x2b, info2b = efb.solver.pcg(K, b, x0=x0, free_mask=~known, tol=1e-8, maxiter=5000)
+    x2b, info2b = efb.solver.pcg(K, b, x0=x0, free_mask=~known, tol=1e-8, maxiter=5000, precond_degree=1)
     assert info2b["iterations"] == info["iterations"] and np.array_equal(x2b.cpu().numpy(), x)
     # opt-in: ONE persistent cooperative kernel per solve; same iterates as the three-kernel form up to summation order
     assert not info["persistent"]
