@@ -52,8 +52,8 @@ constexpr int kMmaTS = 72;                  // doubles per staged task: [k*3+l][
 constexpr int kMmaZero = 72;                // zero tail of a staging buffer
 constexpr int kMmaGE = 192;                 // doubles of the gradient table of one element: [p][l][b ^ swizzle(p)]
 constexpr int kMmaWarpBuf = 2 * kMmaGE;     // per-warp scratch: two tables (element e + 1 is written while e is read)
-constexpr int kMmaP2 = 12;                  // integration warps (16 warps per CTA: 128 registers per thread)
-constexpr int kMmaP3 = 3;                   // gather warps
+constexpr int kMmaP2 = 11;                  // integration warps (16 warps per CTA: 128 registers per thread)
+constexpr int kMmaP3 = 4;                   // gather warps
 constexpr int kMmaStages = 4;               // ring slots
 constexpr int kMmaThreads = (kMmaP2 + kMmaP3 + 1) * 32;
 

@@ -27,7 +27,7 @@ for w in $what; do
         > gpurun_out/${tag}_launches.log 2>&1
       tail -2 gpurun_out/${tag}_launches.log ;;
     full)
-      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'k_elastic|k_replay|k_fused' -s 6 -c 2 \
+      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-k_elastic|k_replay|k_assemble}" -s ${NCU_SKIP:-6} -c ${NCU_COUNT:-2} \
         -f -o gpurun_out/${tag}_full python bench.py --n 128 --steps 2 --warmup 3 --no-cpu --e2e-steps 1 --no-pf --no-solve --no-transient \
         > gpurun_out/${tag}_full.log 2>&1
       tail -2 gpurun_out/${tag}_full.log ;;
