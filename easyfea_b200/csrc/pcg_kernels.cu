@@ -42,9 +42,9 @@ struct EpiStore {
 };
 
 // y[r] = sum_k data[k] x[indices[k]] for local rows; LPR lanes cooperate on one row; returns the thread's part of x_row . y
-template <class IDX, int LPR, class EPI>
+template <class IDX, int LPR, class EPI, class VT = double>
 __device__ __forceinline__ double spmv_rows_epi(long long nrows, const IDX* __restrict__ indptr, const IDX* __restrict__ indices,
-                                                const double* __restrict__ data, const double* __restrict__ x,
+                                                const VT* __restrict__ data, const double* __restrict__ x,
                                                 const unsigned char* __restrict__ row_mask, EPI& epi) {
     const int lane = threadIdx.x % LPR;
     constexpr int RPB = kRedThreads / LPR;  // rows per CTA per pass
@@ -56,7 +56,7 @@ __device__ __forceinline__ double spmv_rows_epi(long long nrows, const IDX* __re
         double s = 0.0;
         if (live && (!row_mask || row_mask[r])) {
             const long long k0 = indptr[r], k1 = indptr[r + 1];
-            for (long long k = k0 + lane; k < k1; k += LPR) s += data[k] * x[indices[k]];
+            for (long long k = k0 + lane; k < k1; k += LPR) s += (double)data[k] * x[indices[k]];
         }
 #pragma unroll
         for (int off = LPR / 2; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off, LPR);
@@ -93,9 +93,9 @@ __global__ void __launch_bounds__(kRedThreads)
 // Software-pipelined form: the adjacency pointers and the first PF column ids of a lane's NEXT node are loaded while the
 // current node is processed, so the only dependent load left on a node's critical path is the gather of x (the plain
 // form pays adjptr -> adj -> x, three DRAM latencies, per node and is latency-bound at ~55 % of HBM bandwidth).
-template <int D, int LPN, int PF, class EPI>
+template <int D, int LPN, int PF, class EPI, class VT = double>
 __device__ __forceinline__ double spmv_nodes_pipe(long long n_nodes, const long long* __restrict__ adjptr, const int* __restrict__ adj,
-                                                  const double* __restrict__ data, const double* __restrict__ x,
+                                                  const VT* __restrict__ data, const double* __restrict__ x,
                                                   const unsigned char* __restrict__ row_mask, EPI& epi) {
     const int lane = threadIdx.x % LPN;
     constexpr int NPB = kRedThreads / LPN;  // nodes per CTA per pass
@@ -122,7 +122,7 @@ __device__ __forceinline__ double spmv_nodes_pipe(long long n_nodes, const long 
             na1 = adjptr[nn + 1];
         }
         const int rowlen = D * (int)(a1 - a0);
-        const double* blk = data + (long long)D * D * a0;
+        const VT* blk = data + (long long)D * D * a0;
         double xv[PF];
 #pragma unroll
         for (int k = 0; k < PF; ++k) {
@@ -143,7 +143,7 @@ __device__ __forceinline__ double spmv_nodes_pipe(long long n_nodes, const long 
             const int l = lane + LPN * k;
             if (l < rowlen) {
 #pragma unroll
-                for (int i = 0; i < D; ++i) s[i] += blk[i * rowlen + l] * xv[k];
+                for (int i = 0; i < D; ++i) s[i] += (double)blk[i * rowlen + l] * xv[k];
             }
         }
         if (rowlen > LPN * PF) {  // longer rows than the prefetch depth: the rest the plain way
@@ -153,7 +153,7 @@ __device__ __forceinline__ double spmv_nodes_pipe(long long n_nodes, const long 
                 const int c = l / D, j = l - c * D;
                 const double xr = x[(long long)cols[c] * D + j];
 #pragma unroll
-                for (int i = 0; i < D; ++i) s[i] += blk[i * rowlen + l] * xr;
+                for (int i = 0; i < D; ++i) s[i] += (double)blk[i * rowlen + l] * xr;
             }
         }
 #pragma unroll
@@ -669,9 +669,9 @@ struct EpiCheb {
 };
 
 // (2d) Chebyshev step k: waits for the neighbours' halo entries of z_k, t = A z_k, d_k, z_{k+1}; the last step publishes (r.z, r.r)
-template <int KIND, int A, int B>
+template <int KIND, int A, int B, class VT>
 __global__ void __launch_bounds__(kRedThreads, EFB_PCG_SPMV_MINB)
-    k_pcg_cheb(long long n, const void* __restrict__ indptr, const void* __restrict__ indices, const double* __restrict__ data,
+    k_pcg_cheb(long long n, const void* __restrict__ indptr, const void* __restrict__ indices, const VT* __restrict__ data,
                const double* __restrict__ zin, double* __restrict__ zout, const double* __restrict__ r, const double* __restrict__ inv_diag,
                double* __restrict__ d, const unsigned char* __restrict__ mask, double* __restrict__ partials, double c1, double c2, int which,
                int last, efb_pcg_peer P, unsigned long long ar_done, unsigned long long halo_wait) {
@@ -685,11 +685,11 @@ __global__ void __launch_bounds__(kRedThreads, EFB_PCG_SPMV_MINB)
     EpiCheb epi{r, inv_diag, zin, d, zout, (P.n_send > 0 && !last) ? P.push_id : nullptr, &P, c1, c2, which, 0.0, 0.0};
     if constexpr (KIND == 0) {
         if constexpr (A == 4)
-            spmv_rows_epi<int, B>(n, (const int*)indptr, (const int*)indices, data, zin, mask, epi);
+            spmv_rows_epi<int, B, EpiCheb, VT>(n, (const int*)indptr, (const int*)indices, data, zin, mask, epi);
         else
-            spmv_rows_epi<long long, B>(n, (const long long*)indptr, (const long long*)indices, data, zin, mask, epi);
+            spmv_rows_epi<long long, B, EpiCheb, VT>(n, (const long long*)indptr, (const long long*)indices, data, zin, mask, epi);
     } else {
-        spmv_nodes_pipe<A, B, EFB_SPMV_PF(B)>(n, (const long long*)indptr, (const int*)indices, data, zin, mask, epi);
+        spmv_nodes_pipe<A, B, EFB_SPMV_PF(B), EpiCheb, VT>(n, (const long long*)indptr, (const int*)indices, data, zin, mask, epi);
     }
     if (last) {
         double mine[2], total[2];
@@ -701,16 +701,23 @@ __global__ void __launch_bounds__(kRedThreads, EFB_PCG_SPMV_MINB)
     }
 }
 
-using ChebKernel = void (*)(long long, const void*, const void*, const double*, const double*, double*, const double*, const double*, double*,
+template <class VT>
+using ChebKernel = void (*)(long long, const void*, const void*, const VT*, const double*, double*, const double*, const double*, double*,
                             const unsigned char*, double*, double, double, int, int, efb_pcg_peer, unsigned long long, unsigned long long);
-template <int KIND, int A>
-static ChebKernel pcg_cheb_kernel(int lanes) {
+template <int KIND, int A, class VT>
+static ChebKernel<VT> pcg_cheb_kernel(int lanes) {
     switch (lanes) {
-        case 4: return k_pcg_cheb<KIND, A, 4>;
-        case 8: return k_pcg_cheb<KIND, A, 8>;
-        case 16: return k_pcg_cheb<KIND, A, 16>;
-        default: return k_pcg_cheb<KIND, A, 32>;
+        case 4: return k_pcg_cheb<KIND, A, 4, VT>;
+        case 8: return k_pcg_cheb<KIND, A, 8, VT>;
+        case 16: return k_pcg_cheb<KIND, A, 16, VT>;
+        default: return k_pcg_cheb<KIND, A, 32, VT>;
     }
+}
+
+// matrix values in single precision for the products INSIDE the polynomial preconditioner (any fixed symmetric operator is a
+// valid preconditioner; the outer product, the residual and every vector stay FP64)
+__global__ void k_cast_f32(long long n, const double* __restrict__ src, float* __restrict__ dst) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = (float)src[i];
 }
 
 // unfused building block of the same recurrence: d = c1 d + c2 D^-1 (r - t), z += d  (t = A z of the caller's product)
@@ -1324,8 +1331,16 @@ extern "C" int efb_pcg_cheb_update(int64_t n, const double* r, const double* t, 
     return check_launch("efb_pcg_cheb_update");
 }
 
-extern "C" int efb_pcg_iterate_cheb(const efb_pcg_system* sys, const efb_pcg_peer* peer, int n_iters, int64_t it0, int degree, double lmin,
-                                    double lmax, double* d_vec, void* stream) {
+extern "C" int efb_cast_f32(int64_t n, const double* src, float* dst, void* stream) {
+    if (n == 0) return 0;
+    const long long want = (n + 255) / 256;
+    k_cast_f32<<<(unsigned)(want < 4 * kRedBlocks ? want : 4 * kRedBlocks), 256, 0, as_stream(stream)>>>(n, src, dst);
+    return check_launch("efb_cast_f32");
+}
+
+template <class VT>
+static int pcg_iterate_cheb(const efb_pcg_system* sys, const efb_pcg_peer* peer, int n_iters, int64_t it0, int degree, double lmin,
+                            double lmax, double* d_vec, const VT* cheb_data, void* stream) {
     const efb_pcg_peer& P = *peer;
     if (P.world < 1 || P.world > EFB_MAX_RANKS || P.rank < 0 || P.rank >= P.world || P.n_send < 0 || P.n_send > EFB_MAX_RANKS ||
         P.n_recv < 0 || P.n_recv > EFB_MAX_RANKS) {
@@ -1356,13 +1371,14 @@ extern "C" int efb_pcg_iterate_cheb(const efb_pcg_system* sys, const efb_pcg_pee
         return 1;
     }
     SpmvKernel spmv_k;
-    ChebKernel cheb_k;
+    ChebKernel<VT> cheb_k;
     if (sys->kind == 1) {
         spmv_k = sys->dof_n == 1 ? pcg_spmv_kernel<1, 1>(sys->lanes) : sys->dof_n == 2 ? pcg_spmv_kernel<1, 2>(sys->lanes) : pcg_spmv_kernel<1, 3>(sys->lanes);
-        cheb_k = sys->dof_n == 1 ? pcg_cheb_kernel<1, 1>(sys->lanes) : sys->dof_n == 2 ? pcg_cheb_kernel<1, 2>(sys->lanes) : pcg_cheb_kernel<1, 3>(sys->lanes);
+        cheb_k = sys->dof_n == 1 ? pcg_cheb_kernel<1, 1, VT>(sys->lanes)
+                                 : sys->dof_n == 2 ? pcg_cheb_kernel<1, 2, VT>(sys->lanes) : pcg_cheb_kernel<1, 3, VT>(sys->lanes);
     } else {
         spmv_k = sys->index_bytes == 4 ? pcg_spmv_kernel<0, 4>(sys->lanes) : pcg_spmv_kernel<0, 8>(sys->lanes);
-        cheb_k = sys->index_bytes == 4 ? pcg_cheb_kernel<0, 4>(sys->lanes) : pcg_cheb_kernel<0, 8>(sys->lanes);
+        cheb_k = sys->index_bytes == 4 ? pcg_cheb_kernel<0, 4, VT>(sys->lanes) : pcg_cheb_kernel<0, 8, VT>(sys->lanes);
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -1419,7 +1435,7 @@ extern "C" int efb_pcg_iterate_cheb(const efb_pcg_system* sys, const efb_pcg_pee
                                                             1.0 / theta, P, it, ar_done, halo_done);
         if (timing) cudaEventRecord(ev[ne++], st);
         for (int j = 1; j < degree; ++j) {  // z_j in zb[(j-1) & 1] -> z_{j+1} in zb[j & 1]
-            cheb_k<<<g_cheb, kRedThreads, 0, st>>>(a.n, a.indptr, a.indices, a.data, zb[(j - 1) & 1], zb[j & 1], sys->r, sys->inv_diag, d_vec,
+            cheb_k<<<g_cheb, kRedThreads, 0, st>>>(a.n, a.indptr, a.indices, cheb_data, zb[(j - 1) & 1], zb[j & 1], sys->r, sys->inv_diag, d_vec,
                                                     a.mask, a.partials, c1[j], c2[j], 2 + (j & 1), j == degree - 1 ? 1 : 0, P, ar_done,
                                                     halo_done + (unsigned long long)j);
             if (timing) cudaEventRecord(ev[ne++], st);
@@ -1444,6 +1460,12 @@ extern "C" int efb_pcg_iterate_cheb(const efb_pcg_system* sys, const efb_pcg_pee
         delete[] ev;
     }
     return check_launch("efb_pcg_iterate_cheb");
+}
+
+extern "C" int efb_pcg_iterate_cheb(const efb_pcg_system* sys, const efb_pcg_peer* peer, int n_iters, int64_t it0, int degree, double lmin,
+                                    double lmax, double* d_vec, const float* data32, void* stream) {
+    if (data32) return pcg_iterate_cheb<float>(sys, peer, n_iters, it0, degree, lmin, lmax, d_vec, data32, stream);
+    return pcg_iterate_cheb<double>(sys, peer, n_iters, it0, degree, lmin, lmax, d_vec, sys->data, stream);
 }
 
 extern "C" int efb_pcg_iterate_cg2(const efb_pcg_system* sys, const efb_pcg_peer* peer, int n_iters, int64_t it0, void* stream) {

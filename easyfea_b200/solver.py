@@ -102,6 +102,10 @@ CHEB_POWER_ITERS = 10   # per solve: the matrix of a staggered / Newton loop cha
 # bound by the product itself and the polynomial's 1.1x products + heavier epilogue cost more than the saved reductions
 # (HEXA8 3 M dofs on one B200: 0.60 s against 0.49 s with plain Jacobi; TETRA4 2.6 M dofs per rank on two: 0.69 against 0.62 s)
 CHEB_MAX_NNZ = 32_000_000
+# the m - 1 products INSIDE the polynomial read the matrix values in single precision (efb_cast_f32 once per solve): a polynomial
+# in fl32(A) is still a fixed symmetric operator, i.e. a valid preconditioner, and those products move half the bytes; the outer
+# product, the residual, every vector and every dot product stay FP64.  With it the polynomial pays at every size.
+CHEB_FP32 = True
 CHEB_STALL_ITERS = 400  # outer iterations without a new minimum of |r|: the polynomial is dropped for plain Jacobi
 
 
@@ -153,7 +157,7 @@ def estimate_lmax(A: DeviceCsr, inv_diag, mask, comm=None, iters: int = CHEB_POW
 
 
 def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: int = None, check_every: int = 25, comm=None,
-        fused="auto", persistent: bool = False, single_reduction="auto", precond_degree="auto"):
+        fused="auto", persistent: bool = False, single_reduction="auto", precond_degree="auto", reuse_setup: bool = False):
     """Solve A x = b on the free dofs (free_mask True / 1 = unknown; other entries of x keep the values of x0).
 
     A holds the owned rows in LOCAL numbering `[owned | halo]` columns.  Stops when ||r|| <= tol * ||b - A x_known||
@@ -175,6 +179,8 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
     `precond_degree` = m: Chebyshev-Jacobi polynomial preconditioner of degree m - 1 in D^-1 A (m = 1: plain Jacobi); "auto" =
     CHEB_DEGREE unless the single-reduction or persistent form is forced.  Inside the fused iterations
     (`efb_pcg_iterate_cheb`) the m - 1 extra products cost one neighbour halo flag each and no all-reduce.
+    `reuse_setup=True`: the caller guarantees that `A` and the mask are the ones of its previous call with this flag (time
+    stepping on a constant matrix): the spectral bound and the single-precision copy of the values are taken from `A`.
     `fused=False` keeps
     one collective call per exchange (NCCL through torch.distributed) and one kernel per vector operation — the baseline
     the fused path is measured against (bench.py) and checked against (tests).
@@ -193,9 +199,13 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
             big = float(big.item())
         return big
 
+    if fused == "auto":
+        fused = bool(single_reduction is True or persistent) or largest_shard() <= FUSED_MAX_DOFS
     if precond_degree == "auto":  # an explicitly requested single-reduction / persistent form keeps plain Jacobi
-        if single_reduction is True or persistent:
+        if single_reduction is True or persistent or not fused:
             precond_degree = 1
+        elif CHEB_FP32:  # inner products on single-precision matrix values: a gain at every size (half the matrix traffic)
+            precond_degree = CHEB_DEGREE
         else:
             t = torch.tensor([float(A.nnz)], dtype=torch.float64, device=dev)
             if comm is not None:
@@ -204,8 +214,6 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
     degree = max(1, int(precond_degree))
     if degree > 1:
         single_reduction, persistent = False, False
-    if fused == "auto":
-        fused = bool(single_reduction is True or persistent) or largest_shard() <= FUSED_MAX_DOFS
     if single_reduction == "auto":
         single_reduction = bool(fused) and not persistent and tol >= 1e-10 and largest_shard() <= SINGLE_REDUCTION_MAX_DOFS
     single_reduction = bool(single_reduction) and bool(fused)
@@ -260,10 +268,24 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
 
     lmin = lmax = None
     if degree > 1:
-        lmax = CHEB_SAFETY * estimate_lmax(A, inv_diag, mask, comm)
+        cache = getattr(A, "_cheb_setup", None) if reuse_setup else None
+        if cache is not None and cache[0] == (A.data.data_ptr(), nrows):
+            lmax = cache[1]
+        else:
+            lmax = CHEB_SAFETY * estimate_lmax(A, inv_diag, mask, comm)
+            cache = None
         lmin = lmax / CHEB_RATIO
         theta, coefs = cheb_coefficients(degree, lmin, lmax)
         d_vec = torch.zeros(nrows, dtype=torch.float64, device=dev)
+        data32 = None
+        if CHEB_FP32 and ws is not None:
+            if cache is not None and cache[2] is not None:
+                data32 = cache[2]
+            else:
+                data32 = torch.empty(A.data.numel(), dtype=torch.float32, device=dev)
+                _lib.call("efb_cast_f32", A.data.numel(), dv.ptr(A.data), dv.ptr(data32), st())
+        if reuse_setup:
+            A._cheb_setup = ((A.data.data_ptr(), nrows), lmax, data32)
         z_full = ws.zb[0] if ws is not None else torch.zeros(n_glob, dtype=torch.float64, device=dev)
 
         def cheb_apply(r_vec):
@@ -348,7 +370,7 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
             if degree > 1:
                 k = min(int(check_every), maxiter - it)
                 _lib.call("efb_pcg_iterate_cheb", ctypes.byref(S), ctypes.byref(ws.peer), k, it, degree, float(lmin), float(lmax), dv.ptr(d_vec),
-                          st())
+                          dv.ptr(data32), st())
                 rr, err, _ = ws.status()
                 ws.advance(k, 2, degree)
                 it += k
@@ -422,4 +444,4 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
     rel = (rr / bnorm2) ** 0.5
     return x.clone(), {"iterations": it, "rel_residual": rel, "converged": rel <= tol, "rhs_norm": bnorm2 ** 0.5, "fused": ws is not None,
                        "persistent": ws is not None and use_persistent, "single_reduction": ws is not None and bool(single_reduction),
-                       "precond_degree": degree, "lmax": lmax}
+                       "precond_degree": degree, "lmax": lmax, "precond_fp32": bool(degree > 1 and ws is not None and CHEB_FP32)}

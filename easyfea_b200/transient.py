@@ -215,7 +215,8 @@ class TransientSolve:
         _apply(x0, dofs, torch.zeros_like(vals) if explicit else vals)
         s.refresh_halo(x0, d)
         x, info = pcg(A, b, x0=x0, free_mask=mask, tol=self.pcg_tol, maxiter=self.pcg_maxiter, comm=s.comm(d), fused=self.pcg_fused,
-                      persistent=self.pcg_persistent, single_reduction=self.pcg_single_reduction, precond_degree=self.pcg_precond_degree)
+                      persistent=self.pcg_persistent, single_reduction=self.pcg_single_reduction, precond_degree=self.pcg_precond_degree,
+                      reuse_setup=True)  # the system matrix of a scheme is built once (`_matrix`) and the mask is the scheme's
         self.info = info
         x0[:n_own] = x
         s.refresh_halo(x0, d)

@@ -38,14 +38,16 @@ def main():
     ap.add_argument("--cfg", type=int, default=3)
     ap.add_argument("--n", type=int, default=300)
     ap.add_argument("--degrees", default="1,4")
-    ap.add_argument("--safety", default="1.1")
+    ap.add_argument("--safety", default="1.25")
+    ap.add_argument("--fp32", default="1")
     args = ap.parse_args()
     for deg in [int(v) for v in args.degrees.split(",")]:
         for saf in [float(v) for v in args.safety.split(",")] if deg > 1 else [1.1]:
             solver.CHEB_SAFETY = saf
+            solver.CHEB_FP32 = bool(int(args.fp32))
             simu = build(args.cfg, args.n)
             simu.pcg_precond_degree = deg
-            out = {"cfg": args.cfg, "n": args.n, "degree": deg, "safety": saf, "iters": []}
+            out = {"cfg": args.cfg, "n": args.n, "degree": deg, "safety": saf, "fp32": solver.CHEB_FP32, "iters": []}
             for k in range(3):
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()

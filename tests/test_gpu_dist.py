@@ -67,7 +67,9 @@ def _worker(rank, world, port, out):
         assert info6["converged"], info6
         es.u.zero_()
         es.pcg_fused = False  # NCCL send/recv + all-reduce per iteration: same iterates up to summation order
+        es.pcg_precond_degree = info["precond_degree"]  # the same polynomial as the fused solve it is compared with
         u3, info3 = es.solve(tol=1e-10)
+        es.pcg_precond_degree = "auto"
         assert info3["converged"] and not info3["fused"], info3
         u_nccl = u3[: part.n_owned * 3].cpu().numpy()
         assert abs(info3["iterations"] - info["iterations"]) <= 25, (info, info3)

@@ -148,8 +148,10 @@ def test_pcg_elastic_cube(efb):
     x = x.cpu().numpy()
     assert np.linalg.norm(xc.cpu().numpy() - x) / np.linalg.norm(x) < 1e-5
     # the kernel-per-operation loop with the same polynomial: same iterates up to the summation order
-    xcu, infocu = efb.solver.pcg(K, b, x0=x0, free_mask=~known, tol=1e-8, maxiter=5000, fused=False)
+    # (FP64 matrix values inside the polynomial there, single precision in the fused kernels: the same iteration counts)
+    xcu, infocu = efb.solver.pcg(K, b, x0=x0, free_mask=~known, tol=1e-8, maxiter=5000, fused=False, precond_degree=efb.solver.CHEB_DEGREE)
     assert infocu["converged"] and not infocu["fused"] and abs(infocu["iterations"] - infoc["iterations"]) <= 25, (infoc, infocu)
+    assert infoc["precond_fp32"] and not infocu["precond_fp32"]
     assert np.linalg.norm(xcu.cpu().numpy() - x) / np.linalg.norm(x) < 1e-5
     xc2, infoc2 = efb.solver.pcg(K, b, x0=x0, free_mask=~known, tol=1e-8, maxiter=5000)
     assert infoc2["iterations"] == infoc["iterations"] and np.array_equal(xc2.cpu().numpy(), xc.cpu().numpy())  # reproducible
