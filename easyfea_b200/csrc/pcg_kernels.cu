@@ -1394,7 +1394,8 @@ static int pcg_iterate_cheb(const efb_pcg_system* sys, const efb_pcg_peer* peer,
             const int cap = (int)max((long long)sms, min((long long)kRedBlocks, want));
             g_xr = min(g_xr, cap);
             g_p = min(g_p, cap);
-            const int cap_s = max(cap, (int)min((long long)kRedBlocks, (a.n * sys->lanes + kRedThreads - 1) / kRedThreads / 2));
+            static const int spmv_div = [] { const char* e = getenv("EFB_PCG_SPMV_DIV"); return e ? max(atoi(e), 1) : 2; }();
+            const int cap_s = max(cap, (int)min((long long)kRedBlocks, (a.n * sys->lanes + kRedThreads - 1) / kRedThreads / spmv_div));
             g_spmv = min(g_spmv, cap_s);
             g_cheb = min(g_cheb, cap_s);
         }
