@@ -109,7 +109,7 @@ SIGNATURES = {
     "efb_pcg_ctrl_layout": [_I32P],
     "efb_pcg_iterate": [ctypes.POINTER(EfbPcgSystem), ctypes.POINTER(EfbPcgPeer), ctypes.c_int, c_i64, c_vp],
     "efb_pcg_iterate_cheb": [ctypes.POINTER(EfbPcgSystem), ctypes.POINTER(EfbPcgPeer), ctypes.c_int, c_i64, ctypes.c_int, c_f64, c_f64,
-                             c_vp, c_vp, c_vp],
+                             c_vp, c_vp, ctypes.c_int, c_vp],
     "efb_cast_f32": [c_i64, c_vp, c_vp, c_vp],
     "efb_pcg_cheb_update": [c_i64, c_vp, c_vp, c_vp, c_f64, c_f64, c_vp, c_vp, c_vp],
     "efb_pcg_iterate_cg2": [ctypes.POINTER(EfbPcgSystem), ctypes.POINTER(EfbPcgPeer), ctypes.c_int, c_i64, c_vp],

@@ -10,6 +10,12 @@
 
 #include "common.cuh"
 
+#ifndef EFB_SPMV_REST_UNROLL
+#define EFB_SPMV_REST_UNROLL 2  // columns of a row beyond the prefetched ones: loads of this many steps are in flight together
+#endif
+#define EFB_STR_(x) #x
+#define EFB_UNROLL_N(n) _Pragma(EFB_STR_(unroll n))
+
 namespace efb {
 
 constexpr int kRedBlocks = 1184;  // 148 SMs x 8: fixed grid for every reduction producer
@@ -148,12 +154,110 @@ __device__ __forceinline__ double spmv_nodes_pipe(long long n_nodes, const long 
         }
         if (rowlen > LPN * PF) {  // longer rows than the prefetch depth: the rest the plain way
             const int* cols = adj + a0;
-#pragma unroll 2
+            EFB_UNROLL_N(EFB_SPMV_REST_UNROLL)
             for (int l = lane + LPN * PF; l < rowlen; l += LPN) {
                 const int c = l / D, j = l - c * D;
                 const double xr = x[(long long)cols[c] * D + j];
 #pragma unroll
                 for (int i = 0; i < D; ++i) s[i] += (double)blk[i * rowlen + l] * xr;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int off = LPN / 2; off > 0; off >>= 1) s[i] += __shfl_down_sync(0xffffffffu, s[i], off, LPN);
+        if (n < n_nodes && lane == 0) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                const long long r = n * D + i;
+                const double v = (!row_mask || row_mask[r]) ? s[i] : 0.0;
+                local += epi(r, v);
+            }
+        }
+        n = nn;
+        a0 = na0;
+        a1 = na1;
+#pragma unroll
+        for (int k = 0; k < PF; ++k) col[k] = ncol[k];
+    }
+    return local;
+}
+
+// Block form of the same product: a lane takes whole NEIGHBOUR NODES (c = lane, lane + LPN, ...), i.e. the D x D block of the
+// matrix and the D entries of x of that neighbour: D (D + 1) loads per step instead of D + 1 — more bytes in flight per lane and
+// wider contiguous pieces per row, which is what the single-precision values of the polynomial steps need (with one column per
+// lane a 4-lane group reads 16 bytes of a row per instruction: the step is bound by requests, not bytes, and the halved matrix
+// traffic buys nothing).  Same software pipeline: the neighbour ids of the lane's NEXT node travel while this one is processed.
+template <int D, int LPN, int PF, class EPI, class VT>
+__device__ __forceinline__ double spmv_nodes_blk(long long n_nodes, const long long* __restrict__ adjptr, const int* __restrict__ adj,
+                                                 const VT* __restrict__ data, const double* __restrict__ x,
+                                                 const unsigned char* __restrict__ row_mask, EPI& epi) {
+    const int lane = threadIdx.x % LPN;
+    constexpr int NPB = kRedThreads / LPN;  // nodes per CTA per pass
+    const long long stride = (long long)gridDim.x * NPB;
+    double local = 0.0;
+    long long n = (long long)blockIdx.x * NPB + threadIdx.x / LPN;
+    long long a0 = 0, a1 = 0;
+    if (n < n_nodes) {
+        a0 = adjptr[n];
+        a1 = adjptr[n + 1];
+    }
+    int col[PF];
+#pragma unroll
+    for (int k = 0; k < PF; ++k) {
+        const int c = lane + LPN * k;
+        col[k] = (c < (int)(a1 - a0)) ? adj[a0 + c] : 0;
+    }
+    for (long long base = (long long)blockIdx.x * NPB; base < n_nodes; base += stride) {  // CTA-uniform trip count
+        const long long nn = n + stride;
+        long long na0 = 0, na1 = 0;
+        if (nn < n_nodes) {
+            na0 = adjptr[nn];
+            na1 = adjptr[nn + 1];
+        }
+        const int deg = (int)(a1 - a0), rowlen = D * deg;
+        const VT* blk = data + (long long)D * D * a0;
+        double xv[PF][D];
+        VT bv[PF][D][D];
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const int c = lane + LPN * k;
+            const bool on = c < deg;
+            const double* xp = x + (long long)col[k] * D;
+#pragma unroll
+            for (int j = 0; j < D; ++j) xv[k][j] = on ? xp[j] : 0.0;
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = 0; j < D; ++j) bv[k][i][j] = on ? blk[i * rowlen + c * D + j] : (VT)0;
+        }
+        int ncol[PF];
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const int c = lane + LPN * k;
+            ncol[k] = (c < (int)(na1 - na0)) ? adj[na0 + c] : 0;
+        }
+        double s[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) s[i] = 0.0;
+#pragma unroll
+        for (int k = 0; k < PF; ++k)
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = 0; j < D; ++j) s[i] += (double)bv[k][i][j] * xv[k][j];
+        if (deg > LPN * PF) {  // more neighbours than the prefetch depth: the rest the plain way
+            const int* cols = adj + a0;
+#pragma unroll 2
+            for (int c = lane + LPN * PF; c < deg; c += LPN) {
+                const double* xp = x + (long long)cols[c] * D;
+                double xr[D];
+#pragma unroll
+                for (int j = 0; j < D; ++j) xr[j] = xp[j];
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int j = 0; j < D; ++j) s[i] += (double)blk[i * rowlen + c * D + j] * xr[j];
             }
         }
 #pragma unroll
@@ -669,8 +773,19 @@ struct EpiCheb {
 };
 
 // (2d) Chebyshev step k: waits for the neighbours' halo entries of z_k, t = A z_k, d_k, z_{k+1}; the last step publishes (r.z, r.r)
+// block form of the polynomial steps: two neighbour blocks prefetched per lane at 64 registers (4 CTAs per SM) — A/B on B200 at the
+// phase-field sizes (profiles/README.md): TETRA4 d=3 420 -> 320 us per step, TRI3 d=2 77 -> 74 us
+#ifndef EFB_CHEB_BLK_PF
+#define EFB_CHEB_BLK_PF 2
+#endif
+#ifndef EFB_PCG_CHEB_MINB
+#define EFB_PCG_CHEB_MINB 4
+#endif
+#ifndef EFB_PCG_CHEB_MINB
+#define EFB_PCG_CHEB_MINB EFB_PCG_SPMV_MINB
+#endif
 template <int KIND, int A, int B, class VT>
-__global__ void __launch_bounds__(kRedThreads, EFB_PCG_SPMV_MINB)
+__global__ void __launch_bounds__(kRedThreads, EFB_PCG_CHEB_MINB)
     k_pcg_cheb(long long n, const void* __restrict__ indptr, const void* __restrict__ indices, const VT* __restrict__ data,
                const double* __restrict__ zin, double* __restrict__ zout, const double* __restrict__ r, const double* __restrict__ inv_diag,
                double* __restrict__ d, const unsigned char* __restrict__ mask, double* __restrict__ partials, double c1, double c2, int which,
@@ -689,7 +804,10 @@ __global__ void __launch_bounds__(kRedThreads, EFB_PCG_SPMV_MINB)
         else
             spmv_rows_epi<long long, B, EpiCheb, VT>(n, (const long long*)indptr, (const long long*)indices, data, zin, mask, epi);
     } else {
-        spmv_nodes_pipe<A, B, EFB_SPMV_PF(B), EpiCheb, VT>(n, (const long long*)indptr, (const int*)indices, data, zin, mask, epi);
+        if constexpr (sizeof(VT) == 4)  // single-precision values: whole neighbour blocks per lane (EFB_CHEB_BLK_PF steps prefetched)
+            spmv_nodes_blk<A, B, EFB_CHEB_BLK_PF, EpiCheb, VT>(n, (const long long*)indptr, (const int*)indices, data, zin, mask, epi);
+        else
+            spmv_nodes_pipe<A, B, EFB_SPMV_PF(B), EpiCheb, VT>(n, (const long long*)indptr, (const int*)indices, data, zin, mask, epi);
     }
     if (last) {
         double mine[2], total[2];
@@ -707,6 +825,7 @@ using ChebKernel = void (*)(long long, const void*, const void*, const VT*, cons
 template <int KIND, int A, class VT>
 static ChebKernel<VT> pcg_cheb_kernel(int lanes) {
     switch (lanes) {
+        case 2: return k_pcg_cheb<KIND, A, 2, VT>;
         case 4: return k_pcg_cheb<KIND, A, 4, VT>;
         case 8: return k_pcg_cheb<KIND, A, 8, VT>;
         case 16: return k_pcg_cheb<KIND, A, 16, VT>;
@@ -1340,7 +1459,7 @@ extern "C" int efb_cast_f32(int64_t n, const double* src, float* dst, void* stre
 
 template <class VT>
 static int pcg_iterate_cheb(const efb_pcg_system* sys, const efb_pcg_peer* peer, int n_iters, int64_t it0, int degree, double lmin,
-                            double lmax, double* d_vec, const VT* cheb_data, void* stream) {
+                            double lmax, double* d_vec, const VT* cheb_data, int cheb_lanes, void* stream) {
     const efb_pcg_peer& P = *peer;
     if (P.world < 1 || P.world > EFB_MAX_RANKS || P.rank < 0 || P.rank >= P.world || P.n_send < 0 || P.n_send > EFB_MAX_RANKS ||
         P.n_recv < 0 || P.n_recv > EFB_MAX_RANKS) {
@@ -1374,8 +1493,11 @@ static int pcg_iterate_cheb(const efb_pcg_system* sys, const efb_pcg_peer* peer,
     ChebKernel<VT> cheb_k;
     if (sys->kind == 1) {
         spmv_k = sys->dof_n == 1 ? pcg_spmv_kernel<1, 1>(sys->lanes) : sys->dof_n == 2 ? pcg_spmv_kernel<1, 2>(sys->lanes) : pcg_spmv_kernel<1, 3>(sys->lanes);
-        cheb_k = sys->dof_n == 1 ? pcg_cheb_kernel<1, 1, VT>(sys->lanes)
-                                 : sys->dof_n == 2 ? pcg_cheb_kernel<1, 2, VT>(sys->lanes) : pcg_cheb_kernel<1, 3, VT>(sys->lanes);
+        static const int cheb_lanes_env = [] { const char* e = getenv("EFB_CHEB_LANES"); return e ? atoi(e) : 0; }();  // dev/tuning knob
+        // block form (single-precision values): few lanes per node — A/B on B200: TRI3 d=2 (7 neighbours) 63 us with 2 lanes, 74 with
+        // 4, 120 with 8; TETRA4 d=3 (15 neighbours) 288 us with 4, 321 with 2, 325 with 8, 521 with 16 (solver.cheb_lanes_per_node)
+        const int cl = cheb_lanes_env > 0 ? cheb_lanes_env : (cheb_lanes > 0 ? cheb_lanes : (sizeof(VT) == 4 ? 4 : sys->lanes));
+        cheb_k = sys->dof_n == 1 ? pcg_cheb_kernel<1, 1, VT>(cl) : sys->dof_n == 2 ? pcg_cheb_kernel<1, 2, VT>(cl) : pcg_cheb_kernel<1, 3, VT>(cl);
     } else {
         spmv_k = sys->index_bytes == 4 ? pcg_spmv_kernel<0, 4>(sys->lanes) : pcg_spmv_kernel<0, 8>(sys->lanes);
         cheb_k = sys->index_bytes == 4 ? pcg_cheb_kernel<0, 4, VT>(sys->lanes) : pcg_cheb_kernel<0, 8, VT>(sys->lanes);
@@ -1464,9 +1586,13 @@ static int pcg_iterate_cheb(const efb_pcg_system* sys, const efb_pcg_peer* peer,
 }
 
 extern "C" int efb_pcg_iterate_cheb(const efb_pcg_system* sys, const efb_pcg_peer* peer, int n_iters, int64_t it0, int degree, double lmin,
-                                    double lmax, double* d_vec, const float* data32, void* stream) {
-    if (data32) return pcg_iterate_cheb<float>(sys, peer, n_iters, it0, degree, lmin, lmax, d_vec, data32, stream);
-    return pcg_iterate_cheb<double>(sys, peer, n_iters, it0, degree, lmin, lmax, d_vec, sys->data, stream);
+                                    double lmax, double* d_vec, const float* data32, int cheb_lanes, void* stream) {
+    if (cheb_lanes != 0 && cheb_lanes != 2 && cheb_lanes != 4 && cheb_lanes != 8 && cheb_lanes != 16 && cheb_lanes != 32) {
+        set_error("efb_pcg_iterate_cheb: cheb_lanes must be 0 (default), 2, 4, 8, 16 or 32");
+        return 1;
+    }
+    if (data32) return pcg_iterate_cheb<float>(sys, peer, n_iters, it0, degree, lmin, lmax, d_vec, data32, cheb_lanes, stream);
+    return pcg_iterate_cheb<double>(sys, peer, n_iters, it0, degree, lmin, lmax, d_vec, sys->data, 0, stream);
 }
 
 extern "C" int efb_pcg_iterate_cg2(const efb_pcg_system* sys, const efb_pcg_peer* peer, int n_iters, int64_t it0, void* stream) {

@@ -45,6 +45,18 @@ def lanes_per_node(nnz: int, nrows: int) -> int:
     return 32
 
 
+def cheb_lanes_per_node(nnz: int, nrows: int, dof_n: int) -> int:
+    """lanes per node of the BLOCK form of the node product (the polynomial steps on single-precision values: a lane takes whole
+    neighbour blocks).  Measured on B200 at the phase-field sizes: TRI3 d=2 (7 neighbours) 63 us per step with 2 lanes, 74 with
+    4, 120 with 8; TETRA4 d=3 (15 neighbours) 288 us with 4, 321 with 2, 325 with 8."""
+    deg = nnz / max(nrows, 1) / max(dof_n, 1)
+    if deg <= 10:
+        return 2
+    if deg <= 40:
+        return 4
+    return 8
+
+
 def spmv(A: DeviceCsr, x: torch.Tensor, y: torch.Tensor = None, row_offset: int = 0, mask=None, partials=None):
     nrows = A.indptr.numel() - 1
     if y is None:
@@ -370,7 +382,7 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
             if degree > 1:
                 k = min(int(check_every), maxiter - it)
                 _lib.call("efb_pcg_iterate_cheb", ctypes.byref(S), ctypes.byref(ws.peer), k, it, degree, float(lmin), float(lmax), dv.ptr(d_vec),
-                          dv.ptr(data32), st())
+                          dv.ptr(data32), cheb_lanes_per_node(A.nnz, nrows, S.dof_n) if (S.kind == 1 and data32 is not None) else 0, st())
                 rr, err, _ = ws.status()
                 ws.advance(k, 2, degree)
                 it += k

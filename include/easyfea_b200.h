@@ -325,10 +325,11 @@ int efb_pcg_iterate(const efb_pcg_system* sys, const efb_pcg_peer* peer, int n_i
  * efb_pcg_iterate.  Before iteration 0 the caller puts p_0 = z_0 = q(D^-1 A) D^-1 r_0 (owned + halo) in p buffer 0 and r.z in
  * the control block.  The caller advances ar_seq by 2*n_iters and halo_seq by degree*n_iters afterwards. */
 int efb_pcg_iterate_cheb(const efb_pcg_system* sys, const efb_pcg_peer* peer, int n_iters, int64_t it0, int degree, double lmin,
-                         double lmax, double* d_vec, const float* data32, void* stream);
+                         double lmax, double* d_vec, const float* data32, int cheb_lanes, void* stream);
 /* data32 (same layout as sys->data, or NULL): the matrix values in single precision for the products INSIDE the polynomial — half
  * the matrix traffic of degree - 1 of the degree products of an iteration.  A polynomial in fl32(A) is still a fixed symmetric
- * operator, hence a valid preconditioner; the outer product, residuals, vectors and dot products stay FP64. */
+ * operator, hence a valid preconditioner; the outer product, residuals, vectors and dot products stay FP64.  Those products use
+ * the block form of the node product (a lane takes whole neighbour blocks) with cheb_lanes lanes per node (0 = 4). */
 int efb_cast_f32(int64_t n, const double* src, float* dst, void* stream);
 /* unfused building block of the same recurrence: d = c1 d + c2 D^-1 (r - t), z += d; t = A z of the caller (NULL: 0) */
 int efb_pcg_cheb_update(int64_t n, const double* r, const double* t, const double* inv_diag, double c1, double c2, double* d, double* z,

@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")/.."
 name=$1; shift
 tmp=$(mktemp -d)
-for f in api elem_kernels pf_kernels csr_kernels pcg_kernels post_kernels; do
+for f in api elem_kernels pf_kernels csr_kernels pcg_kernels post_kernels fused_kernels fused_mma; do
   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xptxas -v "$@" -c easyfea_b200/csrc/$f.cu -o $tmp/$f.o 2> $tmp/$f.log &
 done
 wait
