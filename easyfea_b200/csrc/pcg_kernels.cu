@@ -10,6 +10,9 @@
 
 #include "common.cuh"
 
+#ifndef EFB_SPMV_MINB
+#define EFB_SPMV_MINB 4  // resident CTAs per SM of the product kernels: the block form wants 64 registers
+#endif
 #ifndef EFB_SPMV_REST_UNROLL
 #define EFB_SPMV_REST_UNROLL 2  // columns of a row beyond the prefetched ones: loads of this many steps are in flight together
 #endif
@@ -287,16 +290,22 @@ __device__ __forceinline__ double spmv_nodes_blk(long long n_nodes, const long l
 #define EFB_SPMV_PF(LPN) ((LPN) == 32 ? 3 : 2)
 #endif
 
+// the node product every kernel uses: block form (a lane takes whole neighbour blocks), one step prefetched for D = 3, two for
+// D <= 2 (A/B on B200 at 64 registers / 4 CTAs per SM, profiles/README.md: TETRA4 d=3 454 -> 331 us = 6.1 TB/s, TRI3 d=2 76 -> 69 us)
 template <int D, int LPN>
 __device__ __forceinline__ double spmv_nodes(long long n_nodes, const long long* __restrict__ adjptr, const int* __restrict__ adj,
                                              const double* __restrict__ data, const double* __restrict__ x, long long x_row_offset,
                                              const unsigned char* __restrict__ row_mask, double* __restrict__ y, bool want_dot) {
     EpiStore epi{x, x_row_offset, y, want_dot};
+#ifdef EFB_SPMV_COLUMN_FORM
     return spmv_nodes_pipe<D, LPN, EFB_SPMV_PF(LPN)>(n_nodes, adjptr, adj, data, x, row_mask, epi);
+#else
+    return spmv_nodes_blk<D, LPN, (D == 3 ? 1 : 2), EpiStore, double>(n_nodes, adjptr, adj, data, x, row_mask, epi);
+#endif
 }
 
 template <int D, int LPN>
-__global__ void __launch_bounds__(kRedThreads, 6)  // bound by loads in flight: 6 resident CTAs beat 5 with 8 more registers
+__global__ void __launch_bounds__(kRedThreads, EFB_SPMV_MINB)  // block form: 64 registers (4 CTAs per SM) hold a whole neighbour block per step
     k_spmv_node(long long n_nodes, const long long* __restrict__ adjptr, const int* __restrict__ adj, const double* __restrict__ data,
                 const double* __restrict__ x, long long x_row_offset, const unsigned char* __restrict__ row_mask, double* __restrict__ y,
                 double* __restrict__ dot_partials) {
@@ -325,6 +334,7 @@ static int launch_spmv_node(long long n_nodes, const long long* adjptr, const in
         k_spmv_node<D, L><<<g, kRedThreads, 0, st>>>(n_nodes, adjptr, adj, data, x, x_row_offset, row_mask, y, partials); \
     }
     switch (lpn) {
+        case 2: EFB_SPMVN(2); break;
         case 4: EFB_SPMVN(4); break;
         case 8: EFB_SPMVN(8); break;
         case 16: EFB_SPMVN(16); break;
@@ -571,7 +581,7 @@ __device__ __forceinline__ bool publish_reduction(const efb_pcg_peer& P, PcgCtrl
 }
 
 #ifndef EFB_PCG_SPMV_MINB
-#define EFB_PCG_SPMV_MINB 6  // the SpMV is bound by loads in flight: 6 resident CTAs (<= 40 registers) like the standalone kernel
+#define EFB_PCG_SPMV_MINB EFB_SPMV_MINB  // like the standalone kernel
 #endif
 struct SpmvArgs {  // host-side bundle only; the kernels take plain __restrict__ pointers (alias analysis, load batching)
     long long n;  // rows (CSR) or nodes (node blocks)
@@ -853,6 +863,7 @@ __global__ void k_cheb_update(long long n, const double* __restrict__ r, const d
 template <int KIND, int A>
 static SpmvKernel pcg_spmv_kernel(int lanes) {
     switch (lanes) {
+        case 2: return k_pcg_spmv<KIND, A, 2>;
         case 4: return k_pcg_spmv<KIND, A, 4>;
         case 8: return k_pcg_spmv<KIND, A, 8>;
         case 16: return k_pcg_spmv<KIND, A, 16>;
@@ -1047,6 +1058,7 @@ using PersistentKernel = void (*)(long long, const long long*, const int*, const
 template <int D>
 static PersistentKernel pcg_persistent_kernel(int lanes) {
     switch (lanes) {
+        case 2: return k_pcg_persistent<D, 2>;
         case 4: return k_pcg_persistent<D, 4>;
         case 8: return k_pcg_persistent<D, 8>;
         case 16: return k_pcg_persistent<D, 16>;
@@ -1233,6 +1245,7 @@ using Cg2SpmvKernel = void (*)(long long, const void*, const void*, const double
 template <int KIND, int A>
 static Cg2SpmvKernel cg2_spmv_kernel(int lanes) {
     switch (lanes) {
+        case 2: return k_cg2_spmv<KIND, A, 2>;
         case 4: return k_cg2_spmv<KIND, A, 4>;
         case 8: return k_cg2_spmv<KIND, A, 8>;
         case 16: return k_cg2_spmv<KIND, A, 16>;

@@ -27,22 +27,21 @@ def lanes_per_row(nnz: int, nrows: int) -> int:
     return 32
 
 
-def lanes_per_node(nnz: int, nrows: int) -> int:
-    """lanes cooperating on one node of the node-block product.  Measured on B200 (profiles/README.md, lanes A/B): few lanes
-    per node keep more independent nodes in flight per warp and let the two prefetched steps cover most of a short row —
-    TETRA4 d=3 (45 entries per row) 2.9 TB/s with 32 lanes, 4.7 TB/s with 8; HEXA8 d=1 (27) 2.8 -> 4.6 TB/s with 4."""
+def lanes_per_node(nnz: int, nrows: int, dof_n: int = 1) -> int:
+    """lanes cooperating on one node of the node-block product (block form: a lane takes whole neighbour blocks, so the count
+    follows the number of NEIGHBOURS, not the row length).  Measured on B200 at the phase-field sizes (profiles/README.md):
+    TRI3 d=2 (7 neighbours) 69-72 us with 2 or 4 lanes, 88-97 with 8; TETRA4 d=3 (15) 331 us with 4 or 8, 424 with 2;
+    HEXA8 d=3 (27): 4 beats 8 and 2 on the polynomial steps."""
     import os
 
     if os.environ.get("EFB_SPMV_LANES"):  # dev/tuning knob
         return int(os.environ["EFB_SPMV_LANES"])
-    avg = nnz / max(nrows, 1)
-    if avg <= 32:
+    deg = nnz / max(nrows, 1) / max(dof_n, 1)
+    if deg <= 10:
+        return 2
+    if deg <= 40:
         return 4
-    if avg <= 128:
-        return 8
-    if avg <= 384:
-        return 16
-    return 32
+    return 8
 
 
 def cheb_lanes_per_node(nnz: int, nrows: int, dof_n: int) -> int:
@@ -66,7 +65,7 @@ def spmv(A: DeviceCsr, x: torch.Tensor, y: torch.Tensor = None, row_offset: int 
         adjptr, adj, d, max_deg = ng  # node-block product: the column structure is read from the node adjacency
         n_nodes = nrows // d
         _lib.call("efb_spmv_nodeblock", n_nodes, d, dv.ptr(adjptr), dv.ptr(adj), dv.ptr(A.data), dv.ptr(x), int(row_offset),
-                  dv.ptr(mask), dv.ptr(y), dv.ptr(partials), lanes_per_node(A.nnz, nrows), dv.stream_ptr())
+                  dv.ptr(mask), dv.ptr(y), dv.ptr(partials), lanes_per_node(A.nnz, nrows, d), dv.stream_ptr())
         return y
     _lib.call("efb_spmv_csr", nrows, A.index_bytes, dv.ptr(A.indptr), dv.ptr(A.indices), dv.ptr(A.data), dv.ptr(x), int(row_offset),
               dv.ptr(mask), dv.ptr(y), dv.ptr(partials), lanes_per_row(A.nnz, nrows), dv.stream_ptr())
@@ -81,7 +80,7 @@ def _system_struct(A: DeviceCsr, nrows, mask, inv_diag, x, r, z, Ap, partials) -
         adjptr, adj, d, max_deg = ng
         S.kind, S.dof_n, S.index_bytes = 1, d, 0
         S.indptr, S.indices = adjptr.data_ptr(), adj.data_ptr()
-        S.lanes = lanes_per_node(A.nnz, nrows)
+        S.lanes = lanes_per_node(A.nnz, nrows, d)
     else:
         S.kind, S.dof_n, S.index_bytes = 0, 0, A.index_bytes
         S.indptr, S.indices = A.indptr.data_ptr(), A.indices.data_ptr()

@@ -233,7 +233,7 @@ int efb_assemble_elastic_mma_smem(int t_cap, int rec_words, int pw_max);
  * efb_pcg_partials_size() doubles of partials, efb_pcg_reduce folds them (deterministic). */
 int efb_pcg_partials_size(void);
 /* y[r] = sum_k data[k] x[indices[k]] for local rows r < nrows (masked rows give 0); x is indexed by GLOBAL column;
- * if dot_partials != NULL also the partials of sum_r x[x_row_offset + r] * y[r].  lanes_per_row in {4,8,16,32}. */
+ * if dot_partials != NULL also the partials of sum_r x[x_row_offset + r] * y[r].  lanes_per_row in {4,8,16,32} (node-block form: {2,4,8,16,32}). */
 int efb_spmv_csr(int64_t nrows, int index_bytes, const void* indptr, const void* indices, const double* data,
                  const double* x, int64_t x_row_offset, const uint8_t* row_mask, double* y, double* dot_partials,
                  int lanes_per_row, void* stream);
