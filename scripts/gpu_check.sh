@@ -22,7 +22,7 @@ for w in $what; do
       timeout 1500 python bench.py --n $n > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
       tail -c 3000 gpurun_out/${tag}_bench.json; tail -5 gpurun_out/${tag}_bench.err ;;
     launches)
-      timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+      timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c ${NCU_LAUNCHES:-400} --csv \
         --log-file gpurun_out/${tag}_launches.csv python bench.py --n 128 --steps 3 --warmup 3 --no-cpu --e2e-steps 1 --no-pf --no-solve --no-transient \
         > gpurun_out/${tag}_launches.log 2>&1
       tail -2 gpurun_out/${tag}_launches.log ;;
