@@ -10,6 +10,22 @@
 
 #include "common.cuh"
 
+// neighbour blocks prefetched per lane in the block form of the node product, by dof_n (A/B on B200, profiles/README.md)
+#ifndef EFB_BLK_PF64
+#define EFB_BLK_PF64(D) ((D) == 3 ? 1 : ((D) == 2 ? EFB_BLK_PF64_D2 : EFB_BLK_PF_D1))
+#endif
+#ifndef EFB_BLK_PF32
+#define EFB_BLK_PF32(D) ((D) == 3 ? 2 : ((D) == 2 ? EFB_BLK_PF32_D2 : EFB_BLK_PF_D1))
+#endif
+#ifndef EFB_BLK_PF64_D2
+#define EFB_BLK_PF64_D2 3  // TRI3 d=2, 2 lanes: 70.0 -> 66.7 us (4: 77 us)
+#endif
+#ifndef EFB_BLK_PF32_D2
+#define EFB_BLK_PF32_D2 4  // single precision: 62.1 -> 59.2 us
+#endif
+#ifndef EFB_BLK_PF_D1
+#define EFB_BLK_PF_D1 4    // scalar systems (damage): 36.1 / 42.6 -> 35.2 / 36.0 us
+#endif
 #ifndef EFB_SPMV_MINB
 #define EFB_SPMV_MINB 4  // resident CTAs per SM of the product kernels: the block form wants 64 registers
 #endif
@@ -300,7 +316,7 @@ __device__ __forceinline__ double spmv_nodes(long long n_nodes, const long long*
 #ifdef EFB_SPMV_COLUMN_FORM
     return spmv_nodes_pipe<D, LPN, EFB_SPMV_PF(LPN)>(n_nodes, adjptr, adj, data, x, row_mask, epi);
 #else
-    return spmv_nodes_blk<D, LPN, (D == 3 ? 1 : 2), EpiStore, double>(n_nodes, adjptr, adj, data, x, row_mask, epi);
+    return spmv_nodes_blk<D, LPN, EFB_BLK_PF64(D), EpiStore, double>(n_nodes, adjptr, adj, data, x, row_mask, epi);
 #endif
 }
 
@@ -827,7 +843,7 @@ __global__ void __launch_bounds__(kRedThreads, EFB_PCG_CHEB_MINB)
             spmv_rows_epi<long long, B, EpiCheb, VT>(n, (const long long*)indptr, (const long long*)indices, data, zin, mask, epi);
     } else {
         if constexpr (sizeof(VT) == 4)  // single-precision values: whole neighbour blocks per lane (EFB_CHEB_BLK_PF steps prefetched)
-            spmv_nodes_blk<A, B, EFB_CHEB_BLK_PF, EpiCheb, VT>(n, (const long long*)indptr, (const int*)indices, data, zin, mask, epi);
+            spmv_nodes_blk<A, B, EFB_BLK_PF32(A), EpiCheb, VT>(n, (const long long*)indptr, (const int*)indices, data, zin, mask, epi);
         else
             spmv_nodes_pipe<A, B, EFB_SPMV_PF(B), EpiCheb, VT>(n, (const long long*)indptr, (const int*)indices, data, zin, mask, epi);
     }
