@@ -242,8 +242,9 @@ def test_fused_assembly_owned_rows_prefix(efb):
     assert torch.equal(out[:nz], full[:nz]) and bool((out[nz:] == -7.0).all())
 
 
+@pytest.mark.parametrize("path", ["fused", "mma"])
 @pytest.mark.parametrize("n", [100, 200])
-def test_fused_assembly_large_sampled_parity(efb, n):
+def test_fused_assembly_large_sampled_parity(efb, n, path):
     """BASELINE config 2 at 1 M and at the benchmarked 8 M elements (nnz 1.95e9: 91 % of the int32 range, 64-bit offsets in
     the schedule): sampled rows of the fused assembly against np.bincount of the oracle's K_e on the sub-mesh around them,
     bit-exact structure of those rows, rigid-body null space and symmetry of the whole matrix"""
@@ -260,8 +261,15 @@ def test_fused_assembly_large_sampled_parity(efb, n):
     Nn = coords.shape[0]
     mat = orc.IsoMaterial(3, 210000.0, 0.3)
     pat = efb.asm.Assembler().pattern(3, True, Nn * 3, (g,))
-    sched = efb.asm.FusedSchedule(pat.graph)
-    data = efb.asm.assemble_elastic_fused(sched, mat.C)
+    if path == "mma":  # the step of the benchmark: efb_assemble_elastic_mma
+        ms = efb.asm.MmaSchedule(pat.graph)
+        assert ms.fits()
+        data = efb.asm.assemble_elastic_mma(ms, mat.C)
+        del ms
+    else:
+        sched = efb.asm.FusedSchedule(pat.graph)
+        data = efb.asm.assemble_elastic_fused(sched, mat.C)
+        del sched
     K = efb.asm.DeviceCsr(pat.indptr, pat.indices, data, pat.shape, pat.node_graph)
     dev = data.device
     for comp in range(3):  # rigid translations: K t = 0
