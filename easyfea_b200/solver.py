@@ -117,7 +117,7 @@ CHEB_MAX_NNZ = 32_000_000
 # in fl32(A) is still a fixed symmetric operator, i.e. a valid preconditioner, and those products move half the bytes; the outer
 # product, the residual, every vector and every dot product stay FP64.  With it the polynomial pays at every size.
 CHEB_FP32 = True
-CHEB_STALL_ITERS = 400  # outer iterations without a new minimum of |r|: the polynomial is dropped for plain Jacobi
+CHEB_STALL_ITERS = 400  # outer iterations in which |r| has not halved: the polynomial is dropped for plain Jacobi
 
 
 def cheb_coefficients(degree: int, lmin: float, lmax: float):
@@ -387,7 +387,7 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
                 it += k
                 if err:
                     raise _lib.EfbError("PCG: a wait on a neighbour rank timed out (peer process lost?)")
-                if rr == rr and rr < best_rr:
+                if rr == rr and rr < 0.25 * best_rr:  # |r| halved since the last mark
                     best_rr, best_it = rr, it
                 if rr != rr or it - best_it >= CHEB_STALL_ITERS:  # lmax underestimated: the polynomial is not positive
                     stalled = True
@@ -431,7 +431,7 @@ def pcg(A: DeviceCsr, b, x0=None, free_mask=None, tol: float = 1e-8, maxiter: in
                 it += 1
             rr = float(scal[3].item())
             if degree > 1:
-                if rr == rr and rr < best_rr:
+                if rr == rr and rr < 0.25 * best_rr:
                     best_rr, best_it = rr, it
                 if rr != rr or it - best_it >= CHEB_STALL_ITERS:
                     stalled = True

@@ -205,6 +205,40 @@ def test_pcg_elastic_cube(efb):
     assert np.linalg.norm(Kreg @ x4.cpu().numpy() - rhs_full) / np.linalg.norm(rhs_full) <= 1e-9
 
 
+def test_pcg_polynomial_stall_falls_back_to_jacobi(efb, monkeypatch):
+    """a spectral bound far below the largest eigenvalue of D^-1 A makes the Chebyshev polynomial indefinite: the solve must not
+    hang or diverge — after CHEB_STALL_ITERS iterations without a new minimum of |r| it finishes with plain Jacobi"""
+    import warnings
+
+    from easyfea_b200 import meshgen
+
+    n = 8
+    coords, connect = meshgen.structured_mesh("HEXA8", n, jitter=0.15, seed=2)
+    g = efb.mesh.ElemGroup("HEXA8", connect, coords)
+    Nn = coords.shape[0]
+    Ndof = 3 * Nn
+    mat = orc.IsoMaterial(3, 210000.0, 0.3)
+    K = efb.asm.Assembler().Assemble_csr({g: efb.op.elastic_Ke_dev(g, mat.C)}, 3, Ndof, True, as_device=True)
+    lat = np.arange(Nn) % (n + 1)
+    known = np.zeros(Ndof, bool)
+    for c in range(3):
+        known[np.flatnonzero(lat == 0) * 3 + c] = True
+    known[np.flatnonzero(lat == n) * 3] = True
+    x0 = np.zeros(Ndof)
+    x0[np.flatnonzero(lat == n) * 3] = 0.1
+    b = np.zeros(Ndof)
+    xr, infor = efb.solver.pcg(K, b, x0=x0, free_mask=~known, tol=1e-8, maxiter=5000, precond_degree=1)
+    monkeypatch.setattr(efb.solver, "CHEB_SAFETY", 0.3)      # lmax used = 0.3 x the estimate: the polynomial changes sign
+    monkeypatch.setattr(efb.solver, "CHEB_STALL_ITERS", 50)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        x, info = efb.solver.pcg(K, b, x0=x0, free_mask=~known, tol=1e-8, maxiter=5000, precond_degree=4)
+    assert info["converged"], info
+    if info.get("fell_back_to_jacobi"):
+        assert any("stalled" in str(m.message) for m in w)
+    assert np.linalg.norm(x.cpu().numpy() - xr.cpu().numpy()) <= 1e-5 * np.linalg.norm(xr.cpu().numpy())
+
+
 def dv_t(a):
     from easyfea_b200 import device as dv
 
