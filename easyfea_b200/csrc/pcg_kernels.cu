@@ -809,11 +809,8 @@ struct EpiCheb {
 };
 
 // (2d) Chebyshev step k: waits for the neighbours' halo entries of z_k, t = A z_k, d_k, z_{k+1}; the last step publishes (r.z, r.r)
-// block form of the polynomial steps: two neighbour blocks prefetched per lane at 64 registers (4 CTAs per SM) — A/B on B200 at the
-// phase-field sizes (profiles/README.md): TETRA4 d=3 420 -> 320 us per step, TRI3 d=2 77 -> 74 us
-#ifndef EFB_CHEB_BLK_PF
-#define EFB_CHEB_BLK_PF 2
-#endif
+// polynomial steps in block form at 64 registers (4 CTAs per SM) — A/B on B200 at the phase-field sizes (profiles/README.md):
+// TETRA4 d=3 420 -> 288 us per step, TRI3 d=2 77 -> 59 us
 #ifndef EFB_PCG_CHEB_MINB
 #define EFB_PCG_CHEB_MINB 4
 #endif
@@ -842,7 +839,7 @@ __global__ void __launch_bounds__(kRedThreads, EFB_PCG_CHEB_MINB)
         else
             spmv_rows_epi<long long, B, EpiCheb, VT>(n, (const long long*)indptr, (const long long*)indices, data, zin, mask, epi);
     } else {
-        if constexpr (sizeof(VT) == 4)  // single-precision values: whole neighbour blocks per lane (EFB_CHEB_BLK_PF steps prefetched)
+        if constexpr (sizeof(VT) == 4)  // single-precision values: block form, EFB_BLK_PF32(dof_n) neighbour blocks prefetched per lane
             spmv_nodes_blk<A, B, EFB_BLK_PF32(A), EpiCheb, VT>(n, (const long long*)indptr, (const int*)indices, data, zin, mask, epi);
         else
             spmv_nodes_pipe<A, B, EFB_SPMV_PF(B), EpiCheb, VT>(n, (const long long*)indptr, (const int*)indices, data, zin, mask, epi);
