@@ -1,6 +1,7 @@
 // C-ABI entry points of the element kernels: launch configuration + (dim, nPe) dispatch.
 #include "common.cuh"
 #include "elem_kernels.cuh"
+#include "scalar_warp.cuh"
 
 #include <stdlib.h>
 #include <string.h>
@@ -505,8 +506,48 @@ __global__ void __launch_bounds__(256) k_scalar(GroupView g, ScalarOp op, int EP
     scalar_block<DIM, NPE>(g, op, EPB, blockIdx.x, blockDim.x, smem);
 }
 
+// warp-autonomous form (scalar_warp.cuh) for elements of at most 8 nodes: persistent CTAs of 8 warps, one batch of 32/LPE elements
+// per warp and pass, only warp barriers
+template <int DIM, int NPE>
+__global__ void __launch_bounds__(256) k_scalar_w(GroupView g, ScalarOp op, long long nbatches) {
+    extern __shared__ double smem[];
+    using SW = ScalarWarp<DIM, NPE>;
+    scalar_warp_tables<DIM, NPE>(g, smem, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double* ws = smem + SW::tables(g.nPg) + warp * SW::per_warp(g.nPg, op.has_k);
+    for (long long b = (long long)blockIdx.x * nw + warp; b < nbatches; b += (long long)gridDim.x * nw)
+        scalar_warp_batch<DIM, NPE>(g, op, b, smem, ws);
+}
+
 template <int DIM, int NPE>
 static int launch_scalar(const efb_group* g, const ScalarOp& op, cudaStream_t st, const char* what) {
+    if constexpr (NPE <= 8) {
+        // dev: EFB_SCALAR_BLOCK=1 forces the block form, =-1 the warp form
+        static const int force = [] { const char* e = getenv("EFB_SCALAR_BLOCK"); return e ? atoi(e) : 0; }();
+        // measured on B200 (scripts/scalar_probe.py, profiles/README.md): the warp form wins for TRI3 (every operator), for the
+        // operators without gradients and block expansion (UV / V with dof_n = 1: HEXA8 1.80 -> 1.32 ms, TETRA4 1.28 -> 0.81) and
+        // for TETRA4 stiffness-type operators; the block form keeps the block-expanded outputs and the QUAD4 / HEXA8 gradients
+        const bool warp_wins = NPE == 3 || (op.dof_n == 1 && (!op.has_k || (DIM == 3 && NPE == 4)));
+        if (force < 0 || (force == 0 && warp_wins)) {
+            using SW = ScalarWarp<DIM, NPE>;
+            constexpr int NW = 8;
+            const size_t bytes = sizeof(double) * SW::total(g->nPg, op.has_k, NW);
+            if (bytes <= 100 * 1024) {
+                if (ensure_smem(k_scalar_w<DIM, NPE>, bytes)) return 1;
+                const long long nbatches = (g->Ne + SW::EPW - 1) / SW::EPW;
+                if (nbatches == 0) return 0;
+                int dev = 0, sms = 148, per_sm = 1;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scalar_w<DIM, NPE>, NW * 32, bytes) != cudaSuccess || per_sm < 1) per_sm = 1;
+                long long grid = (nbatches + NW - 1) / NW;
+                if (grid > (long long)sms * per_sm) grid = (long long)sms * per_sm;
+                k_scalar_w<DIM, NPE><<<(unsigned)grid, NW * 32, bytes, st>>>(view_of(g), op, nbatches);
+                return check_launch(what);
+            }
+        }
+    }
     const int TPE = NPE, EPB = elems_per_block<DIM, NPE>(TPE, g->nPg, NPE * NPE + NPE, op.has_k);
     const SmemMap<DIM, NPE> sm(g->nPg, EPB, NPE * NPE + NPE, op.has_k);
     const size_t bytes = sizeof(double) * sm.total();

@@ -1,0 +1,184 @@
+// Warp-autonomous form of the scalar operator body (O2 `UV`, O3 `GradUGradV / GradU_A_GradV`, O4 `V`, S4 damage system;
+// Bilinear.py:25-59, 229-249, Linear.py:18-36, Simulations/_phasefield.py:540-573) for elements of at most 8 nodes.
+// Same arithmetic as scalar_block (elem_kernels.cuh) — same sums in the same order — but no CTA barrier and no F / F^-1 / det
+// arrays in shared memory: a warp owns a batch of 32/LPE elements (LPE = 4 or 8 lanes per element), gathers their coordinates,
+// integrates the geometry of a Gauss point per lane in registers (only wJ and the physical gradients go to its private shared
+// memory), contracts one column per lane, and writes the block-expanded outputs of the whole batch as one contiguous, coalesced
+// range.  Only warp barriers: the phases of the 8 warps of a CTA drift apart and hide each other's latencies; per-element shared
+// memory drops from 512 to 148-296 doubles (HEXA8), i.e. 16 resident warps per SM instead of 12 behind 5 CTA barriers.
+// Written with the lane macros of csr_kernels.cuh so that tests/hostcheck runs the same body on the host.
+#pragma once
+#include "csr_kernels.cuh"
+#include "elem_kernels.cuh"
+
+namespace efb {
+
+template <int DIM, int NPE>
+struct ScalarWarp {
+    static_assert(NPE <= 8, "warp form: at most 8 nodes per element");
+    static constexpr int LPE = NPE <= 4 ? 4 : 8;  // lanes per element
+    static constexpr int EPW = 32 / LPE;          // elements per warp batch
+    static constexpr int GS = DIM;                // doubles per (Gauss point, node) in the gradient table
+    EFB_HD static int tables(int nPg) { return (nPg * DIM * NPE + nPg * NPE + nPg + 1) & ~1; }
+    // per-warp scratch: X | wJ | gradients (has_k) | Ms | Fs
+    EFB_HD static int o_wJ() { return EPW * NPE * DIM; }
+    EFB_HD static int o_G(int nPg) { return o_wJ() + EPW * nPg; }
+    EFB_HD static int o_Ms(int nPg, bool grad) { return o_G(nPg) + (grad ? EPW * nPg * NPE * GS : 0); }
+    EFB_HD static int o_Fs(int nPg, bool grad) { return o_Ms(nPg, grad) + EPW * NPE * NPE; }
+    EFB_HD static int per_warp(int nPg, bool grad) { return (o_Fs(nPg, grad) + EPW * NPE + 1) | 1; }  // odd: warps start in different banks
+    EFB_HD static size_t total(int nPg, bool grad, int nwarps) { return (size_t)tables(nPg) + (size_t)nwarps * per_warp(nPg, grad); }
+};
+
+// reference-element tables of the group -> shared memory (once per CTA; the caller puts a CTA barrier behind it)
+template <int DIM, int NPE>
+EFB_D void scalar_warp_tables(const GroupView& g, double* smem, int tid, int nthreads) {
+    const int nPg = g.nPg;
+    double* dNt = smem;
+    double* Nt = dNt + nPg * DIM * NPE;
+    double* wt = Nt + nPg * NPE;
+    for (int i = tid; i < nPg * DIM * NPE; i += nthreads) dNt[i] = g.dN_pg[i];
+    for (int i = tid; i < nPg * NPE; i += nthreads) Nt[i] = g.N_pg[i];
+    for (int i = tid; i < nPg; i += nthreads) wt[i] = g.w_pg[i];
+}
+
+// one batch (elements batch*EPW ...) on one warp; `tab` = the tables, `ws` = this warp's scratch
+template <int DIM, int NPE>
+EFB_D void scalar_warp_batch(const GroupView& g, const ScalarOp& op, long long batch, const double* tab, double* ws) {
+    using SW = ScalarWarp<DIM, NPE>;
+    constexpr int LPE = SW::LPE, EPW = SW::EPW, GS = SW::GS;
+    const int nPg = g.nPg;
+    const double* dNt = tab;
+    const double* Nt = dNt + nPg * DIM * NPE;
+    const double* wt = Nt + nPg * NPE;
+    double* X = ws;
+    double* wJ = ws + SW::o_wJ();
+    double* G = ws + SW::o_G(nPg);
+    double* Ms = ws + SW::o_Ms(nPg, op.has_k);
+    double* Fs = ws + SW::o_Fs(nPg, op.has_k);
+    const long long e0 = batch * EPW;
+    const int nvalid = (g.Ne - e0 < EPW) ? (int)(g.Ne - e0) : EPW;
+
+    EFB_LANES(lane) {  // gather: lane (el, t) fetches node t of element el
+        const int el = lane / LPE, t = lane % LPE;
+        if (el < nvalid && t < NPE) {
+            const double* src = g.coord + (long long)g.connect[(e0 + el) * NPE + t] * g.coord_stride;
+            EFB_UNROLL
+            for (int d = 0; d < DIM; ++d) X[(el * NPE + t) * DIM + d] = src[d];
+        }
+    }
+    EFB_LANES(lane) {  // geometry of the Gauss points t, t + LPE, ... of element el, in registers   _group_elem.py:864-915, 1083-1105
+        const int el = lane / LPE, t = lane % LPE;
+        if (el < nvalid) {
+            const double* Xe = X + el * NPE * DIM;
+            for (int p = t; p < nPg; p += LPE) {
+                double F[DIM * DIM], Fi[DIM * DIM];
+                EFB_UNROLL
+                for (int r = 0; r < DIM; ++r)
+                    EFB_UNROLL
+                    for (int c = 0; c < DIM; ++c) {
+                        const double* row = dNt + (p * DIM + r) * NPE;
+                        double s = 0.0;
+                        EFB_UNROLL
+                        for (int n = 0; n < NPE; ++n) s += row[n] * Xe[n * DIM + c];
+                        F[r * DIM + c] = s;
+                    }
+                const double det = det_inv<DIM>(F, Fi);
+                wJ[el * nPg + p] = fabs(det) * wt[p];
+                if (op.has_k) {
+                    double* gp = G + ((el * nPg + p) * NPE) * GS;
+                    EFB_UNROLL
+                    for (int a = 0; a < NPE; ++a)
+                        EFB_UNROLL
+                        for (int d = 0; d < DIM; ++d) {
+                            double s = 0.0;
+                            EFB_UNROLL
+                            for (int k = 0; k < DIM; ++k) s += Fi[d * DIM + k] * dNt[(p * DIM + k) * NPE + a];
+                            gp[a * GS + d] = s;
+                        }
+                }
+            }
+        }
+    }
+    EFB_LANES(lane) {  // contraction: lane (el, b) accumulates column b (the sums of scalar_block, in its order)
+        const int el = lane / LPE, b = lane % LPE;
+        if (el < nvalid && b < NPE) {
+            const long long e = e0 + el;
+            double acc[NPE];
+            EFB_UNROLL
+            for (int a = 0; a < NPE; ++a) acc[a] = 0.0;
+            double fb = 0.0;
+            for (int p = 0; p < nPg; ++p) {
+                const double w = wJ[el * nPg + p];
+                const double* Np = Nt + p * NPE;
+                if (op.has_r) {
+                    const double c = coef_at(op.r, op.r_mode, op.r_scalar, e, p, nPg) * w * Np[b];
+                    EFB_UNROLL
+                    for (int a = 0; a < NPE; ++a) acc[a] += Np[a] * c;
+                }
+                if (op.has_k) {
+                    const double c = coef_at(op.k, op.k_mode, op.k_scalar, e, p, nPg) * w;
+                    const double* gp = G + ((el * nPg + p) * NPE) * GS;
+                    const double* gb = gp + b * GS;
+                    double Ag[DIM];
+                    if (op.A) {
+                        const double* Ap = op.A + (op.A_mode == 0 ? 0 : (op.A_mode == 1 ? e * DIM * DIM : (e * nPg + p) * (long long)(DIM * DIM)));
+                        EFB_UNROLL
+                        for (int i = 0; i < DIM; ++i) {
+                            double s = 0.0;
+                            EFB_UNROLL
+                            for (int kk = 0; kk < DIM; ++kk) s += Ap[i * DIM + kk] * gb[kk];
+                            Ag[i] = c * s;
+                        }
+                    } else {
+                        EFB_UNROLL
+                        for (int i = 0; i < DIM; ++i) Ag[i] = c * gb[i];
+                    }
+                    EFB_UNROLL
+                    for (int a = 0; a < NPE; ++a) {
+                        const double* ga = gp + a * GS;
+                        double s = 0.0;
+                        EFB_UNROLL
+                        for (int i = 0; i < DIM; ++i) s += ga[i] * Ag[i];
+                        acc[a] += s;
+                    }
+                }
+                if (op.has_f) fb += coef_at(op.f, op.f_mode, op.f_scalar, e, p, nPg) * w * Np[b];
+            }
+            EFB_UNROLL
+            for (int a = 0; a < NPE; ++a) Ms[el * NPE * NPE + a * NPE + b] = op.scale * acc[a];
+            Fs[el * NPE + b] = op.scale * fb;
+        }
+    }
+    EFB_LANES(lane) {  // block-expanded write-out: the batch's outputs are one contiguous range
+        const int dn = op.dof_n, ndof = NPE * dn;
+        if (op.Ke) {
+            double* dst = op.Ke + e0 * (long long)(ndof * ndof);
+            const int per = ndof * ndof, total = nvalid * per;
+            for (int i = lane; i < total; i += 32) {
+                const int el = i / per, rem = i - el * per;
+                const int row = rem / ndof, col = rem - row * ndof;
+                dst[i] = (row % dn == col % dn) ? Ms[el * NPE * NPE + (row / dn) * NPE + col / dn] : 0.0;
+            }
+        }
+        if (op.Fe) {
+            if (op.f_keep_axis) {
+                double* dst = op.Fe + e0 * (long long)(ndof * dn);
+                const int per = ndof * dn, total = nvalid * per;
+                for (int i = lane; i < total; i += 32) {
+                    const int el = i / per, rem = i - el * per;
+                    const int row = rem / dn, comp = rem - row * dn;
+                    dst[i] = (row % dn == comp) ? Fs[el * NPE + row / dn] : 0.0;
+                }
+            } else {
+                double* dst = op.Fe + e0 * (long long)ndof;
+                const int total = nvalid * ndof;
+                for (int i = lane; i < total; i += 32) {
+                    const int el = i / ndof, rem = i - el * ndof;
+                    dst[i] = Fs[el * NPE + rem / dn];
+                }
+            }
+        }
+    }
+}
+
+}  // namespace efb

@@ -11,6 +11,7 @@
 #include "../../easyfea_b200/csrc/csr_kernels.cuh"
 #include "../../easyfea_b200/csrc/elem_kernels.cuh"
 #include "../../easyfea_b200/csrc/pf_math.cuh"
+#include "../../easyfea_b200/csrc/scalar_warp.cuh"
 #include "../../include/easyfea_b200.h"
 
 using namespace efb;
@@ -126,6 +127,25 @@ extern "C" int hc_elastic_Ke_warp(const efb_group* g, const double* C, int form,
     return 2;
 }
 
+template <int D, int N>
+static int run_scalar(const efb_group* g, const ScalarOp& op) {
+    if constexpr (N <= 8) {  // the warp-autonomous form the device takes for these element types (HC_SCALAR_BLOCK=1: the block form)
+        if (!getenv("HC_SCALAR_BLOCK")) {
+            using SW = ScalarWarp<D, N>;
+            std::vector<double> smem(SW::total(g->nPg, op.has_k, 1));
+            const GroupView v = view_of(g);
+            scalar_warp_tables<D, N>(v, smem.data(), 0, 1);
+            for (long long b = 0; b * SW::EPW < g->Ne; ++b) scalar_warp_batch<D, N>(v, op, b, smem.data(), smem.data() + SW::tables(g->nPg));
+            return 0;
+        }
+    }
+    const int TPE = N, EPB = epb_for(TPE);
+    SmemMap<D, N> sm(g->nPg, EPB, N * N + N);
+    std::vector<double> smem(sm.total());
+    for (long long b = 0; b * EPB < g->Ne; ++b) scalar_block<D, N>(view_of(g), op, EPB, b, EPB * TPE, smem.data());
+    return 0;
+}
+
 extern "C" int hc_scalar(const efb_group* g, const double* r, int r_mode, double r_scalar, int has_r, const double* A, int A_mode,
                          const double* k, int k_mode, double k_scalar, int has_k, const double* f, int f_mode, double f_scalar,
                          int has_f, int dof_n, double scale, double* Ke, double* Fe, int f_keep_axis) {
@@ -134,14 +154,8 @@ extern "C" int hc_scalar(const efb_group* g, const double* r, int r_mode, double
     op.A = A; op.A_mode = A_mode; op.k = k; op.k_mode = k_mode; op.k_scalar = k_scalar; op.has_k = has_k;
     op.f = f; op.f_mode = f_mode; op.f_scalar = f_scalar; op.has_f = has_f;
     op.dof_n = dof_n; op.scale = scale; op.Ke = Ke; op.Fe = Fe; op.f_keep_axis = f_keep_axis;
-#define X(D, N)                                                                                                  \
-    if (g->dim == D && g->nPe == N) {                                                                            \
-        const int TPE = N, EPB = epb_for(TPE);                                                                   \
-        SmemMap<D, N> sm(g->nPg, EPB, N * N + N);                                                                \
-        std::vector<double> smem(sm.total());                                                                    \
-        for (long long b = 0; b * EPB < g->Ne; ++b) scalar_block<D, N>(view_of(g), op, EPB, b, EPB * TPE, smem.data()); \
-        return 0;                                                                                                \
-    }
+#define X(D, N) \
+    if (g->dim == D && g->nPe == N) return run_scalar<D, N>(g, op);
     FOR_EACH(X)
 #undef X
     return 2;

@@ -103,7 +103,12 @@ def test_elastic_Ke_warp_forms(hostcheck, elemType, form):
 
 @pytest.mark.parametrize("elemType", list(ELEM_CASES))
 @pytest.mark.parametrize("mt", ["rigi", "mass"])
-def test_scalar_operators(hostcheck, elemType, mt):
+@pytest.mark.parametrize("body", ["warp", "block"])
+def test_scalar_operators(hostcheck, elemType, mt, body, monkeypatch):
+    """both bodies of the scalar operators: the warp-autonomous form (csrc/scalar_warp.cuh, elements of at most 8 nodes) and the
+    phase-structured block form (every element type); the device picks per operator (elem_kernels.cu launch_scalar)"""
+    if body == "block":
+        monkeypatch.setenv("HC_SCALAR_BLOCK", "1")
     rng = np.random.default_rng(4)
     coords, connect = make_mesh(elemType)
     g, keep, tab = host_group(elemType, coords, connect, mt)
