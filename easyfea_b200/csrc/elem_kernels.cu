@@ -525,10 +525,9 @@ static int launch_scalar(const efb_group* g, const ScalarOp& op, cudaStream_t st
     if constexpr (NPE <= 8) {
         // dev: EFB_SCALAR_BLOCK=1 forces the block form, =-1 the warp form
         static const int force = [] { const char* e = getenv("EFB_SCALAR_BLOCK"); return e ? atoi(e) : 0; }();
-        // measured on B200 (scripts/scalar_probe.py, profiles/README.md): the warp form wins for TRI3 (every operator), for the
-        // operators without gradients and block expansion (UV / V with dof_n = 1: HEXA8 1.80 -> 1.32 ms, TETRA4 1.28 -> 0.81) and
-        // for TETRA4 stiffness-type operators; the block form keeps the block-expanded outputs and the QUAD4 / HEXA8 gradients
-        const bool warp_wins = NPE == 3 || (op.dof_n == 1 && (!op.has_k || (DIM == 3 && NPE == 4)));
+        // measured on B200 (scripts/scalar_probe.py, profiles/README.md): the warp form wins for every operator and element type
+        // of at most 8 nodes (TRI3 2.2x, TETRA4 1.5-2.5x, QUAD4 1.3-1.5x, HEXA8 1.3-1.8x)
+        const bool warp_wins = true;
         if (force < 0 || (force == 0 && warp_wins)) {
             using SW = ScalarWarp<DIM, NPE>;
             constexpr int NW = 8;

@@ -19,11 +19,12 @@ struct ScalarWarp {
     static constexpr int LPE = NPE <= 4 ? 4 : 8;  // lanes per element
     static constexpr int EPW = 32 / LPE;          // elements per warp batch
     static constexpr int GS = DIM;                // doubles per (Gauss point, node) in the gradient table
+    static constexpr int GPS = (NPE * DIM) | 1;   // doubles per Gauss point in it: odd, so the lanes (one Gauss point each) hit different banks
     EFB_HD static int tables(int nPg) { return (nPg * DIM * NPE + nPg * NPE + nPg + 1) & ~1; }
     // per-warp scratch: X | wJ | gradients (has_k) | Ms | Fs
     EFB_HD static int o_wJ() { return EPW * NPE * DIM; }
     EFB_HD static int o_G(int nPg) { return o_wJ() + EPW * nPg; }
-    EFB_HD static int o_Ms(int nPg, bool grad) { return o_G(nPg) + (grad ? EPW * nPg * NPE * GS : 0); }
+    EFB_HD static int o_Ms(int nPg, bool grad) { return o_G(nPg) + (grad ? EPW * nPg * GPS : 0); }
     EFB_HD static int o_Fs(int nPg, bool grad) { return o_Ms(nPg, grad) + EPW * NPE * NPE; }
     EFB_HD static int per_warp(int nPg, bool grad) { return (o_Fs(nPg, grad) + EPW * NPE + 1) | 1; }  // odd: warps start in different banks
     EFB_HD static size_t total(int nPg, bool grad, int nwarps) { return (size_t)tables(nPg) + (size_t)nwarps * per_warp(nPg, grad); }
@@ -41,11 +42,45 @@ EFB_D void scalar_warp_tables(const GroupView& g, double* smem, int tid, int nth
     for (int i = tid; i < nPg; i += nthreads) wt[i] = g.w_pg[i];
 }
 
+// block-expanded outputs of one batch, lane `lane` of 32; DN = dof_n known at compile time (0: read it from op)
+template <int NPE, int DN>
+EFB_D void scalar_warp_writeout(const ScalarOp& op, long long e0, int nvalid, const double* EFB_RESTRICT Ms, const double* EFB_RESTRICT Fs,
+                                int lane) {
+    const int dn = DN ? DN : op.dof_n, ndof = NPE * dn;
+    if (op.Ke) {
+        double* dst = op.Ke + e0 * (long long)(ndof * ndof);
+        const int per = ndof * ndof, total = nvalid * per;
+        for (int i = lane; i < total; i += 32) {
+            const int el = i / per, rem = i - el * per;
+            const int row = rem / ndof, col = rem - row * ndof;
+            dst[i] = (row % dn == col % dn) ? Ms[el * NPE * NPE + (row / dn) * NPE + col / dn] : 0.0;
+        }
+    }
+    if (op.Fe) {
+        if (op.f_keep_axis) {
+            double* dst = op.Fe + e0 * (long long)(ndof * dn);
+            const int per = ndof * dn, total = nvalid * per;
+            for (int i = lane; i < total; i += 32) {
+                const int el = i / per, rem = i - el * per;
+                const int row = rem / dn, comp = rem - row * dn;
+                dst[i] = (row % dn == comp) ? Fs[el * NPE + row / dn] : 0.0;
+            }
+        } else {
+            double* dst = op.Fe + e0 * (long long)ndof;
+            const int total = nvalid * ndof;
+            for (int i = lane; i < total; i += 32) {
+                const int el = i / ndof, rem = i - el * ndof;
+                dst[i] = Fs[el * NPE + rem / dn];
+            }
+        }
+    }
+}
+
 // one batch (elements batch*EPW ...) on one warp; `tab` = the tables, `ws` = this warp's scratch
 template <int DIM, int NPE>
 EFB_D void scalar_warp_batch(const GroupView& g, const ScalarOp& op, long long batch, const double* tab, double* ws) {
     using SW = ScalarWarp<DIM, NPE>;
-    constexpr int LPE = SW::LPE, EPW = SW::EPW, GS = SW::GS;
+    constexpr int LPE = SW::LPE, EPW = SW::EPW, GS = SW::GS, GPS = SW::GPS;
     const int nPg = g.nPg;
     const double* dNt = tab;
     const double* Nt = dNt + nPg * DIM * NPE;
@@ -85,7 +120,7 @@ EFB_D void scalar_warp_batch(const GroupView& g, const ScalarOp& op, long long b
                 const double det = det_inv<DIM>(F, Fi);
                 wJ[el * nPg + p] = fabs(det) * wt[p];
                 if (op.has_k) {
-                    double* gp = G + ((el * nPg + p) * NPE) * GS;
+                    double* gp = G + (el * nPg + p) * GPS;
                     EFB_UNROLL
                     for (int a = 0; a < NPE; ++a)
                         EFB_UNROLL
@@ -117,7 +152,7 @@ EFB_D void scalar_warp_batch(const GroupView& g, const ScalarOp& op, long long b
                 }
                 if (op.has_k) {
                     const double c = coef_at(op.k, op.k_mode, op.k_scalar, e, p, nPg) * w;
-                    const double* gp = G + ((el * nPg + p) * NPE) * GS;
+                    const double* gp = G + (el * nPg + p) * GPS;
                     const double* gb = gp + b * GS;
                     double Ag[DIM];
                     if (op.A) {
@@ -149,35 +184,13 @@ EFB_D void scalar_warp_batch(const GroupView& g, const ScalarOp& op, long long b
             Fs[el * NPE + b] = op.scale * fb;
         }
     }
-    EFB_LANES(lane) {  // block-expanded write-out: the batch's outputs are one contiguous range
-        const int dn = op.dof_n, ndof = NPE * dn;
-        if (op.Ke) {
-            double* dst = op.Ke + e0 * (long long)(ndof * ndof);
-            const int per = ndof * ndof, total = nvalid * per;
-            for (int i = lane; i < total; i += 32) {
-                const int el = i / per, rem = i - el * per;
-                const int row = rem / ndof, col = rem - row * ndof;
-                dst[i] = (row % dn == col % dn) ? Ms[el * NPE * NPE + (row / dn) * NPE + col / dn] : 0.0;
-            }
-        }
-        if (op.Fe) {
-            if (op.f_keep_axis) {
-                double* dst = op.Fe + e0 * (long long)(ndof * dn);
-                const int per = ndof * dn, total = nvalid * per;
-                for (int i = lane; i < total; i += 32) {
-                    const int el = i / per, rem = i - el * per;
-                    const int row = rem / dn, comp = rem - row * dn;
-                    dst[i] = (row % dn == comp) ? Fs[el * NPE + row / dn] : 0.0;
-                }
-            } else {
-                double* dst = op.Fe + e0 * (long long)ndof;
-                const int total = nvalid * ndof;
-                for (int i = lane; i < total; i += 32) {
-                    const int el = i / ndof, rem = i - el * ndof;
-                    dst[i] = Fs[el * NPE + rem / dn];
-                }
-            }
-        }
+    // block-expanded write-out: the batch's outputs are one contiguous range (dof_n is 1, 2 or 3 in the reference: compile-time
+    // divisors; any other value takes the generic loop)
+    EFB_LANES(lane) {
+        if (op.dof_n == 1) scalar_warp_writeout<NPE, 1>(op, e0, nvalid, Ms, Fs, lane);
+        else if (op.dof_n == 2) scalar_warp_writeout<NPE, 2>(op, e0, nvalid, Ms, Fs, lane);
+        else if (op.dof_n == 3) scalar_warp_writeout<NPE, 3>(op, e0, nvalid, Ms, Fs, lane);
+        else scalar_warp_writeout<NPE, 0>(op, e0, nvalid, Ms, Fs, lane);
     }
 }
 
