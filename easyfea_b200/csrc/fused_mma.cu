@@ -17,9 +17,9 @@
 //
 // One persistent CTA per SM, warp-specialised (no CTA-wide barrier in the steady state):
 //   * a LOADER warp streams the per-cluster records (connectivity, staging slots, node records, round headers) and gather
-//     programs into a 3-slot shared-memory ring with bulk asynchronous copies (cp.async.bulk on mbarriers), two clusters ahead;
-//   * 8 INTEGRATION warps (two per SM sub-partition: the FP64 pipe is the limiter) take passes of 4 elements round-robin over
-//     the global pass sequence: Jacobians (12 DMMA); lane (p, e) inverts its Jacobian and writes the 24 scaled gradients of
+//     programs into a 4-slot shared-memory ring with bulk asynchronous copies (cp.async.bulk on mbarriers), three clusters ahead;
+//   * 11 INTEGRATION warps (16 warps per CTA is what 128 registers per thread allow; 20 warps at 96 registers measured 20-30 %
+//     slower) take passes of 4 elements over the pass sequence, the assignment rotating from cluster to cluster: Jacobians (12 DMMA); lane (p, e) inverts its Jacobian and writes the 24 scaled gradients of
 //     (e, p) to a per-warp table (bank-swizzled: conflict-free stores and fragment loads); per element the B fragments (6
 //     loads), the needed row tiles (2 loads + 6 DMMA each) and the T rows of the owned nodes into one of TWO staging buffers
 //     stage[slot][k*3+l][b ^ x] (slot = (owned node, element), x = node swizzle); the coordinates of a pass are requested one
@@ -52,9 +52,18 @@ constexpr int kMmaTS = 72;                  // doubles per staged task: [k*3+l][
 constexpr int kMmaZero = 72;                // zero tail of a staging buffer
 constexpr int kMmaGE = 192;                 // doubles of the gradient table of one element: [p][l][b ^ swizzle(p)]
 constexpr int kMmaWarpBuf = 2 * kMmaGE;     // per-warp scratch: two tables (element e + 1 is written while e is read)
-constexpr int kMmaP2 = 11;                  // integration warps (16 warps per CTA: 128 registers per thread)
-constexpr int kMmaP3 = 4;                   // gather warps
-constexpr int kMmaStages = 4;               // ring slots
+#ifndef EFB_MMA_P2
+#define EFB_MMA_P2 11
+#endif
+#ifndef EFB_MMA_P3
+#define EFB_MMA_P3 4
+#endif
+#ifndef EFB_MMA_STAGES
+#define EFB_MMA_STAGES 4
+#endif
+constexpr int kMmaP2 = EFB_MMA_P2;          // integration warps (16 warps per CTA: 128 registers per thread); -D overrides are for A/B builds
+constexpr int kMmaP3 = EFB_MMA_P3;          // gather warps
+constexpr int kMmaStages = EFB_MMA_STAGES;  // ring slots
 constexpr int kMmaThreads = (kMmaP2 + kMmaP3 + 1) * 32;
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {

@@ -56,7 +56,7 @@ def main():
         out["two_kernel_ms"] = timed(lambda: (operators.elastic_Ke_dev(g, C, "rigi", 1.0, out=Ke), pat.replay([Ke], out=data)), args.reps)
         ref = data.clone()
         del Ke
-    for S in [int(s) for s in args.S.split(",")]:
+    for S in [int(s) for s in args.S.split(",") if s]:
         try:
             torch.cuda.synchronize()
             import time
