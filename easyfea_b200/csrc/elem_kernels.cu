@@ -508,8 +508,11 @@ __global__ void __launch_bounds__(256) k_scalar(GroupView g, ScalarOp op, int EP
 
 // warp-autonomous form (scalar_warp.cuh) for elements of at most 8 nodes: persistent CTAs of 8 warps, one batch of 32/LPE elements
 // per warp and pass, only warp barriers
+#ifndef EFB_SCALAR_W_MINB
+#define EFB_SCALAR_W_MINB 3  // 80 registers (HEXA8: 94 without the bound, no spills): 3 CTAs per SM for the operators without a gradient table
+#endif
 template <int DIM, int NPE>
-__global__ void __launch_bounds__(256) k_scalar_w(GroupView g, ScalarOp op, long long nbatches) {
+__global__ void __launch_bounds__(256, EFB_SCALAR_W_MINB) k_scalar_w(GroupView g, ScalarOp op, long long nbatches) {
     extern __shared__ double smem[];
     using SW = ScalarWarp<DIM, NPE>;
     scalar_warp_tables<DIM, NPE>(g, smem, threadIdx.x, blockDim.x);

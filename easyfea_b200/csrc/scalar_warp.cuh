@@ -5,7 +5,7 @@
 // integrates the geometry of a Gauss point per lane in registers (only wJ and the physical gradients go to its private shared
 // memory), contracts one column per lane, and writes the block-expanded outputs of the whole batch as one contiguous, coalesced
 // range.  Only warp barriers: the phases of the 8 warps of a CTA drift apart and hide each other's latencies; per-element shared
-// memory drops from 512 to 148-296 doubles (HEXA8), i.e. 16 resident warps per SM instead of 12 behind 5 CTA barriers.
+// memory drops from 512 to 112-312 doubles (HEXA8), i.e. 16-24 resident warps per SM instead of 12 behind 5 CTA barriers.
 // Written with the lane macros of csr_kernels.cuh so that tests/hostcheck runs the same body on the host.
 #pragma once
 #include "csr_kernels.cuh"
@@ -20,12 +20,17 @@ struct ScalarWarp {
     static constexpr int EPW = 32 / LPE;          // elements per warp batch
     static constexpr int GS = DIM;                // doubles per (Gauss point, node) in the gradient table
     static constexpr int GPS = (NPE * DIM) | 1;   // doubles per Gauss point in it: odd, so the lanes (one Gauss point each) hit different banks
-    EFB_HD static int tables(int nPg) { return (nPg * DIM * NPE + nPg * NPE + nPg + 1) & ~1; }
+    // doubles per Gauss point in the dN table: = 2 mod 4, so that the lanes of an element (one Gauss point each) read their rows —
+    // 128-bit loads — from different 16-byte bank groups (a stride of DIM * NPE = 24 doubles was a 4-way conflict, ncu)
+    static constexpr int DPS = ((DIM * NPE + 1) & ~3) + 2;
+    // doubles per element in Ms: the elements of a half warp store their columns into different banks
+    static constexpr int MSS = ((NPE * NPE + 15) & ~15) + LPE;
+    EFB_HD static int tables(int nPg) { return (nPg * DPS + nPg * NPE + nPg + 1) & ~1; }
     // per-warp scratch: X | wJ | gradients (has_k) | Ms | Fs
     EFB_HD static int o_wJ() { return EPW * NPE * DIM; }
     EFB_HD static int o_G(int nPg) { return o_wJ() + EPW * nPg; }
     EFB_HD static int o_Ms(int nPg, bool grad) { return o_G(nPg) + (grad ? EPW * nPg * GPS : 0); }
-    EFB_HD static int o_Fs(int nPg, bool grad) { return o_Ms(nPg, grad) + EPW * NPE * NPE; }
+    EFB_HD static int o_Fs(int nPg, bool grad) { return o_Ms(nPg, grad) + EPW * MSS; }
     EFB_HD static int per_warp(int nPg, bool grad) { return (o_Fs(nPg, grad) + EPW * NPE + 1) | 1; }  // odd: warps start in different banks
     EFB_HD static size_t total(int nPg, bool grad, int nwarps) { return (size_t)tables(nPg) + (size_t)nwarps * per_warp(nPg, grad); }
 };
@@ -34,16 +39,17 @@ struct ScalarWarp {
 template <int DIM, int NPE>
 EFB_D void scalar_warp_tables(const GroupView& g, double* smem, int tid, int nthreads) {
     const int nPg = g.nPg;
+    using SW = ScalarWarp<DIM, NPE>;
     double* dNt = smem;
-    double* Nt = dNt + nPg * DIM * NPE;
+    double* Nt = dNt + nPg * SW::DPS;
     double* wt = Nt + nPg * NPE;
-    for (int i = tid; i < nPg * DIM * NPE; i += nthreads) dNt[i] = g.dN_pg[i];
+    for (int i = tid; i < nPg * DIM * NPE; i += nthreads) dNt[(i / (DIM * NPE)) * SW::DPS + i % (DIM * NPE)] = g.dN_pg[i];
     for (int i = tid; i < nPg * NPE; i += nthreads) Nt[i] = g.N_pg[i];
     for (int i = tid; i < nPg; i += nthreads) wt[i] = g.w_pg[i];
 }
 
 // block-expanded outputs of one batch, lane `lane` of 32; DN = dof_n known at compile time (0: read it from op)
-template <int NPE, int DN>
+template <int NPE, int DN, int MSS>
 EFB_D void scalar_warp_writeout(const ScalarOp& op, long long e0, int nvalid, const double* EFB_RESTRICT Ms, const double* EFB_RESTRICT Fs,
                                 int lane) {
     const int dn = DN ? DN : op.dof_n, ndof = NPE * dn;
@@ -53,7 +59,7 @@ EFB_D void scalar_warp_writeout(const ScalarOp& op, long long e0, int nvalid, co
         for (int i = lane; i < total; i += 32) {
             const int el = i / per, rem = i - el * per;
             const int row = rem / ndof, col = rem - row * ndof;
-            dst[i] = (row % dn == col % dn) ? Ms[el * NPE * NPE + (row / dn) * NPE + col / dn] : 0.0;
+            dst[i] = (row % dn == col % dn) ? Ms[el * MSS + (row / dn) * NPE + col / dn] : 0.0;
         }
     }
     if (op.Fe) {
@@ -80,10 +86,10 @@ EFB_D void scalar_warp_writeout(const ScalarOp& op, long long e0, int nvalid, co
 template <int DIM, int NPE>
 EFB_D void scalar_warp_batch(const GroupView& g, const ScalarOp& op, long long batch, const double* tab, double* ws) {
     using SW = ScalarWarp<DIM, NPE>;
-    constexpr int LPE = SW::LPE, EPW = SW::EPW, GS = SW::GS, GPS = SW::GPS;
+    constexpr int LPE = SW::LPE, EPW = SW::EPW, GS = SW::GS, GPS = SW::GPS, DPS = SW::DPS, MSS = SW::MSS;
     const int nPg = g.nPg;
     const double* dNt = tab;
-    const double* Nt = dNt + nPg * DIM * NPE;
+    const double* Nt = dNt + nPg * DPS;
     const double* wt = Nt + nPg * NPE;
     double* X = ws;
     double* wJ = ws + SW::o_wJ();
@@ -111,7 +117,7 @@ EFB_D void scalar_warp_batch(const GroupView& g, const ScalarOp& op, long long b
                 for (int r = 0; r < DIM; ++r)
                     EFB_UNROLL
                     for (int c = 0; c < DIM; ++c) {
-                        const double* row = dNt + (p * DIM + r) * NPE;
+                        const double* row = dNt + p * DPS + r * NPE;
                         double s = 0.0;
                         EFB_UNROLL
                         for (int n = 0; n < NPE; ++n) s += row[n] * Xe[n * DIM + c];
@@ -127,7 +133,7 @@ EFB_D void scalar_warp_batch(const GroupView& g, const ScalarOp& op, long long b
                         for (int d = 0; d < DIM; ++d) {
                             double s = 0.0;
                             EFB_UNROLL
-                            for (int k = 0; k < DIM; ++k) s += Fi[d * DIM + k] * dNt[(p * DIM + k) * NPE + a];
+                            for (int k = 0; k < DIM; ++k) s += Fi[d * DIM + k] * dNt[p * DPS + k * NPE + a];
                             gp[a * GS + d] = s;
                         }
                 }
@@ -180,17 +186,17 @@ EFB_D void scalar_warp_batch(const GroupView& g, const ScalarOp& op, long long b
                 if (op.has_f) fb += coef_at(op.f, op.f_mode, op.f_scalar, e, p, nPg) * w * Np[b];
             }
             EFB_UNROLL
-            for (int a = 0; a < NPE; ++a) Ms[el * NPE * NPE + a * NPE + b] = op.scale * acc[a];
+            for (int a = 0; a < NPE; ++a) Ms[el * MSS + a * NPE + b] = op.scale * acc[a];
             Fs[el * NPE + b] = op.scale * fb;
         }
     }
     // block-expanded write-out: the batch's outputs are one contiguous range (dof_n is 1, 2 or 3 in the reference: compile-time
     // divisors; any other value takes the generic loop)
     EFB_LANES(lane) {
-        if (op.dof_n == 1) scalar_warp_writeout<NPE, 1>(op, e0, nvalid, Ms, Fs, lane);
-        else if (op.dof_n == 2) scalar_warp_writeout<NPE, 2>(op, e0, nvalid, Ms, Fs, lane);
-        else if (op.dof_n == 3) scalar_warp_writeout<NPE, 3>(op, e0, nvalid, Ms, Fs, lane);
-        else scalar_warp_writeout<NPE, 0>(op, e0, nvalid, Ms, Fs, lane);
+        if (op.dof_n == 1) scalar_warp_writeout<NPE, 1, MSS>(op, e0, nvalid, Ms, Fs, lane);
+        else if (op.dof_n == 2) scalar_warp_writeout<NPE, 2, MSS>(op, e0, nvalid, Ms, Fs, lane);
+        else if (op.dof_n == 3) scalar_warp_writeout<NPE, 3, MSS>(op, e0, nvalid, Ms, Fs, lane);
+        else scalar_warp_writeout<NPE, 0, MSS>(op, e0, nvalid, Ms, Fs, lane);
     }
 }
 

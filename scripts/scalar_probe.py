@@ -13,9 +13,12 @@ from easyfea_b200 import mesh, meshgen, operators  # noqa: E402
 from easyfea_b200 import device as dv  # noqa: E402
 
 
-def timeit(fn, reps=10):
+def timeit(fn, reps=None):
+    reps = int(os.environ.get("SCALAR_PROBE_REPS", "10")) if reps is None else reps
     fn()
     torch.cuda.synchronize()
+    if reps <= 0:  # one launch per operator (ncu captures)
+        return float("nan")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
