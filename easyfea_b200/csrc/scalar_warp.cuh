@@ -25,6 +25,7 @@ struct ScalarWarp {
     static constexpr int DPS = ((DIM * NPE + 1) & ~3) + 2;
     // doubles per element in Ms: the elements of a half warp store their columns into different banks
     static constexpr int MSS = ((NPE * NPE + 15) & ~15) + LPE;
+    static_assert(DPS >= DIM * NPE && DPS % 4 == 2 && MSS >= NPE * NPE, "table strides");
     EFB_HD static int tables(int nPg) { return (nPg * DPS + nPg * NPE + nPg + 1) & ~1; }
     // per-warp scratch: X | wJ | gradients (has_k) | Ms | Fs
     EFB_HD static int o_wJ() { return EPW * NPE * DIM; }
